@@ -1,0 +1,178 @@
+"""L0 runtime: SPMD world discovery (rank / size / local device) and the comm object.
+
+The reference captures ``MPI.COMM_WORLD`` rank/size at import time
+(``/root/reference/mpi_comms.py:11-13``) and again per optimizer
+(``/root/reference/ps.py:71-73``) and is launched with ``mpirun -n N``
+(``/root/reference/Makefile:2``).  Here the world is one process per GPU started by
+``torchrun`` / :mod:`pytorch_ps_mpi_b200.launch`; rank and size come from the standard
+``RANK`` / ``WORLD_SIZE`` / ``LOCAL_RANK`` environment (or an explicit :func:`init`), and
+``torch.distributed`` (NCCL on GPUs, gloo on CPU) is used for *bootstrap plumbing only* —
+handle exchange, barriers, object slow path.  The hot paths never touch it.
+"""
+from __future__ import annotations
+
+import datetime
+import os
+import threading
+import uuid
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["World", "init", "world", "rank", "size", "is_initialized", "shutdown", "COMM_WORLD"]
+
+
+@dataclass
+class World:
+    """The process's view of the SPMD job (the ``MPI.COMM_WORLD`` analogue)."""
+
+    rank: int = 0
+    size: int = 1
+    local_rank: int = 0
+    device: torch.device = field(default_factory=lambda: torch.device("cpu"))
+    backend: Optional[str] = None          # 'nccl' | 'gloo' | None (single process)
+    job_id: str = ""
+    owns_pg: bool = False                  # we created the default process group
+    _cpu_group: Optional[object] = None    # gloo group for host objects when the default is NCCL
+
+    # mpi4py-flavoured accessors so reference-style code keeps working
+    def Get_rank(self) -> int:
+        return self.rank
+
+    def Get_size(self) -> int:
+        return self.size
+
+    # -- bootstrap helpers (slow path; never on a hot path) -----------------------------
+    @property
+    def cpu_group(self):
+        """A gloo group for host-side object exchange (handles, sizes, pickled objects)."""
+        if self.size == 1:
+            return None
+        if self.backend == "gloo":
+            return dist.group.WORLD
+        if self._cpu_group is None:
+            self._cpu_group = dist.new_group(backend="gloo")
+        return self._cpu_group
+
+    def barrier(self) -> None:
+        if self.size > 1:
+            dist.barrier(group=self.cpu_group)
+
+    def all_gather_object(self, obj):
+        if self.size == 1:
+            return [obj]
+        out = [None] * self.size
+        dist.all_gather_object(out, obj, group=self.cpu_group)
+        return out
+
+    def broadcast_object(self, obj, src: int = 0):
+        if self.size == 1:
+            return obj
+        box = [obj]
+        dist.broadcast_object_list(box, src=src, group=self.cpu_group)
+        return box[0]
+
+
+_WORLD: Optional[World] = None
+_LOCK = threading.Lock()
+
+
+def _env_int(name: str, default: int) -> int:
+    v = os.environ.get(name)
+    return int(v) if v not in (None, "") else default
+
+
+def init(backend: Optional[str] = None, device: Optional[torch.device] = None,
+         timeout_s: float = 600.0) -> World:
+    """Discover (and if needed create) the world.  Idempotent.
+
+    * If ``torch.distributed`` is already initialised, adopt it.
+    * Else if ``WORLD_SIZE`` > 1 is in the environment, create the default process group
+      (``nccl`` when CUDA is available, else ``gloo``) using the env rendezvous.
+    * Else run single-process (size 1) with no process group at all.
+    """
+    global _WORLD
+    with _LOCK:
+        if _WORLD is not None:
+            return _WORLD
+        env_size = _env_int("WORLD_SIZE", 1)
+        local_rank = _env_int("LOCAL_RANK", _env_int("RANK", 0))
+        use_cuda = torch.cuda.is_available() and (device is None or device.type == "cuda")
+        if device is None:
+            if use_cuda:
+                device = torch.device("cuda", local_rank % max(torch.cuda.device_count(), 1))
+            else:
+                device = torch.device("cpu")
+        if device.type == "cuda":
+            torch.cuda.set_device(device)
+        owns = False
+        if dist.is_available() and dist.is_initialized():
+            be = dist.get_backend()
+            w = World(dist.get_rank(), dist.get_world_size(), local_rank, device, be)
+        elif env_size > 1:
+            be = backend or ("nccl" if device.type == "cuda" else "gloo")
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29511")
+            kw = {}
+            if be == "nccl":
+                kw["device_id"] = device
+            dist.init_process_group(backend=be, timeout=datetime.timedelta(seconds=timeout_s), **kw)
+            owns = True
+            w = World(dist.get_rank(), dist.get_world_size(), local_rank, device, be)
+        else:
+            w = World(0, 1, 0, device, None)
+        w.owns_pg = owns
+        # a job-unique id every rank agrees on (names shm segments / unix sockets)
+        jid = uuid.uuid4().hex[:12] if w.rank == 0 else None
+        w.job_id = w.broadcast_object(jid, src=0) if w.size > 1 else jid
+        _WORLD = w
+        return w
+
+
+def world() -> World:
+    return _WORLD if _WORLD is not None else init()
+
+
+def is_initialized() -> bool:
+    return _WORLD is not None
+
+
+def rank() -> int:
+    return world().rank
+
+
+def size() -> int:
+    return world().size
+
+
+def shutdown() -> None:
+    """Tear down the world (destroys the process group only if :func:`init` created it)."""
+    global _WORLD
+    with _LOCK:
+        w, _WORLD = _WORLD, None
+    if w is not None and w.owns_pg and dist.is_initialized():
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+class _CommWorldProxy:
+    """``COMM_WORLD`` stand-in: resolves lazily so importing the package never blocks."""
+
+    def Get_rank(self) -> int:
+        return world().rank
+
+    def Get_size(self) -> int:
+        return world().size
+
+    def Barrier(self) -> None:
+        world().barrier()
+
+    def __getattr__(self, item):
+        return getattr(world(), item)
+
+
+COMM_WORLD = _CommWorldProxy()

@@ -1,0 +1,185 @@
+"""Worker bodies for the spawned multi-process tests (import-safe: no work at import)."""
+import os
+
+import numpy as np
+import torch
+
+
+def _world(rank, size):
+    import pytorch_ps_mpi_b200 as ps
+    w = ps.runtime.init()
+    assert (w.rank, w.size) == (rank, size)
+    return ps, w
+
+
+# --- reference test_comms.py:9-16 ------------------------------------------------------
+def gather_objects(rank, size, transport):
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    comms = ps.comms
+    obj = {"str": "str", "rank": rank, "list": [rank] * (rank + 1)}
+    msg = comms.igather(obj, name=1)
+    assert set(msg[2]) == {"pickle_time", "compress_time", "alloc_time", "igather_time", "alloc_bytes"}
+    objs = comms.irecv(msg[0], msg[1], name=1)
+    sent = [{"str": "str", "rank": r, "list": [r] * (r + 1)} for r in range(size)]
+    if rank == 0:
+        assert objs == sent
+    else:
+        assert objs is None
+    # tensors of every dtype survive (the reference cast to float32, mpi_comms.py:48)
+    t = {"w": torch.arange(6, dtype=torch.float32).view(2, 3).bfloat16() * (rank + 1),
+         "i": torch.tensor([rank], dtype=torch.int64), "np": np.full(3, rank, dtype=np.float64)}
+    r = comms.irecv(*comms.igather(t, name="t")[:2], name="t")
+    if rank == 0:
+        for k, o in enumerate(r):
+            assert o["w"].dtype == torch.bfloat16 and torch.equal(o["w"], t["w"] / (rank + 1) * (k + 1))
+            assert o["i"].item() == k and o["np"].dtype == torch.float64
+    comms.barrier()
+
+
+# --- reference test_comms.py:19-26 -----------------------------------------------------
+def bcast_objects(rank, size, transport):
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    comms = ps.comms
+    obj = {"x": "x", "list": [1]}
+    if rank == 0:
+        obj = {"a": "a", "list": [0]}
+    tmp = comms.ibroadcast(obj)
+    recv = comms.irecv1(*tmp)
+    assert recv == {"a": "a", "list": [0]}
+    big = torch.arange(3_000_000, dtype=torch.float32) if rank == 0 else None   # > ring size: chunked
+    got = comms.irecv1(*comms.ibroadcast(big))
+    assert torch.equal(got, torch.arange(3_000_000, dtype=torch.float32))
+    comms.barrier()
+
+
+# --- reference test_iallgather.py:37-54 + test_mpi.py:34-96 ------------------------------
+def iallgather_objects(rank, size, transport):
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    comms = ps.comms
+
+    def make(r):
+        return {"rank": r, "list": [r] * (r + 1)}
+
+    ia = comms.Iallgather()
+    msgs = [comms.format_for_send(make(rank))[0], comms.format_for_send({"a": "a", "async": [rank] * (rank + 1)})[0]]
+    sizes = ia.prepare([len(m) for m in msgs])
+    resp = []
+    for (req, count), m in zip(sizes, msgs):
+        req.Wait()
+        assert int(count[rank]) == len(m) and len(count) == size
+        resp.append(ia.send(m, count))
+    jar = ia.recv(*resp[0])
+    assert jar == [make(r) for r in range(size)]
+    jar2 = ia.recv(*resp[1])
+    assert jar2 == [{"a": "a", "async": [r] * (r + 1)} for r in range(size)]
+    comms.barrier()
+
+
+def p2p_any_source(rank, size, transport):
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    comms = ps.comms
+    if rank == 0:
+        seen = set()
+        for _ in range(size - 1):
+            req = comms.irecv_obj(src=comms.ANY_SOURCE, tag=3)
+            m = req.Wait()
+            assert m["rank"] == req.source
+            seen.add(req.source)
+        assert seen == set(range(1, size))
+    else:
+        comms.isend_obj({"rank": rank, "t": torch.ones(rank)}, dst=0, tag=3).Wait()
+    comms.barrier()
+
+
+# --- BASELINE config 1: 2-layer MLP, MNIST-shaped synthetic, world_size 2 -------------------
+def _mlp_data(rank, step, batch=16):
+    g = torch.Generator().manual_seed(1000 * step + rank)
+    return torch.randn(batch, 1, 28, 28, generator=g), torch.randint(0, 10, (batch,), generator=g)
+
+
+def _oracle_sum_sgd(size, steps, optim, hyper, coding_factory):
+    """Single-process oracle: sum of every rank's (coded) gradient → torch.optim step."""
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=32)
+    opt = (torch.optim.SGD if optim == "sgd" else torch.optim.Adam)(model.parameters(), **hyper)
+    for s in range(steps):
+        total = [torch.zeros_like(p) for p in model.parameters()]
+        for r in range(size):
+            code = coding_factory()
+            x, y = _mlp_data(r, s)
+            model.zero_grad()
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            for t, p in zip(total, model.parameters()):
+                t += code.decode(code.encode(p.grad)).reshape(p.shape).to(t.dtype)
+        for t, p in zip(total, model.parameters()):
+            p.grad = t
+        opt.step()
+    return [p.detach().clone() for p in model.parameters()]
+
+
+def mlp_train(rank, size, mode, optim, coding, transport):
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    factory = {"identity": ps.Identity, "cast": lambda: ps.Cast("bf16"), "scale": lambda: ps.Scale("int8"),
+               "topk": lambda: ps.TopK(ratio=0.25)}[coding]
+    hyper = {"lr": 0.05, "momentum": 0.9, "weight_decay": 1e-4} if optim == "sgd" else {"lr": 1e-2, "eps": 1e-12}
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=32)
+    cls = ps.SGD if optim == "sgd" else ps.Adam
+    opt = cls(model.named_parameters(), model.parameters(), code=factory(), mode=mode, **hyper)
+    steps = 3
+    for s in range(steps):
+        x, y = _mlp_data(rank, s)
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss.backward()
+        out = opt.step()
+        assert isinstance(out, tuple) and len(out) == 2
+        data = out[1]
+        for k in ("comm_wait", "optim_step_time", "decode_time", "msg_bytes", "packaged_bytes", "code_wait",
+                  "iallgather_prepare_time", "isend_time"):
+            assert k in data, k
+    assert opt.steps == steps and opt.rank == rank and opt.size == size
+    want = _oracle_sum_sgd(size, steps, optim, hyper, factory)
+    tol = 1e-5 if optim == "sgd" else 2e-4     # reference Adam: sqrt(v)+eps  vs torch: sqrt(v/bc2)+eps
+    for p, q in zip(model.parameters(), want):
+        assert torch.allclose(p, q, rtol=tol, atol=tol), (mode, optim, coding, (p - q).abs().max())
+    # every rank ends with identical parameters
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    allp = w.all_gather_object(flat)
+    for f in allp:
+        assert torch.equal(f, allp[0])
+    opt.close()
+
+
+def mlp_async(rank, size, transport):
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=32)
+    opt = ps.SGD(model.named_parameters(), model.parameters(), lr=0.05, code=ps.Identity(), mode="async", quota=1)
+    before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    if rank == 0:
+        n = opt.serve()
+        assert n == 4 * (size - 1)          # quota 1: one update per gradient message
+        st = [d.get("staleness", [0]) for d in opt.timings if d.get("staleness")]
+        assert all(s[0] >= 0 for s in st)
+    else:
+        import time
+        for s in range(4):
+            x, y = _mlp_data(rank, s)
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            opt.step()
+            time.sleep(0.01 * rank)          # injected delay → staleness
+    opt.close()
+    after = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    if rank == 0:
+        assert not torch.equal(before, after)

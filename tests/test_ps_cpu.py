@@ -1,0 +1,30 @@
+"""BASELINE config 1: 2-layer MLP on MNIST-shaped synthetic data, world_size 2, CPU plumbing.
+
+Every mode is checked against a single-process oracle (sum of all ranks' coded gradients →
+``torch.optim``), and all ranks must end bit-identical.
+"""
+import pytest
+
+from pytorch_ps_mpi_b200.launch import spawn
+from tests import _mp
+
+
+@pytest.mark.parametrize("mode,optim,coding,transport", [
+    ("ps", "sgd", "identity", "shm"),
+    ("ps", "adam", "cast", "shm"),
+    ("ps", "sgd", "topk", "gloo"),
+    ("allgather", "sgd", "identity", "shm"),
+    ("allgather", "adam", "scale", "gloo"),
+    ("allgather", "sgd", "topk", "shm"),
+])
+def test_mlp_sync(mode, optim, coding, transport):
+    spawn(_mp.mlp_train, 2, (mode, optim, coding, transport))
+
+
+def test_mlp_sync_three_ranks():
+    spawn(_mp.mlp_train, 3, ("ps", "sgd", "identity", "shm"))
+
+
+@pytest.mark.parametrize("transport", ["shm", "gloo"])
+def test_mlp_async(transport):
+    spawn(_mp.mlp_async, 3, (transport,))
