@@ -1,0 +1,255 @@
+#!/usr/bin/env python
+"""Headline benchmark: ResNet-18 synchronous parameter-server SGD, samples/sec on N B200s.
+
+``python bench.py --gpus N --steps K --warmup W`` (N > 1 under ``torch.distributed.run``).
+Metric / config are BASELINE.json's: "samples/sec (whole box, device-timed, max over ranks) for
+ResNet-18 PS-SGD", bf16, synthetic ImageNet-shaped data, random-init weights, weak scaling
+(fixed per-GPU batch).  One JSON line on rank 0.
+
+Arms
+----
+``--impl ours`` (default)  this framework: ``pytorch_ps_mpi_b200.SGD`` (device engine).
+``--impl reference``       the unmodified reference from ``baseline/_ref`` — it cannot be installed
+                           (no setup.py/pyproject; mpi4py/blosc/codings missing; ``mpi_comms.py:50``
+                           is a SyntaxError on py3.12) → prints ``{"impl": "reference",
+                           "unavailable": ...}`` and exits 0.
+``--impl comparator``      labelled reference-EQUIVALENT algorithm (host-staged pickle all-gather +
+                           eager per-parameter optimizer ops, ``baseline/comparator.py``) for our own
+                           tables; never reported as the reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "comparator"])
+    ap.add_argument("--model", default="resnet18", choices=["resnet18", "resnet50", "mlp", "bert_base"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--mode", default="ps", choices=["ps", "allgather", "async"])
+    ap.add_argument("--code", default="identity")
+    ap.add_argument("--optim", default="sgd", choices=["sgd", "adam"])
+    ap.add_argument("--seq", type=int, default=128, help="sequence length (bert_base)")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def reference_unavailable():
+    why = ("reference is not installable: /root/reference has no setup.py/pyproject.toml (pip: 'not installable'), "
+           "its deps mpi4py/blosc/toolz/distributed/codings are absent offline, and mpi_comms.py:50 "
+           "(d.cuda(async=True)) is a SyntaxError on Python 3.12")
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+    return 0
+
+
+def make_code(ps, name):
+    name = name.lower()
+    if name == "identity":
+        return ps.Identity()
+    if name.startswith("cast"):
+        return ps.Cast(name.split(":")[1] if ":" in name else "bf16")
+    if name.startswith("scale"):
+        return ps.Scale(name.split(":")[1] if ":" in name else "int8")
+    if name.startswith("topk"):
+        return ps.TopK(ratio=float(name.split(":")[1]) if ":" in name else 0.01, values="bf16")
+    raise ValueError(name)
+
+
+def build(args, device, ps):
+    from pytorch_ps_mpi_b200 import models
+    torch.manual_seed(0)
+    if args.model in ("resnet18", "resnet50"):
+        model = models.build(args.model).to(device).to(memory_format=torch.channels_last).bfloat16()
+        shape, in_dtype = (args.batch, 3, 224, 224), torch.uint8
+
+        def make_batch(gen):
+            x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=gen)
+            y = torch.randint(0, 1000, (args.batch,), generator=gen)
+            return x, y
+
+        mean = torch.tensor([0.485, 0.456, 0.406], device=device).view(1, 3, 1, 1) * 255
+        std = torch.tensor([0.229, 0.224, 0.225], device=device).view(1, 3, 1, 1) * 255
+
+        def loss_fn(x, y):
+            xb = ((x.float() - mean) / std).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            return torch.nn.functional.cross_entropy(model(xb).float(), y)
+        cfg = {"global_batch": None, "image": "3x224x224 uint8"}
+    elif args.model == "mlp":
+        model = models.mnist_mlp().to(device)
+
+        def make_batch(gen):
+            return torch.randn(args.batch, 1, 28, 28, generator=gen), torch.randint(0, 10, (args.batch,), generator=gen)
+
+        def loss_fn(x, y):
+            return torch.nn.functional.cross_entropy(model(x), y)
+        cfg = {}
+    else:
+        model = models.bert_base().to(device).bfloat16()
+        S = args.seq
+
+        def make_batch(gen):
+            ids = torch.randint(0, 30522, (args.batch, S), generator=gen)
+            lab = torch.where(torch.rand(args.batch, S, generator=gen) < 0.15, ids, torch.full_like(ids, -100))
+            return ids, lab
+
+        def loss_fn(x, y):
+            return model(x, mlm_labels=y, nsp_labels=None)
+        cfg = {"seq_len": S}
+    return model, make_batch, loss_fn, cfg
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_unavailable()
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device", "impl": args.impl}))
+        return 1
+    import pytorch_ps_mpi_b200 as ps
+    from pytorch_ps_mpi_b200.utils import ClockSampler
+    import torch.distributed as dist
+
+    w = ps.runtime.init()
+    assert w.size == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={w.size}"
+    device = w.device
+    torch.backends.cudnn.benchmark = True
+    model, make_batch, loss_fn, cfg = build(args, device, ps)
+
+    if args.impl == "comparator":
+        from baseline.comparator import ComparatorSGD
+        opt = ComparatorSGD(model.named_parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    else:
+        named = list(model.named_parameters())
+        hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-4) if args.optim == "sgd" else dict(lr=1e-4, weight_decay=0.01)
+        cls = ps.SGD if args.optim == "sgd" else ps.Adam
+        opt = cls(named, [p for _, p in named], code=make_code(ps, args.code), mode=args.mode, engine="device",
+                  average=True, **hyper)
+    eng = getattr(opt, "_engine", None)
+
+    # distinct batches so no step re-reads a cached input; pinned host copies for the e2e arm
+    gen = torch.Generator().manual_seed(1234 + w.rank)
+    nbuf = 4
+    host = [tuple(t.pin_memory() for t in make_batch(gen)) for _ in range(nbuf)]
+    dev = [tuple(t.to(device) for t in hb) for hb in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def train_step(x, y):
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(x, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier_sync():
+        torch.cuda.synchronize(device)
+        w.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(run_steps, fn):
+        barrier_sync()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn(run_steps)
+        e.record()
+        torch.cuda.synchronize(device)
+        ms = s.elapsed_time(e)
+        w.barrier()
+        t = torch.tensor([ms], dtype=torch.float64)
+        if w.size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=w.cpu_group)
+        return float(t.item())
+
+    # ---- arm 1: device-resident inputs (kernel/step time) ----
+    def loop_device(n):
+        for i in range(n):
+            x, y = dev[i % nbuf]
+            train_step(x, y)
+
+    loop_device(max(args.warmup, 3))
+    launches0 = eng.launches if eng is not None else 0
+    with ClockSampler(device.index or 0) as clk:
+        ms = timed(args.steps, loop_device)
+    launches = (eng.launches - launches0) if eng is not None else 0
+    clocks = clk.summary()
+    global_batch = args.batch * w.size
+    value = global_batch * args.steps / (ms / 1e3)
+
+    # ---- arm 2: end to end through the public API: H2D of the step's inputs (pinned) + D2H of the loss ----
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream(device=device)
+        loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+        def loop_e2e(n):
+            cur = torch.cuda.current_stream(device)
+            nxt = None
+            with torch.cuda.stream(copy_stream):
+                nxt = tuple(t.to(device, non_blocking=True) for t in host[0])
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            for i in range(n):
+                cur.wait_event(ev)
+                x, y = nxt
+                if i + 1 < n:                       # prefetch the next step's inputs while this one computes
+                    with torch.cuda.stream(copy_stream):
+                        nxt = tuple(t.to(device, non_blocking=True) for t in host[(i + 1) % nbuf])
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                loss = train_step(x, y)
+                for t in (x, y):
+                    t.record_stream(cur)
+                loss_host.copy_(loss.detach().float(), non_blocking=True)      # D2H read of the step's result
+            cur.synchronize()
+
+        loop_e2e(3)
+        ms_e2e = timed(args.steps, loop_e2e)
+        e2e = {"value": global_batch * args.steps / (ms_e2e / 1e3), "unit": "samples/sec",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+               "last_loss": float(loss_host.item())}
+
+    if eng is not None:
+        eng.check()
+    if w.rank == 0:
+        out = {
+            "metric": "samples/sec (whole box, device-timed, max over ranks), ResNet-18 PS-SGD" if args.model == "resnet18"
+                      else f"samples/sec (whole box, device-timed, max over ranks), {args.model} PS-{args.optim.upper()}",
+            "value": value, "unit": "samples/sec", "n_gpus": w.size, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.model != "mlp" else "fp32", "data": "synthetic (random images/labels, random-init weights)",
+            "impl": args.impl,
+            "config": {"model": args.model, "global_batch": global_batch, "per_gpu_batch": args.batch,
+                       "seq_len": cfg.get("seq_len"), "parallelism": f"dp{w.size} (rank-0 parameter server, mode={args.mode})",
+                       "optimizer": args.optim, "coding": args.code, "memory_format": "channels_last",
+                       "l2": "inputs larger than L2: 4 rotating input batches; per-step activations+weights >> 126 MB, no explicit flush",
+                       "symmetric_memory": getattr(getattr(eng, "arena", None), "provider", None),
+                       "multicast": bool(getattr(getattr(eng, "arena", None), "has_multicast", False)),
+                       "bcast": {0: "local", 1: "unicast-p2p", 2: "multimem.st"}.get(getattr(eng, "bcast", -1)),
+                       "reduce": {0: "p2p rank-ordered", 1: "multimem.ld_reduce"}.get(getattr(eng, "reduce", -1))},
+            "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
+                       "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0)},
+            "e2e": e2e, "gpu_launches": launches,
+        }
+        print(json.dumps(out))
+    w.barrier()
+    if hasattr(opt, "close"):
+        opt.close()
+    ps.runtime.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,225 @@
+// Python bindings of the CUDA extension (_psb200_cuda): symmetric memory, kernel launchers.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/extension.h>
+
+#include <cstring>
+#include <memory>
+
+#include "kernels.h"
+#include "symm_mem.h"
+
+namespace py = pybind11;
+
+namespace {
+
+void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+cudaStream_t cur_stream() { return c10::cuda::getCurrentCUDAStream().stream(); }
+
+int dt_code(at::ScalarType t) {
+  switch (t) {
+    case at::kFloat: return DT_F32;
+    case at::kBFloat16: return DT_BF16;
+    case at::kHalf: return DT_F16;
+    default: throw std::runtime_error("unsupported dtype (need float32 / bfloat16 / float16)");
+  }
+}
+
+// A tensor view over raw (VMM-mapped) device memory; `owner` keeps the mapping alive.
+at::Tensor blob_tensor(uint64_t ptr, std::vector<int64_t> shape, at::ScalarType dtype, int device, py::object owner) {
+  auto keep = std::make_shared<py::object>(std::move(owner));
+  auto deleter = [keep](void*) mutable {
+    py::gil_scoped_acquire g;
+    keep.reset();
+  };
+  auto opts = at::TensorOptions().dtype(dtype).device(at::kCUDA, device);
+  return at::from_blob(reinterpret_cast<void*>(ptr), shape, deleter, opts);
+}
+
+// Static part of the fused PS launch (pointers never change after the arenas are built).
+struct UpdatePlan {
+  UpdateArgs a{};
+  int kind = 0, wire = 0, opt = 0, grid = 0;
+
+  void set_rank_ptrs(int r, uint64_t wire_p, uint64_t scales_p, uint64_t param_p, uint64_t signal_p) {
+    if (r < 0 || r >= PSB_MAX_RANKS) throw std::runtime_error("rank out of range");
+    a.wire[r] = reinterpret_cast<const void*>(wire_p);
+    a.scales[r] = reinterpret_cast<const float*>(scales_p);
+    a.param_dst[r] = reinterpret_cast<void*>(param_p);
+    a.signal_peer[r] = reinterpret_cast<uint64_t*>(signal_p);
+  }
+
+  void launch(uint64_t epoch, const std::vector<std::vector<double>>& groups, uint32_t contrib_mask, double inv_count,
+              int wait_grads, int signal_mode, uint32_t ack_mask, uint64_t version, uint64_t select_out,
+              int average_dynamic, uint64_t active_ptr, double timeout_s) {
+    if (groups.size() > PSB_MAX_GROUPS) throw std::runtime_error("too many param groups for one launch");
+    for (size_t i = 0; i < groups.size(); ++i) {
+      const auto& g = groups[i];
+      if (g.size() != 11) throw std::runtime_error("group hyper tuple must have 11 entries");
+      GroupHyper& h = a.groups[i];
+      h.lr = (float)g[0], h.weight_decay = (float)g[1], h.momentum = (float)g[2], h.dampening = (float)g[3];
+      h.beta1 = (float)g[4], h.beta2 = (float)g[5], h.eps = (float)g[6], h.step_size = (float)g[7];
+      h.nesterov = (int)g[8], h.amsgrad = (int)g[9], h.first_step = (int)g[10], h.pad = 0;
+    }
+    a.epoch = epoch;
+    a.contrib_mask = contrib_mask;
+    a.inv_count = (float)inv_count;
+    a.wait_grads = wait_grads;
+    a.signal_mode = signal_mode;
+    a.ack_mask = ack_mask;
+    a.version = version;
+    a.select_out = reinterpret_cast<const uint64_t*>(select_out);
+    a.average_dynamic = average_dynamic;
+    a.active = reinterpret_cast<const uint8_t*>(active_ptr);
+    a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    psb_launch_update(cur_stream(), kind, wire, opt, a, grid);
+    check_launch("psb_update_kernel launch");
+  }
+};
+
+void encode(int kind, int wire, const std::vector<at::Tensor>& grads, const std::vector<int>& first_tile,
+            const std::vector<int>& ntiles, const std::vector<int>& param_idx, uint64_t tiles_ptr, uint64_t wire_ptr,
+            uint64_t scales_ptr, uint64_t amax_ptr, uint64_t residual_ptr, int bytes_per_tile, int cap, double ratio) {
+  const size_t n = grads.size();
+  if (first_tile.size() != n || ntiles.size() != n || param_idx.size() != n) throw std::runtime_error("encode: length mismatch");
+  if (n == 0) return;
+  cudaStream_t s = cur_stream();
+  EncodeArgs a{};
+  a.tiles = reinterpret_cast<const TileInfo*>(tiles_ptr);
+  a.wire = reinterpret_cast<void*>(wire_ptr);
+  a.scales = reinterpret_cast<float*>(scales_ptr);
+  a.amax_bits = reinterpret_cast<uint32_t*>(amax_ptr);
+  a.residual = reinterpret_cast<float*>(residual_ptr);
+  a.bytes_per_tile = bytes_per_tile;
+  a.cap = cap;
+  a.ratio = ratio;
+  a.grad_dt = dt_code(grads[0].scalar_type());
+  for (size_t base = 0; base < n; base += PSB_ENCODE_MAX) {
+    const int m = (int)std::min<size_t>(PSB_ENCODE_MAX, n - base);
+    a.batch.n = m;
+    a.batch.cum[0] = 0;
+    for (int i = 0; i < m; ++i) {
+      const at::Tensor& g = grads[base + i];
+      if (!g.is_cuda() || !g.is_non_overlapping_and_dense()) throw std::runtime_error("encode: gradients must be dense CUDA tensors");
+      if (dt_code(g.scalar_type()) != a.grad_dt) throw std::runtime_error("encode: mixed gradient dtypes in one bucket");
+      if (reinterpret_cast<uintptr_t>(g.data_ptr()) % 16 != 0) throw std::runtime_error("encode: gradient not 16-byte aligned");
+      a.batch.src[i] = g.data_ptr();
+      a.batch.first_tile[i] = first_tile[base + i];
+      a.batch.param[i] = param_idx[base + i];
+      a.batch.cum[i + 1] = a.batch.cum[i] + ntiles[base + i];
+    }
+    if (kind == KIND_SCALED) {
+      psb_launch_absmax(s, a);
+      check_launch("psb_absmax_kernel launch");
+    }
+    psb_launch_encode(s, kind, wire, a);
+    check_launch("psb_encode_kernel launch");
+  }
+}
+
+void signal(const std::vector<uint64_t>& targets, int slot, uint64_t value, int extra_slot, uint64_t extra_value) {
+  std::vector<uint64_t*> t;
+  for (auto p : targets) t.push_back(reinterpret_cast<uint64_t*>(p));
+  psb_launch_signal(cur_stream(), t.data(), (int)t.size(), slot, value,
+                    extra_slot >= 0 ? reinterpret_cast<uint64_t*>(1) : nullptr, extra_slot < 0 ? 0 : extra_slot, extra_value);
+  check_launch("psb_signal_kernel launch");
+}
+
+void wait_flags(uint64_t signal_local, int slot0, uint32_t mask, uint64_t want, double timeout_s) {
+  psb_launch_wait(cur_stream(), reinterpret_cast<const uint64_t*>(signal_local), slot0, mask, want,
+                  (unsigned long long)(timeout_s * 1e9));
+  check_launch("psb_wait_kernel launch");
+}
+
+void select_ready(uint64_t signal_local, uint64_t consumed, uint32_t cand_mask, int quota, uint64_t out, double timeout_s) {
+  psb_launch_select(cur_stream(), reinterpret_cast<const uint64_t*>(signal_local), reinterpret_cast<uint64_t*>(consumed),
+                    cand_mask, quota, reinterpret_cast<uint64_t*>(out), (unsigned long long)(timeout_s * 1e9));
+  check_launch("psb_select_kernel launch");
+}
+
+}  // namespace
+
+void bind_gemm(py::module_& m);   // gemm_bindings.cpp
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "pytorch_ps_mpi_b200 CUDA runtime: VMM symmetric memory + sm_100a kernels";
+  m.attr("TILE") = PSB_TILE;
+  m.attr("SIGNAL_SLOTS") = PSB_SIGNAL_SLOTS;
+  m.attr("SIG_GRAD_READY") = SIG_GRAD_READY;
+  m.attr("SIG_PARAMS_READY") = SIG_PARAMS_READY;
+  m.attr("SIG_CONSUMED") = SIG_CONSUMED;
+  m.attr("SIG_ERROR") = SIG_ERROR;
+  m.attr("SIG_VERSION") = SIG_VERSION;
+  m.attr("SIG_ACK") = SIG_ACK;
+  m.attr("SIG_GRAD_VERSION") = SIG_GRAD_VERSION;
+  m.attr("MAX_RANKS") = PSB_MAX_RANKS;
+  m.attr("MAX_GROUPS") = PSB_MAX_GROUPS;
+
+  py::class_<psb::SymmBlock, std::shared_ptr<psb::SymmBlock>>(m, "SymmBlock")
+      .def(py::init<int, int, int, size_t, const std::string&>(), py::arg("rank"), py::arg("world"), py::arg("device"),
+           py::arg("bytes"), py::arg("sock_prefix"), py::call_guard<py::gil_scoped_release>())
+      .def("map_peers", &psb::SymmBlock::map_peers, py::call_guard<py::gil_scoped_release>())
+      .def("mc_supported", &psb::SymmBlock::mc_supported)
+      .def("mc_create", &psb::SymmBlock::mc_create)
+      .def("mc_import", &psb::SymmBlock::mc_import, py::call_guard<py::gil_scoped_release>())
+      .def("mc_add_device", &psb::SymmBlock::mc_add_device)
+      .def("mc_bind_and_map", &psb::SymmBlock::mc_bind_and_map)
+      .def("stop_server", &psb::SymmBlock::stop_server, py::call_guard<py::gil_scoped_release>())
+      .def_property_readonly("size", &psb::SymmBlock::size)
+      .def_property_readonly("rank", &psb::SymmBlock::rank)
+      .def_property_readonly("world", &psb::SymmBlock::world)
+      .def_property_readonly("device", &psb::SymmBlock::device)
+      .def_property_readonly("ptrs", &psb::SymmBlock::ptrs)
+      .def_property_readonly("mc_ptr", &psb::SymmBlock::mc_ptr)
+      .def_property_readonly("last_error", &psb::SymmBlock::last_error)
+      .def("ptr", &psb::SymmBlock::ptr);
+
+  m.def("blob_tensor",
+        [](uint64_t ptr, int64_t nbytes, int device, py::object owner) {
+          return blob_tensor(ptr, {nbytes}, at::kByte, device, std::move(owner));
+        },
+        "uint8 tensor view over raw device memory (owner is kept alive by the tensor); .view(dtype) it in Python");
+
+  py::class_<UpdatePlan>(m, "UpdatePlan")
+      .def(py::init<>())
+      .def_readwrite("kind", &UpdatePlan::kind)
+      .def_readwrite("wire", &UpdatePlan::wire)
+      .def_readwrite("opt", &UpdatePlan::opt)
+      .def_readwrite("grid", &UpdatePlan::grid)
+      .def("set_rank_ptrs", &UpdatePlan::set_rank_ptrs)
+      .def("configure",
+           [](UpdatePlan& p, int world, int rank, int ntiles, int bytes_per_tile, int cap, int param_dt, int bcast, int reduce,
+              uint64_t param_mc, uint64_t wire_mc, uint64_t param_local, uint64_t master, uint64_t buf0, uint64_t buf1,
+              uint64_t buf2, uint64_t tiles, uint64_t signal_local, uint64_t done_counter, uint64_t stats) {
+             p.a.world = world, p.a.rank = rank, p.a.ntiles = ntiles, p.a.bytes_per_tile = bytes_per_tile, p.a.cap = cap;
+             p.a.param_dt = param_dt, p.a.bcast = bcast, p.a.reduce = reduce;
+             p.a.param_mc = reinterpret_cast<void*>(param_mc);
+             p.a.wire_mc = reinterpret_cast<const void*>(wire_mc);
+             p.a.param_local = reinterpret_cast<void*>(param_local);
+             p.a.master = reinterpret_cast<float*>(master);
+             p.a.buf0 = reinterpret_cast<float*>(buf0);
+             p.a.buf1 = reinterpret_cast<float*>(buf1);
+             p.a.buf2 = reinterpret_cast<float*>(buf2);
+             p.a.tiles = reinterpret_cast<const TileInfo*>(tiles);
+             p.a.signal_local = reinterpret_cast<uint64_t*>(signal_local);
+             p.a.done_counter = reinterpret_cast<unsigned int*>(done_counter);
+             p.a.stats = reinterpret_cast<uint32_t*>(stats);
+           })
+      .def("launch", &UpdatePlan::launch, py::arg("epoch"), py::arg("groups"), py::arg("contrib_mask"),
+           py::arg("inv_count"), py::arg("wait_grads"), py::arg("signal_mode"), py::arg("ack_mask") = 0,
+           py::arg("version") = 0, py::arg("select_out") = 0, py::arg("average_dynamic") = 0, py::arg("active_ptr") = 0,
+           py::arg("timeout_s") = 30.0);
+
+  m.def("update_max_grid", &psb_update_max_grid);
+  m.def("encode", &encode);
+  m.def("signal", &signal, py::arg("targets"), py::arg("slot"), py::arg("value"), py::arg("extra_slot") = -1,
+        py::arg("extra_value") = 0);
+  m.def("wait_flags", &wait_flags);
+  m.def("select_ready", &select_ready);
+  bind_gemm(m);
+}

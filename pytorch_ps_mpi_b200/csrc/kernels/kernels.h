@@ -1,0 +1,89 @@
+// Host-callable launchers of the sm_100a kernels (plain C++ types; no torch headers here).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+#define PSB_ENCODE_MAX 64
+
+// One launch encodes up to PSB_ENCODE_MAX gradient tensors (a "bucket" of hook firings).
+struct EncodeBatch {
+  const void* src[PSB_ENCODE_MAX];     // gradient tensors (contiguous, 16-byte aligned)
+  int32_t first_tile[PSB_ENCODE_MAX];  // first arena tile of each
+  int32_t cum[PSB_ENCODE_MAX + 1];     // prefix sum of tile counts
+  int32_t param[PSB_ENCODE_MAX];       // parameter index of each
+  int32_t n;
+};
+
+struct EncodeArgs {
+  EncodeBatch batch;
+  const TileInfo* tiles;
+  void* wire;            // local wire arena
+  float* scales;         // local per-parameter scale table (KIND_SCALED)
+  uint32_t* amax_bits;   // per-parameter abs-max scratch (float bits, atomicMax)
+  float* residual;       // error-feedback residual (flat fp32) or nullptr
+  int32_t bytes_per_tile;
+  int32_t cap;           // top-k entries per tile
+  double ratio;
+  int32_t grad_dt;
+};
+
+struct UpdateArgs {
+  const void* wire[PSB_MAX_RANKS];     // every rank's wire arena as mapped in THIS process
+  const float* scales[PSB_MAX_RANKS];  // every rank's scale table
+  void* param_dst[PSB_MAX_RANKS];      // every rank's parameter arena (unicast publication)
+  void* param_mc;                      // multicast alias of the parameter arena (NVLS) or nullptr
+  const void* wire_mc;                 // multicast alias of the wire arena (NVLS reduce) or nullptr
+  void* param_local;                   // this rank's parameter arena
+  float* master;                       // fp32 master weights (nullptr → parameters are the master)
+  float* buf0;                         // momentum_buffer / exp_avg
+  float* buf1;                         // exp_avg_sq
+  float* buf2;                         // max_exp_avg_sq
+  const TileInfo* tiles;
+  const uint8_t* active;               // per-parameter "got a gradient this step" (nullptr = all)
+  uint64_t* signal_local;
+  uint64_t* signal_peer[PSB_MAX_RANKS];
+  unsigned int* done_counter;          // zero before launch; the kernel leaves it zero
+  uint32_t* stats;                     // [0]=tiles processed (debug / tests), may be nullptr
+  GroupHyper groups[PSB_MAX_GROUPS];
+  int32_t world, rank, ntiles, bytes_per_tile, cap;
+  int32_t param_dt, bcast, reduce;
+  uint32_t contrib_mask;               // ranks whose gradient is summed
+  float inv_count;                     // 1 or 1/#contributors (average=True)
+  uint64_t epoch;
+  int32_t wait_grads;                  // spin on SIG_GRAD_READY of every contributor first
+  int32_t signal_mode;                 // 0 none | 1 SIG_PARAMS_READY → all | 2 SIG_CONSUMED[rank] → all
+  uint32_t ack_mask;                   // async: ranks to acknowledge (SIG_ACK) when done
+  uint64_t version;                    // async: value published to SIG_VERSION
+  const uint64_t* select_out;          // async: device-side {mask, count, epochs…} from psb_select_kernel (or nullptr)
+  int32_t average_dynamic;             // async: divide by the selected count
+  unsigned long long timeout_ns;
+};
+
+void psb_launch_absmax(cudaStream_t s, const EncodeArgs& a);
+void psb_launch_encode(cudaStream_t s, int kind, int wire, const EncodeArgs& a);
+void psb_launch_update(cudaStream_t s, int kind, int wire, int opt, const UpdateArgs& a, int grid);
+void psb_launch_signal(cudaStream_t s, uint64_t* const* targets, int ntargets, int slot, uint64_t value,
+                       uint64_t* extra_slot_base, int extra_slot, uint64_t extra_value);
+void psb_launch_wait(cudaStream_t s, const uint64_t* signal_local, int slot0, uint32_t mask, uint64_t want,
+                     unsigned long long timeout_ns);
+// async PS: block until >= quota workers of `cand_mask` have SIG_GRAD_READY > consumed[r]; writes the
+// chosen mask + their epochs to `out` (out[0]=mask, out[1]=count, out[2+r]=epoch of rank r)
+void psb_launch_select(cudaStream_t s, const uint64_t* signal_local, uint64_t* consumed, uint32_t cand_mask,
+                       int quota, uint64_t* out, unsigned long long timeout_ns);
+int psb_update_max_grid(int kind, int wire, int opt);
+
+// bcast_gemm.cu — tcgen05 / TMEM / TMA GEMM whose weight tiles are gated on the PS broadcast epoch
+struct BcastGemmArgs {
+  const void* tmap_a;   // CUtensorMap* (host memory, passed as __grid_constant__ by value in launcher)
+  const void* tmap_b;
+  const void* tmap_c;
+  const float* bias;    // nullable
+  const uint64_t* ready_flag;   // nullable: SIG_PARAMS_READY slot to acquire before the first weight TMA
+  uint64_t ready_epoch;
+  int32_t M, N, K;
+  int32_t relu;
+  unsigned long long timeout_ns;
+};
+void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms);

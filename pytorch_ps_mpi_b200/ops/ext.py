@@ -30,7 +30,7 @@ HOST_SO = PKG / f"_psb200_host{SUFFIX}"
 CUDA_SO = PKG / f"_psb200_cuda{SUFFIX}"
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 _lock = threading.Lock()
@@ -97,7 +97,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     cus = cuda_sources()
     headers = list((CSRC / "kernels").glob("*.cuh")) + list((CSRC / "kernels").glob("*.h")) + \
         list((CSRC / "runtime").glob("*.h"))
-    cpps = [CSRC / "runtime" / "symm_mem.cpp", CSRC / "bindings.cpp"]
+    cpps = [CSRC / "runtime" / "symm_mem.cpp", CSRC / "bindings.cpp", CSRC / "gemm_bindings.cpp"]
     all_src = cus + cpps + headers
     if not force and _newer(CUDA_SO, all_src):
         return CUDA_SO

@@ -1,0 +1,502 @@
+"""Device engine: the B200 hot path behind ``MPI_PS.step()``.
+
+Per step, per rank (nothing on this path touches the host after the launches are queued, and
+nothing goes through NCCL/MPI):
+
+1. **backward hooks** (``ps.py:65-66,98-101`` in the reference: encode on a thread pool) collect
+   gradients into buckets; each full bucket is encoded by ONE ``psb_encode_kernel`` launch on a
+   side stream straight into this rank's *symmetric wire arena* (cast / abs-max scale /
+   block-wise top-k), overlapping with the rest of backward;
+2. ``step()`` raises this rank's ``GRAD_READY`` epoch flag (``st.release.sys`` into the server's
+   signal pad — the ``Igatherv`` post of ``mpi_comms.py:88``);
+3. the server (rank 0 in ``mode='ps'``; every rank in ``mode='allgather'``) launches
+   ``psb_update_kernel`` once: wait flags → pull every rank's wire tiles over NVLink (or one
+   ``multimem.ld_reduce`` through the switch) → decode + rank-ordered fp32 sum → SGD/Adam on fp32
+   master state → publish the new parameter tiles into every rank's *symmetric parameter
+   arena* (``multimem.st`` or peer stores) → raise ``PARAMS_READY``;
+4. workers queue a one-thread wait kernel on their compute stream (the ``req.Wait()`` of
+   ``mpi_comms.py:121``); the model's parameters ARE views of the parameter arena, so the next
+   forward reads the fresh weights with no copy.
+
+``mode='async'`` (AsySG-InCon, ``README.md:56-81``): rank 0 is a dedicated server; a device-side
+``select`` kernel waits until ``quota`` workers (ANY source) have posted a gradient, the update
+kernel sums exactly those, publishes parameters + version and acknowledges the contributors;
+workers never wait for parameters (inconsistent reads) — only for the ack of their previous
+gradient before overwriting their wire arena.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import runtime
+from ..codings import KIND_DENSE, KIND_SCALED, KIND_TOPK, TILE, WIRE_BF16, WIRE_F16, WIRE_F32, wire_code_of
+from ..ops import ext
+from .layout import FlatLayout
+from .symmetric import SymmetricArena
+
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_DONE_EPOCH = 1 << 62
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+class DeviceEngine:
+    def __init__(self, opt, master_fp32: bool = True, reduce: str = "auto"):
+        self.opt = opt
+        self.m = ext.cuda()
+        self.world = runtime.world()
+        self.rank, self.size = opt.rank, opt.size
+        if self.size > self.m.MAX_RANKS:
+            raise ValueError(f"device engine supports up to {self.m.MAX_RANKS} ranks per server")
+        if len(opt.param_groups) > self.m.MAX_GROUPS:
+            raise ValueError(f"device engine supports up to {self.m.MAX_GROUPS} param groups")
+        self.mode = opt.mode
+        names = {id(p): n for n, p in opt._named.items()}
+        self.layout = FlatLayout(opt.param_groups, names)
+        p0 = self.layout.slots[0].param
+        self.device, self.dtype = p0.device, p0.dtype
+        self.dt = _DT[self.dtype]
+        self.psz = p0.element_size()
+        self.spec = opt.code.device_spec()
+        self.kind = self.spec.kind
+        self.wire = self.spec.resolved_wire(self.dtype)
+        self.bpt = self.spec.bytes_per_tile(self.dtype)
+        self.cap = self.spec.tile_capacity()
+        self.timeout_s = float(os.environ.get("PSB200_DEVICE_TIMEOUT", "60"))
+        self.bucket_bytes = int(os.environ.get("PSB200_BUCKET_BYTES", 16 << 20))
+        L = self.layout
+        nt, n_pad = L.ntiles, L.numel_padded
+
+        # ---- symmetric block: [signal pad | scales | wire arena | parameter arena] ----
+        self.off_signal = 0
+        self.off_scales = _align(self.m.SIGNAL_SLOTS * 8)
+        self.off_wire = self.off_scales + _align(max(L.nparams, 1) * 4)
+        self.off_param = self.off_wire + _align(nt * self.bpt)
+        total = self.off_param + _align(n_pad * self.psz)
+        self.arena = SymmetricArena(total, self.device, self.world)
+        A = self.arena
+        self.signal = A.tensor(self.off_signal, self.m.SIGNAL_SLOTS * 8, torch.int64)
+        self.scales = A.tensor(self.off_scales, max(L.nparams, 1) * 4, torch.float32)
+        self.wire_arena = A.tensor(self.off_wire, nt * self.bpt, torch.uint8)
+        self.param_arena = A.tensor(self.off_param, n_pad * self.psz, self.dtype)
+
+        # ---- move the model's parameters into the parameter arena (zero-copy from now on) ----
+        with torch.no_grad():
+            self.param_arena.zero_()
+            for s in L.slots:
+                flat = self.param_arena[s.offset: s.offset + s.numel]
+                pd = s.param.data
+                if pd.is_contiguous() or not pd.is_non_overlapping_and_dense():
+                    view = flat.view(pd.shape)
+                else:   # e.g. channels_last conv weights: keep the physical layout cuDNN wants
+                    view = torch.as_strided(flat, pd.shape, pd.stride())
+                view.copy_(pd)
+                s.param.data = view
+        torch.cuda.synchronize(self.device)
+        self.world.barrier()
+        # identical start on every rank: adopt rank 0's weights (the reference silently relies on
+        # equal seeds — there is no initial synchronisation anywhere in ps.py)
+        if self.size > 1 and self.rank != 0 and os.environ.get("PSB200_SYNC_INIT", "1") == "1":
+            src = A.tensor(self.off_param, n_pad * self.psz, self.dtype, rank=0)
+            self.param_arena.copy_(src)
+            torch.cuda.synchronize(self.device)
+        self.world.barrier()
+
+        # ---- server-side state ----
+        self.is_server = (self.mode == "allgather") or self.rank == 0 or self.size == 1
+        self.tiles = L.tile_table_fast().to(self.device)
+        self.amax = torch.zeros(max(L.nparams, 1), dtype=torch.int32, device=self.device)
+        self.active_dev = torch.ones(max(L.nparams, 1), dtype=torch.uint8, device=self.device)
+        self.active_host = torch.ones(max(L.nparams, 1), dtype=torch.uint8).pin_memory()
+        self._active_all = True
+        self.counters = torch.zeros(8, dtype=torch.int32, device=self.device)   # [0] done, [1] stats
+        self.residual = None
+        if self.kind == KIND_TOPK and self.spec.error_feedback:
+            self.residual = torch.zeros(n_pad, dtype=torch.float32, device=self.device)
+        self.master = self.buf0 = self.buf1 = self.buf2 = None
+        if self.is_server:
+            if self.dtype != torch.float32 and master_fp32:
+                self.master = self.param_arena.float()
+            need_b0 = opt.optim == "adam" or any(g.get("momentum", 0) != 0 for g in opt.param_groups)
+            if need_b0:
+                self.buf0 = torch.zeros(n_pad, dtype=torch.float32, device=self.device)
+            if opt.optim == "adam":
+                self.buf1 = torch.zeros(n_pad, dtype=torch.float32, device=self.device)
+                if any(g.get("amsgrad", False) for g in opt.param_groups):
+                    self.buf2 = torch.zeros(n_pad, dtype=torch.float32, device=self.device)
+            self._expose_state()
+        self._group_steps = [0] * len(opt.param_groups)
+
+        # ---- publication / reduction strategy ----
+        mc = A.has_multicast
+        if self.mode == "allgather" or self.size == 1:
+            self.bcast = 0                                  # BCAST_LOCAL
+        else:
+            self.bcast = 2 if (mc and os.environ.get("PSB200_BCAST", "auto") != "unicast") else 1
+        nvls_ok = mc and self.kind == KIND_DENSE and self.wire in (WIRE_F32, WIRE_BF16, WIRE_F16) and self.size > 1
+        if reduce == "nvls" and not nvls_ok:
+            raise ValueError("reduce='nvls' needs multicast memory and a dense fp32/bf16/fp16 wire")
+        # 'auto' keeps the rank-ordered (bit-reproducible) P2P sum; 'nvls' lets the switch reduce
+        self.reduce = 1 if (reduce == "nvls" or (reduce == "auto" and nvls_ok and
+                                                 os.environ.get("PSB200_REDUCE", "") == "nvls")) else 0
+
+        # ---- the launch plan ----
+        self.plan = None
+        if self.is_server:
+            P = self.m.UpdatePlan()
+            P.kind, P.wire, P.opt = self.kind, self.wire, (0 if opt.optim == "sgd" else 1)
+            P.grid = min(nt, self.m.update_max_grid(self.kind, self.wire, P.opt))
+            for r in range(self.size):
+                base = A.ptrs[r]
+                P.set_rank_ptrs(r, base + self.off_wire, base + self.off_scales, base + self.off_param,
+                                base + self.off_signal)
+            P.configure(self.size, self.rank, nt, self.bpt, self.cap, self.dt, self.bcast, self.reduce,
+                        (A.mc_ptr + self.off_param) if mc else 0, (A.mc_ptr + self.off_wire) if mc else 0,
+                        A.local_ptr + self.off_param,
+                        self.master.data_ptr() if self.master is not None else 0,
+                        self.buf0.data_ptr() if self.buf0 is not None else 0,
+                        self.buf1.data_ptr() if self.buf1 is not None else 0,
+                        self.buf2.data_ptr() if self.buf2 is not None else 0,
+                        self.tiles.data_ptr(), A.local_ptr + self.off_signal,
+                        self.counters.data_ptr(), self.counters.data_ptr() + 4)
+            self.plan = P
+        self.comm_stream = torch.cuda.Stream(device=self.device)
+        self._pending: List[tuple] = []
+        self._pending_bytes = 0
+        self._fired: set = set()
+        self._keep: List[torch.Tensor] = []
+        self._raw_bytes = 0
+        self._first_flush_done = False
+        self.launches = 0                     # kernels of OURS launched (bench 'gpu_launches')
+        self._closed = False
+        self._epoch = 0                       # completed engine steps (the epoch-flag clock)
+        # async bookkeeping
+        self.version = 0
+        self._consumed = torch.zeros(64, dtype=torch.int64, device=self.device)
+        self._select_out = torch.zeros(64, dtype=torch.int64, device=self.device)
+        self._select_host = torch.zeros(64, dtype=torch.int64).pin_memory()
+        self._async_done_workers: set = set()
+        self.world.barrier()
+
+    # ---------------------------------------------------------------------------------- state
+    @staticmethod
+    def _like(flat: torch.Tensor, param: torch.Tensor) -> torch.Tensor:
+        """View a flat arena slice with the parameter's shape AND physical layout."""
+        if param.is_contiguous() or not param.is_non_overlapping_and_dense():
+            return flat.view(param.shape)
+        return torch.as_strided(flat, param.shape, param.stride())
+
+    def _expose_state(self):
+        """Make ``opt.state[p]`` views of the flat fp32 state (checkpoint parity)."""
+        o = self.opt
+        for s in self.layout.slots:
+            st = o.state[s.param]
+            sl = slice(s.offset, s.offset + s.numel)
+            if o.optim == "sgd":
+                if self.buf0 is not None:
+                    st["momentum_buffer"] = self._like(self.buf0[sl], s.param)
+            else:
+                st.setdefault("step", 0)
+                st["exp_avg"] = self._like(self.buf0[sl], s.param)
+                st["exp_avg_sq"] = self._like(self.buf1[sl], s.param)
+                if self.buf2 is not None:
+                    st["max_exp_avg_sq"] = self._like(self.buf2[sl], s.param)
+            if self.master is not None:
+                st["master_param"] = self._like(self.master[sl], s.param)
+
+    def sync_state_to_torch(self):
+        if not self.is_server:
+            return
+        o = self.opt
+        if o.optim == "adam":
+            for s in self.layout.slots:
+                o.state[s.param]["step"] = self._group_steps[s.group]
+
+    def sync_state_from_torch(self):
+        """After ``load_state_dict``: copy loaded tensors back into the flat state."""
+        if not self.is_server:
+            return
+        o = self.opt
+        with torch.no_grad():
+            for s in self.layout.slots:
+                st = o.state.get(s.param, {})
+                sl = slice(s.offset, s.offset + s.numel)
+                for key, buf in (("momentum_buffer", self.buf0 if o.optim == "sgd" else None),
+                                 ("exp_avg", self.buf0 if o.optim == "adam" else None),
+                                 ("exp_avg_sq", self.buf1), ("max_exp_avg_sq", self.buf2),
+                                 ("master_param", self.master)):
+                    if buf is not None and key in st and st[key] is not None:
+                        if st[key].data_ptr() != buf[sl].data_ptr():
+                            self._like(buf[sl], s.param).copy_(st[key].to(buf.dtype))
+                if o.optim == "adam" and "step" in st:
+                    self._group_steps[s.group] = max(self._group_steps[s.group], int(st["step"]))
+            if self.master is not None:
+                # parameters may have been re-loaded by the user: re-seed masters that lack a saved copy
+                for s in self.layout.slots:
+                    if "master_param" not in o.state.get(s.param, {}):
+                        self._like(self.master[s.offset: s.offset + s.numel], s.param).copy_(s.param.data.float())
+        self._expose_state()
+
+    # ------------------------------------------------------------------------------- backward
+    def on_grad(self, grad: torch.Tensor, name: str, param: torch.nn.Parameter):
+        """Backward hook (``ps.py:98-101``): bucket the gradient; encode when the bucket fills."""
+        s = self.layout.by_id[id(param)]
+        g = grad.detach()
+        if g.dtype != self.dtype:
+            g = g.to(self.dtype)
+        if g.stride() != param.stride() or g.data_ptr() % 16:
+            # the arena is in the parameter's physical order: bring the gradient into it
+            g = torch.empty_strided(param.shape, param.stride(), dtype=g.dtype, device=g.device).copy_(g)
+        if s.index in self._fired:           # gradient accumulation: later micro-batches add up
+            raise RuntimeError(f"parameter {name!r} produced two gradients before step(); "
+                               "call step() after every backward (the reference encodes per backward)")
+        self._fired.add(s.index)
+        self._pending.append((s, g))
+        self._pending_bytes += s.numel * self.psz
+        self._raw_bytes += s.numel * self.psz
+        if self._pending_bytes >= self.bucket_bytes:
+            self._flush()
+
+    def _flush(self):
+        if not self._pending:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        cs = self.comm_stream
+        cs.wait_event(ev)
+        batch, self._pending, self._pending_bytes = self._pending, [], 0
+        with torch.cuda.stream(cs):
+            if not self._first_flush_done:
+                self._first_flush_done = True
+                self._before_first_encode()
+            grads = [g for _, g in batch]
+            for g in grads:
+                g.record_stream(cs)
+            self.m.encode(self.kind, self.wire, grads, [s.first_tile for s, _ in batch],
+                          [s.ntiles for s, _ in batch], [s.index for s, _ in batch],
+                          self.tiles.data_ptr(), self.arena.local_ptr + self.off_wire,
+                          self.arena.local_ptr + self.off_scales, self.amax.data_ptr(),
+                          self.residual.data_ptr() if self.residual is not None else 0,
+                          self.bpt, self.cap, float(self.spec.ratio))
+            nb = (len(batch) + 63) // 64
+            self.launches += nb * (2 if self.kind == KIND_SCALED else 1)
+        self._keep.extend(grads)
+
+    def _before_first_encode(self):
+        """Runs on the comm stream before this step's first write into the wire arena."""
+        epoch = self._epoch + 1              # the step these gradients belong to
+        if self.kind == KIND_SCALED:
+            self.amax.zero_()
+        if self.size == 1:
+            return
+        sig = self.arena.local_ptr + self.off_signal
+        if self.mode == "allgather" and epoch > 1:
+            # every peer must have finished READING our previous wire tiles
+            self.m.wait_flags(sig, self.m.SIG_CONSUMED, (1 << self.size) - 1, epoch - 1, self.timeout_s)
+            self.launches += 1
+        elif self.mode == "async" and self.rank != 0 and epoch > 1:
+            self.m.wait_flags(sig, self.m.SIG_ACK, 1, epoch - 1, self.timeout_s)
+            self.launches += 1
+
+    # ----------------------------------------------------------------------------------- step
+    def _hypers(self) -> List[List[float]]:
+        o = self.opt
+        out = []
+        for gi, g in enumerate(o.param_groups):
+            self._group_steps[gi] += 1
+            t = self._group_steps[gi]
+            if o.optim == "sgd":
+                out.append([float(g["lr"]), float(g["weight_decay"]), float(g["momentum"]), float(g["dampening"]),
+                            0.0, 0.0, 0.0, 0.0, float(bool(g["nesterov"])), 0.0, float(t == 1)])
+            else:
+                b1, b2 = g["betas"]
+                step_size = float(g["lr"]) * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)     # ps.py:257-259
+                out.append([float(g["lr"]), float(g["weight_decay"]), 0.0, 0.0, float(b1), float(b2),
+                            float(g["eps"]), step_size, 0.0, float(bool(g.get("amsgrad", False))), float(t == 1)])
+        return out
+
+    def _handle_inactive(self):
+        """Parameters whose hook did not fire this step (``p.grad is None``, ``ps.py:178-179``)."""
+        L = self.layout
+        if len(self._fired) == L.nparams:
+            if not self._active_all:
+                self.active_host.fill_(1)
+                self.active_dev.copy_(self.active_host, non_blocking=True)
+                self._active_all = True
+            return 0
+        self.active_host.zero_()
+        for i in self._fired:
+            self.active_host[i] = 1
+        self.active_dev.copy_(self.active_host, non_blocking=True)
+        self._active_all = False
+        # a tile the server will read must not carry last step's payload
+        for s in L.slots:
+            if s.index not in self._fired:
+                self.wire_arena[s.first_tile * self.bpt: (s.first_tile + s.ntiles) * self.bpt].zero_()
+        return self.active_dev.data_ptr()
+
+    def step(self) -> Dict[str, float]:
+        o = self.opt
+        t0 = time.time()
+        data = {"comm_wait": 0.0, "optim_step_time": 0.0, "decode_time": 0.0,
+                "iallgather_prepare_time": 0.0, "isend_time": 0.0}
+        if self.mode == "async" and self.size > 1:
+            return self._step_async(data)
+        self._flush()
+        data["code_wait"] = time.time() - t0
+        epoch = self._epoch + 1
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)                       # backward is complete up to here
+        cs = self.comm_stream
+        cs.wait_event(ev)
+        sig_base = [p + self.off_signal for p in self.arena.ptrs]
+        t1 = time.time()
+        with torch.cuda.stream(cs):
+            if not self._first_flush_done:
+                self._first_flush_done = True
+                self._before_first_encode()
+            active_ptr = self._handle_inactive()
+            if self.size > 1:
+                targets = [sig_base[0]] if self.mode == "ps" else sig_base
+                self.m.signal(targets, self.m.SIG_GRAD_READY + self.rank, epoch)
+                self.launches += 1
+            data["isend_time"] = time.time() - t1
+            t2 = time.time()
+            if self.is_server:
+                n = self.size
+                inv = (1.0 / n) if o.average else 1.0
+                self.plan.launch(epoch, self._hypers(), (1 << n) - 1, inv, 1 if n > 1 else 0,
+                                 0 if n == 1 else (1 if self.mode == "ps" else 2),
+                                 active_ptr=active_ptr, timeout_s=self.timeout_s)
+                self.launches += 1
+            else:
+                self._hypers()               # keep per-group step counters aligned with the server
+            data["optim_step_time"] = time.time() - t2
+            done = torch.cuda.Event()
+            done.record(cs)
+        t3 = time.time()
+        if self.size > 1 and self.mode == "ps" and self.rank != 0:
+            # the req.Wait() of mpi_comms.py:121 — a one-thread kernel on the compute stream
+            self.m.wait_flags(sig_base[self.rank], self.m.SIG_PARAMS_READY, 1, epoch, self.timeout_s)
+            self.launches += 1
+        else:
+            cur.wait_event(done)
+        data["comm_wait"] = time.time() - t3
+        self._end_of_step(data)
+        return data
+
+    def _end_of_step(self, data):
+        L = self.layout
+        nfired = max(len(self._fired), 1)
+        data["msg_bytes"] = self._raw_bytes / nfired
+        wire_bytes = sum(L.slots[i].ntiles for i in self._fired) * self.bpt if self._fired else 0
+        data["packaged_bytes"] = wire_bytes / nfired
+        data["engine"] = "device"
+        self._epoch += 1
+        self._fired = set()
+        self._keep = []
+        self._raw_bytes = 0
+        self._first_flush_done = False
+        if os.environ.get("PSB200_CHECK") == "1":
+            self.check()
+
+    # ------------------------------------------------------------------------------ async mode
+    def _step_async(self, data):
+        o = self.opt
+        sig_base = [p + self.off_signal for p in self.arena.ptrs]
+        cs = self.comm_stream
+        cur = torch.cuda.current_stream(self.device)
+        if self.rank != 0:
+            self._flush()
+            epoch = self._epoch + 1
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                if not self._first_flush_done:
+                    self._first_flush_done = True
+                    self._before_first_encode()
+                self._handle_inactive()
+                # publish "gradient `epoch` is in my arena"
+                self.m.signal([sig_base[0]], self.m.SIG_GRAD_READY + self.rank, epoch)
+                self.launches += 1
+            self._end_of_step(data)
+            return data                      # never waits for parameters: inconsistent reads
+        # ---- rank 0: the server ----
+        self._fired = set()
+        self._pending, self._pending_bytes, self._keep = [], 0, []
+        n = self.size
+        cand = ((1 << n) - 1) & ~1
+        for r in self._async_done_workers:
+            cand &= ~(1 << r)
+        if cand == 0:
+            data["ps_done"] = True
+            return data
+        quota = max(1, min(o.quota, bin(cand).count("1")))
+        t0 = time.time()
+        with torch.cuda.stream(cs):
+            self.m.select_ready(sig_base[0], self._consumed.data_ptr(), cand, quota,
+                                self._select_out.data_ptr(), self.timeout_s)
+            self.version += 1
+            self.plan.launch(o.steps, self._hypers(), 0, 1.0, 0, 1, 0, self.version,
+                             self._select_out.data_ptr(), 1 if o.average else 0, 0, self.timeout_s)
+            self.launches += 2
+            self._select_host.copy_(self._select_out, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cs)
+        done.synchronize()                   # the server loop is host-driven (it has nothing else to do)
+        data["comm_wait"] = time.time() - t0
+        mask = int(self._select_host[0].item())
+        finished = int(self._select_host[40].item())
+        for r in range(n):
+            if finished >> r & 1:
+                self._async_done_workers.add(r)
+        data["contributors"] = [r for r in range(n) if mask >> r & 1]
+        if not data["contributors"]:
+            self.version -= 1                # nothing was applied
+            for gi in range(len(self._group_steps)):
+                self._group_steps[gi] -= 1
+        data["param_version"] = self.version
+        data["ps_done"] = len(self._async_done_workers) >= n - 1 and not data["contributors"]
+        self._epoch += 1
+        data["engine"] = "device"
+        return data
+
+    # ------------------------------------------------------------------------------ diagnostics
+    def check(self):
+        """Raise if any bounded spin timed out (forces a device sync; off the hot path)."""
+        torch.cuda.synchronize(self.device)
+        err = int(self.signal[self.m.SIG_ERROR].item())
+        if err:
+            raise RuntimeError(f"rank {self.rank}: a device-side wait timed out (code {err}); "
+                               "a peer is stalled or dead")
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        try:
+            if self.mode == "async" and self.size > 1 and self.rank != 0:
+                with torch.cuda.stream(self.comm_stream):
+                    if self._epoch > 0:      # the server must have consumed our last gradient first
+                        self.m.wait_flags(self.arena.local_ptr + self.off_signal, self.m.SIG_ACK, 1,
+                                          self._epoch, self.timeout_s)
+                    self.m.signal([self.arena.ptrs[0] + self.off_signal],
+                                  self.m.SIG_GRAD_READY + self.rank, _DONE_EPOCH)
+            torch.cuda.synchronize(self.device)
+            self.world.barrier()
+        finally:
+            # parameters keep their arena views alive; detach them so the block can be freed
+            with torch.no_grad():
+                for s in self.layout.slots:
+                    s.param.data = s.param.data.clone()
+            self.arena.close()

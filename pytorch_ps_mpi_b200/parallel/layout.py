@@ -1,0 +1,82 @@
+"""Flat arena layout: every parameter packed, tile-aligned, into one contiguous index space.
+
+The reference walks parameters one by one in reverse registration (= backward) order
+(``/root/reference/ps.py:121-123``) and pays one message + several eager kernels per parameter.
+Here all parameters live in ONE flat arena so a single kernel launch covers the whole model:
+
+* parameters are laid out in **reverse registration order** (gradients that are ready first sit
+  at the front of the arena);
+* every parameter starts on a :data:`~pytorch_ps_mpi_b200.codings.TILE`-element boundary and owns
+  an integral number of tiles, so a tile never straddles two parameters (per-tensor scales and
+  block-wise top-k stay tile-local);
+* a small ``[ntiles, 4]`` int32 table (parameter, valid elements, param-group, first tile)
+  drives the kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List
+
+import torch
+
+from ..codings import TILE
+
+
+@dataclass
+class ParamSlot:
+    index: int            # position in arena order
+    name: str
+    param: torch.nn.Parameter
+    group: int
+    first_tile: int
+    ntiles: int
+    numel: int
+
+    @property
+    def offset(self) -> int:      # element offset in the arena
+        return self.first_tile * TILE
+
+
+class FlatLayout:
+    def __init__(self, param_groups, names: Dict[int, str]):
+        ordered = []
+        for gi, g in enumerate(param_groups):
+            for p in g["params"]:
+                ordered.append((gi, p))
+        ordered.reverse()                                    # backward order (ps.py:121-123)
+        self.slots: List[ParamSlot] = []
+        self.by_id: Dict[int, ParamSlot] = {}
+        t = 0
+        for i, (gi, p) in enumerate(ordered):
+            n = p.numel()
+            nt = max(1, (n + TILE - 1) // TILE)
+            s = ParamSlot(i, names.get(id(p), f"param{i}"), p, gi, t, nt, n)
+            self.slots.append(s)
+            self.by_id[id(p)] = s
+            t += nt
+        self.ntiles = t
+        self.numel_padded = t * TILE
+        self.nparams = len(self.slots)
+        self.ngroups = len(param_groups)
+
+    def tile_table(self) -> torch.Tensor:
+        """``[ntiles, 4]`` int32: (param, valid, group, first_tile) — ``TileInfo`` in common.cuh."""
+        tab = torch.empty(self.ntiles, 4, dtype=torch.int32)
+        for s in self.slots:
+            for k in range(s.ntiles):
+                valid = min(TILE, s.numel - k * TILE)
+                tab[s.first_tile + k] = torch.tensor([s.index, max(valid, 0), s.group, s.first_tile], dtype=torch.int32)
+        return tab
+
+    def tile_table_fast(self) -> torch.Tensor:
+        """Vectorised construction of :meth:`tile_table` (BERT-size models have ~54k tiles)."""
+        import numpy as np
+        tab = np.empty((self.ntiles, 4), dtype=np.int32)
+        for s in self.slots:
+            k = np.arange(s.ntiles, dtype=np.int64)
+            sl = slice(s.first_tile, s.first_tile + s.ntiles)
+            tab[sl, 0] = s.index
+            tab[sl, 1] = np.clip(s.numel - k * TILE, 0, TILE)
+            tab[sl, 2] = s.group
+            tab[sl, 3] = s.first_tile
+        return torch.from_numpy(tab)

@@ -112,7 +112,7 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None,
             be = dist.get_backend()
             w = World(dist.get_rank(), dist.get_world_size(), local_rank, device, be)
         elif env_size > 1:
-            be = backend or ("nccl" if device.type == "cuda" else "gloo")
+            be = backend or os.environ.get("PSB200_PG_BACKEND") or ("nccl" if device.type == "cuda" else "gloo")
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29511")
             kw = {}

@@ -183,3 +183,120 @@ def mlp_async(rank, size, transport):
     after = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     if rank == 0:
         assert not torch.equal(before, after)
+
+
+# --- device engine, spawned ranks (1 GPU shared by all ranks, or one GPU per rank) ----------
+def gpu_train(rank, size, mode, optim, coding, dtype_name):
+    import math
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    dev = w.device
+    assert dev.type == "cuda"
+    dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[dtype_name]
+    factory = {"identity": ps.Identity, "cast": lambda: ps.Cast("bf16"), "scale": lambda: ps.Scale("int8"),
+               "topk": lambda: ps.TopK(ratio=0.25)}[coding]
+    hyper = {"lr": 0.05, "momentum": 0.9, "weight_decay": 1e-4} if optim == "sgd" else {"lr": 1e-2, "eps": 1e-8}
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=32).to(dev).to(dtype)
+    cls = ps.SGD if optim == "sgd" else ps.Adam
+    opt = cls(model.named_parameters(), model.parameters(), code=factory(), mode=mode, engine="device", **hyper)
+    eng = opt._engine
+    assert eng is not None and eng.arena.provider in ("native", "torch")
+    steps = 3
+    for s in range(steps):
+        x, y = _mlp_data(rank, s)
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(x.to(dev).to(dtype)).float(), y.to(dev))
+        loss.backward()
+        out = opt.step()
+        assert isinstance(out, tuple) and out[1]["engine"] == "device"
+    eng.check()
+    torch.cuda.synchronize()
+    flat = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()]).cpu()
+    allp = w.all_gather_object(flat)
+    for f in allp:
+        assert torch.equal(f, allp[0]), "ranks diverged"
+    if dtype == torch.float32:
+        class HostAdam:      # the reference's Adam math for the oracle (sqrt(v)+eps form)
+            pass
+        want = _oracle_sum_ref(size, steps, optim, hyper, factory)
+        for p, q in zip(model.parameters(), want):
+            assert torch.allclose(p.detach().cpu(), q, rtol=2e-4, atol=2e-5), (mode, optim, coding, (p.detach().cpu() - q).abs().max())
+    info = {"provider": eng.arena.provider, "multicast": eng.arena.has_multicast, "bcast": eng.bcast}
+    if rank == 0:
+        print("gpu_train ok", mode, optim, coding, dtype_name, info, flush=True)
+    opt.close()
+
+
+def _oracle_sum_ref(size, steps, optim, hyper, coding_factory):
+    """Single-process oracle using the package's own host-path optimizer math (reference formulas)."""
+    import pytorch_ps_mpi_b200 as ps
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=32)
+    cls = ps.SGD if optim == "sgd" else ps.Adam
+    opt = cls(model.named_parameters(), model.parameters(), engine="host", use_mpi=False, **hyper)
+    groups = opt._group_of()
+    for s in range(steps):
+        total = [torch.zeros_like(p) for p in model.parameters()]
+        for r in range(size):
+            code = coding_factory()
+            x, y = _mlp_data(r, s)
+            model.zero_grad()
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            for t, p in zip(total, model.parameters()):
+                t += code.decode(code.encode(p.grad)).reshape(p.shape).to(t.dtype)
+        opt.futures, opt.names = [], []
+        with torch.no_grad():
+            for t, p in zip(total, model.parameters()):
+                opt.optim_step(p, t, **opt._hyper(groups[id(p)]))
+    return [p.detach().clone() for p in model.parameters()]
+
+
+def gpu_async(rank, size, coding):
+    import time
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    dev = w.device
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=32).to(dev)
+    code = ps.Identity() if coding == "identity" else ps.TopK(ratio=0.25)
+    opt = ps.SGD(model.named_parameters(), model.parameters(), lr=0.05, code=code, mode="async", quota=1,
+                 engine="device")
+    before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    nsteps = 4
+    if rank == 0:
+        n = opt.serve()
+        assert n == nsteps * (size - 1), n
+    else:
+        for s in range(nsteps):
+            x, y = _mlp_data(rank, s)
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(model(x.to(dev)), y.to(dev)).backward()
+            opt.step()
+            time.sleep(0.01 * rank)
+    opt._engine.check()
+    opt.close()
+    after = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    assert not torch.equal(before, after)
+    # after the drain every rank holds the server's final parameters
+    allp = w.all_gather_object(after.cpu())
+    for f in allp:
+        assert torch.equal(f, allp[0])
+
+
+def symm_arena(rank, size):
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.parallel.symmetric import SymmetricArena
+    A = SymmetricArena(3 << 20, w.device, w)
+    mine = A.tensor(0, 1 << 20, torch.float32)
+    mine.fill_(float(rank + 1))
+    torch.cuda.synchronize()
+    w.barrier()
+    for r in range(size):
+        peer = A.tensor(0, 1 << 20, torch.float32, rank=r)
+        assert float(peer[12345]) == float(r + 1), (rank, r, float(peer[12345]))
+    w.barrier()
+    if rank == 0:
+        print("symm_arena ok", A.provider, "multicast" if A.has_multicast else "no-multicast", A.nbytes, flush=True)
+    A.close()

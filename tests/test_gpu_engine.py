@@ -1,0 +1,136 @@
+"""Device engine end to end on the GPU box.
+
+* single process: ``ps.SGD`` / ``ps.Adam`` (device engine) vs ``torch.optim`` on the same gradients;
+* 2-3 ranks sharing ONE GPU (gloo bootstrap; VMM fd exchange, peer pointers, epoch flags all real);
+* ``multigpu``: one rank per GPU (multicast / NVLS paths).
+"""
+import os
+
+import pytest
+import torch
+
+import pytorch_ps_mpi_b200 as ps
+from pytorch_ps_mpi_b200.launch import spawn
+from pytorch_ps_mpi_b200.models import mnist_mlp
+from tests import _mp
+
+pytestmark = pytest.mark.gpu
+ONE_GPU = {"PSB200_PG_BACKEND": "gloo", "CUDA_VISIBLE_DEVICES": "0", "PSB200_DEVICE_TIMEOUT": "20"}
+
+
+def _run(opt_factory, dtype=torch.float32, steps=4):
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=64).to(dev).to(dtype)
+    opt = opt_factory(model)
+    for s in range(steps):
+        g = torch.Generator().manual_seed(s)
+        x, y = torch.randn(8, 784, generator=g).to(dev).to(dtype), torch.randint(0, 10, (8,), generator=g).to(dev)
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(model(x).float(), y).backward()
+        opt.step()
+    torch.cuda.synchronize()
+    return [p.detach().float().clone() for p in model.parameters()], opt
+
+
+@pytest.mark.parametrize("hyper", [dict(lr=0.1), dict(lr=0.05, momentum=0.9, weight_decay=1e-3),
+                                   dict(lr=0.05, momentum=0.9, nesterov=True)])
+def test_device_sgd_matches_torch(hyper):
+    a, opt = _run(lambda m: ps.SGD(m.named_parameters(), m.parameters(), code=ps.Identity(), engine="device", **hyper))
+    assert opt._engine is not None and opt._engine.launches > 0
+    b, _ = _run(lambda m: torch.optim.SGD(m.parameters(), **hyper))
+    for p, q in zip(a, b):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    opt._engine.check()
+    sd = opt.state_dict()
+    if hyper.get("momentum"):
+        assert all("momentum_buffer" in s for s in sd["state"].values())
+    opt.close()
+
+
+def test_device_adam_matches_host_engine():
+    a, o1 = _run(lambda m: ps.Adam(m.named_parameters(), m.parameters(), lr=1e-3, engine="device"))
+    b, o2 = _run(lambda m: ps.Adam(m.named_parameters(), m.parameters(), lr=1e-3, engine="host"))
+    for p, q in zip(a, b):
+        assert torch.allclose(p, q, rtol=1e-4, atol=1e-6)
+    o1.close(), o2.close()
+
+
+def test_device_bf16_master_weights():
+    a, opt = _run(lambda m: ps.SGD(m.named_parameters(), m.parameters(), lr=0.05, momentum=0.9, engine="device"),
+                  dtype=torch.bfloat16, steps=6)
+    eng = opt._engine
+    assert eng.master is not None and eng.master.dtype == torch.float32
+    for s in eng.layout.slots:      # published bf16 parameter == round(master)
+        m = eng.master[s.offset:s.offset + s.numel]
+        assert torch.equal(m.to(torch.bfloat16), s.param.data.reshape(-1))
+    opt.close()
+
+
+def test_unused_parameter_is_skipped():
+    dev = torch.device("cuda", 0)
+    a = torch.nn.Parameter(torch.randn(3000, device=dev))
+    b = torch.nn.Parameter(torch.randn(100, device=dev))
+    opt = ps.SGD([("a", a), ("b", b)], [a, b], lr=0.1, weight_decay=0.5, engine="device")
+    b0 = b.detach().clone()
+    a0 = a.detach().clone()
+    a.sum().backward()
+    opt.step()
+    torch.cuda.synchronize()
+    assert torch.equal(b.detach(), b0)                       # p.grad is None → untouched (ps.py:178-179)
+    assert torch.allclose(a.detach(), a0 - 0.1 * (1 + 0.5 * a0), rtol=1e-5, atol=1e-6)
+    opt.close()
+
+
+def test_channels_last_conv_weights_keep_layout():
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(8, 16, 3, padding=1).to(dev).to(memory_format=torch.channels_last)
+    ref = torch.nn.Conv2d(8, 16, 3, padding=1).to(dev).to(memory_format=torch.channels_last)
+    ref.load_state_dict(conv.state_dict())
+    opt = ps.SGD(conv.named_parameters(), conv.parameters(), lr=0.1, momentum=0.9, engine="device")
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9)
+    assert conv.weight.is_contiguous(memory_format=torch.channels_last)
+    x = torch.randn(4, 8, 10, 10, device=dev).contiguous(memory_format=torch.channels_last)
+    for _ in range(3):
+        for m, o in ((conv, opt), (ref, ropt)):
+            o.zero_grad()
+            m(x).square().mean().backward()
+            o.step()
+    torch.cuda.synchronize()
+    assert torch.allclose(conv.weight, ref.weight, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(conv.bias, ref.bias, rtol=1e-5, atol=1e-6)
+    opt.close()
+
+
+def test_symmetric_arena_two_ranks_one_gpu():
+    spawn(_mp.symm_arena, 2, env=ONE_GPU, timeout=180)
+
+
+@pytest.mark.parametrize("mode,optim,coding,dtype", [
+    ("ps", "sgd", "identity", "fp32"), ("ps", "adam", "topk", "fp32"), ("allgather", "sgd", "scale", "fp32"),
+    ("ps", "sgd", "cast", "bf16"),
+])
+def test_engine_two_ranks_one_gpu(mode, optim, coding, dtype):
+    spawn(_mp.gpu_train, 2, (mode, optim, coding, dtype), env=ONE_GPU, timeout=240)
+
+
+def test_engine_three_ranks_allgather_one_gpu():
+    spawn(_mp.gpu_train, 3, ("allgather", "adam", "identity", "fp32"), env=ONE_GPU, timeout=240)
+
+
+def test_engine_async_one_gpu():
+    spawn(_mp.gpu_async, 3, ("identity",), env=ONE_GPU, timeout=240)
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("mode,optim,coding,dtype", [("ps", "sgd", "identity", "fp32"), ("ps", "adam", "cast", "bf16"),
+                                                      ("allgather", "sgd", "topk", "fp32")])
+def test_engine_multi_gpu(mode, optim, coding, dtype):
+    n = min(torch.cuda.device_count(), 4)
+    spawn(_mp.gpu_train, n, (mode, optim, coding, dtype), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
+
+
+@pytest.mark.multigpu
+def test_async_multi_gpu():
+    spawn(_mp.gpu_async, min(torch.cuda.device_count(), 4), ("topk",), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
