@@ -204,7 +204,8 @@ class Scale(Coding):
         qmax = _WIRE_MAX[self.wire]
         amax = g.abs().max() if g.numel() else g.new_zeros(())
         amax = torch.where(torch.isfinite(amax) & (amax > 0), amax, torch.ones_like(amax))
-        inv = amax / qmax                       # fp32
+        inv = amax / torch.full_like(amax, qmax)   # IEEE fp32 division (a Python-scalar divisor is a
+        #                                            reciprocal-multiply on CUDA and differs by 1 ulp)
         q = _sat_cast(g / inv, self.wire)       # == g * (qmax/amax) up to fp32 rounding
         return {"q": q, "inv": inv.reshape(1)}
 

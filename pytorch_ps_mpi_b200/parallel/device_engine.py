@@ -47,6 +47,19 @@ def _align(n: int, a: int = 256) -> int:
     return (n + a - 1) // a * a
 
 
+def _dense(t: torch.Tensor) -> bool:
+    """True if ``t``'s strides describe a dense, non-overlapping permutation of its shape."""
+    if t.is_contiguous():
+        return True
+    dims = sorted(((st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1), key=lambda x: x[0])
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
 class DeviceEngine:
     def __init__(self, opt, master_fp32: bool = True, reduce: str = "auto"):
         self.opt = opt
@@ -93,7 +106,7 @@ class DeviceEngine:
             for s in L.slots:
                 flat = self.param_arena[s.offset: s.offset + s.numel]
                 pd = s.param.data
-                if pd.is_contiguous() or not pd.is_non_overlapping_and_dense():
+                if pd.is_contiguous() or not _dense(pd):
                     view = flat.view(pd.shape)
                 else:   # e.g. channels_last conv weights: keep the physical layout cuDNN wants
                     view = torch.as_strided(flat, pd.shape, pd.stride())
@@ -189,7 +202,7 @@ class DeviceEngine:
     @staticmethod
     def _like(flat: torch.Tensor, param: torch.Tensor) -> torch.Tensor:
         """View a flat arena slice with the parameter's shape AND physical layout."""
-        if param.is_contiguous() or not param.is_non_overlapping_and_dense():
+        if param.is_contiguous() or not _dense(param):
             return flat.view(param.shape)
         return torch.as_strided(flat, param.shape, param.stride())
 
