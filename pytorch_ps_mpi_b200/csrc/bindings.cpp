@@ -38,7 +38,13 @@ at::Tensor blob_tensor(uint64_t ptr, std::vector<int64_t> shape, at::ScalarType 
     keep.reset();
   };
   auto opts = at::TensorOptions().dtype(dtype).device(at::kCUDA, device);
-  return at::from_blob(reinterpret_cast<void*>(ptr), shape, deleter, opts);
+  // target_device: a peer's block is mapped into THIS device's address space, but the pointer
+  // attributes still name the owning GPU — tell ATen which device the view belongs to.
+  return at::for_blob(reinterpret_cast<void*>(ptr), shape)
+      .options(opts)
+      .target_device(c10::Device(at::kCUDA, (c10::DeviceIndex)device))
+      .deleter(deleter)
+      .make_tensor();
 }
 
 // Static part of the fused PS launch (pointers never change after the arenas are built).

@@ -1,0 +1,311 @@
+// bcast_gemm: Y[M,N] = act(X[M,K] · W[N,K]^T + bias) in bf16 with fp32 accumulation on the 5th-gen
+// tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA into 128B-swizzled
+// shared memory), whose WEIGHT operand is the tile the parameter server just broadcast.
+//
+// Fusion with the PS→worker broadcast (K4 in SURVEY §2.6; the Ibcast + Wait + first forward
+// matmul of /root/reference/mpi_comms.py:120-133): the weight tensor map points INTO the symmetric
+// parameter arena (this rank's copy that the server's multimem.st fills — or, in pull mode, the
+// server's own arena mapped over NVLink).  The TMA producer warp acquires the PARAMS_READY epoch
+// flag (ld.acquire.sys + fence.proxy.async) immediately before its first weight load, so the
+// kernel launches while the broadcast is still in flight: TMEM allocation, barrier init,
+// descriptor prefetch and the scheduler prologue overlap the tail of the server's update kernel,
+// and this GEMM *is* the req.Wait() for the whole forward pass that follows it on the stream.
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d → smem ring (STAGES x {A 128x64, B BNx64})
+//   warp 1      MMA issuer     one elected lane: tcgen05.mma.cta_group::1.kind::f16, UMMA 128xBNx16,
+//                              tcgen05.commit → frees smem slots / publishes the accumulator
+//   warps 2..5  epilogue       tcgen05.ld 32x32b → +bias → ReLU → bf16 → 16-byte global stores
+//   TMEM        2 accumulator stages x BN fp32 columns (double-buffered against the epilogue)
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "kernels.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 64;                 // 64 bf16 = one 128-byte swizzle row
+constexpr int STAGES = 5;
+constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 16 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;   // 256 (power of two >= 32)
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait is a HW-assisted (suspending) probe; the bound turns a protocol bug into a trap, not a hang
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && spins > (1u << 26)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (1024 B between
+//   8-row groups) | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// tcgen05 instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct GemmParams {
+  const float* bias;
+  __nv_bfloat16* out;
+  const uint64_t* ready_flag;
+  uint64_t ready_epoch;
+  uint64_t* err_slot;
+  int M, N, K, relu;
+  unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+psb_bcast_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + STAGES;             // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;     // [ACC_STAGES]
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation is warp-wide; the same warp frees it at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      // The broadcast gate: do not touch a weight tile before the server published this epoch.
+      if (p.ready_flag != nullptr) {
+        psb::spin_until_ge(p.ready_flag, p.ready_epoch, p.err_slot, p.timeout_ns);
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire → async-proxy (TMA) reads
+      }
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(&tmap_a, &full[stage], sa, kb * BK, m0);
+          tma_load_2d(&tmap_b, &full[stage], sa + A_BYTES, kb * BK, n0);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc();
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4) units
+            umma(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);                         // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete → epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+      if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + quarter * 32 + lane;
+      const bool vec_ok = (p.N % 8) == 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < p.M) {
+          __nv_bfloat16* orow = p.out + (size_t)row * p.N + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int col = n0 + c0 + j;
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              v[t] = __uint_as_float(r[j + t]);
+              if (p.bias != nullptr && col + t < p.N) v[t] += p.bias[col + t];
+              if (p.relu) v[t] = fmaxf(v[t], 0.f);
+            }
+            if (vec_ok && col + 8 <= p.N) {
+              uint4 o = make_uint4(psb::pack_bf16x2(v[0], v[1]), psb::pack_bf16x2(v[2], v[3]),
+                                   psb::pack_bf16x2(v[4], v[5]), psb::pack_bf16x2(v[6], v[7]));
+              *reinterpret_cast<uint4*>(orow + j) = o;
+            } else {
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                if (col + t < p.N) orow[j + t] = __float2bfloat16_rn(v[t]);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+int psb_bcast_gemm_smem_bytes() { return SMEM_BYTES; }
+
+void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(psb_bcast_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    configured = true;
+  }
+  GemmParams p{};
+  p.bias = a.bias;
+  p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a.tmap_c));   // tmap_c carries the output pointer
+  p.ready_flag = a.ready_flag;
+  p.ready_epoch = a.ready_epoch;
+  p.err_slot = a.ready_flag != nullptr ? const_cast<uint64_t*>(a.ready_flag) - SIG_PARAMS_READY + SIG_ERROR : nullptr;
+  p.M = a.M, p.N = a.N, p.K = a.K, p.relu = a.relu;
+  p.timeout_ns = a.timeout_ns;
+  const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  psb_bcast_gemm_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(*reinterpret_cast<const CUtensorMap*>(a.tmap_a),
+                                                          *reinterpret_cast<const CUtensorMap*>(a.tmap_b), p);
+}

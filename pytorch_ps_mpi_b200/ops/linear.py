@@ -1,0 +1,94 @@
+"""``BcastLinear``: a linear layer whose forward GEMM is the hand-written tcgen05 kernel
+(``csrc/kernels/bcast_gemm.cu``) and whose weight operand is consumed straight out of the
+symmetric parameter arena the parameter server broadcasts into.
+
+With a device-engine optimizer attached (:meth:`BcastLinear.attach`), the kernel's TMA producer
+acquires the ``PARAMS_READY`` epoch flag itself, so ``opt.step()`` on a worker no longer queues a
+separate wait kernel: the first forward GEMM *is* the ``req.Wait()`` of the broadcast
+(``/root/reference/mpi_comms.py:120-124``) and everything stream-ordered after it sees the fresh
+weights.  ``pull=True`` makes the weight tensor map point at the SERVER's arena (mapped over
+NVLink), i.e. the worker's TMA engine pulls the tiles across the switch directly into shared
+memory.
+
+Backward is plain library GEMMs (cuBLAS via ``torch.matmul``) — only the forward is on the named
+hot path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ext
+
+
+class _BcastLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, weight, bias, relu, w_ptr, flag_ptr, epoch):
+        m = ext.cuda()
+        N, K = weight.shape
+        y = m.bcast_gemm(x2d, w_ptr or weight.data_ptr(), N, K, bias, relu, flag_ptr, epoch, 30.0)
+        ctx.save_for_backward(x2d, weight, y if relu else None)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2d, weight, y = ctx.saved_tensors
+        if ctx.relu:
+            gy = gy * (y > 0).to(gy.dtype)
+        gx = gy @ weight if ctx.needs_input_grad[0] else None
+        gw = gy.t() @ x2d if ctx.needs_input_grad[1] else None
+        gb = gy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None, None, None, None
+
+
+def bcast_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+                 w_ptr: int = 0, flag_ptr: int = 0, epoch: int = 0) -> torch.Tensor:
+    """``act(x @ weight.T + bias)`` on tcgen05 (bf16 in, fp32 accumulate, bf16 out)."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
+            and weight.shape[1] % 8 == 0):
+        y = F.linear(x, weight, bias)          # shapes/dtypes the kernel does not cover
+        return F.relu(y) if relu else y
+    shp = x.shape
+    x2d = x.reshape(-1, shp[-1])
+    if not x2d.is_contiguous() or x2d.data_ptr() % 16:
+        x2d = x2d.contiguous()
+    y = _BcastLinearFn.apply(x2d, weight, bias, relu, w_ptr, flag_ptr, epoch)
+    return y.view(*shp[:-1], weight.shape[0])
+
+
+class BcastLinear(nn.Linear):
+    """Drop-in ``nn.Linear`` (same parameters / state_dict) running on the tcgen05 GEMM."""
+
+    def __init__(self, in_features, out_features, bias=True, relu=False, **kw):
+        super().__init__(in_features, out_features, bias=bias, **kw)
+        self.relu = relu
+        self._engine = None
+        self._pull = False
+
+    def attach(self, optimizer, pull: bool = False) -> "BcastLinear":
+        """Gate this layer's weight loads on ``optimizer``'s broadcast epoch (device engine only)."""
+        eng = getattr(optimizer, "_engine", None)
+        if eng is None:
+            raise ValueError("attach() needs an optimizer running the device engine")
+        self._engine, self._pull = eng, pull
+        eng.register_gate(self)
+        return self
+
+    def forward(self, x):
+        eng = self._engine
+        if eng is None or not self.weight.is_cuda:
+            return bcast_linear(x, self.weight, self.bias, self.relu)
+        flag_ptr, epoch = eng.gate()
+        w_ptr = eng.peer_param_ptr(self.weight, 0) if (self._pull and eng.size > 1) else 0
+        return bcast_linear(x, self.weight, self.bias, self.relu, w_ptr, flag_ptr, epoch)
+
+    @classmethod
+    def from_linear(cls, lin: nn.Linear, relu: bool = False) -> "BcastLinear":
+        new = cls(lin.in_features, lin.out_features, bias=lin.bias is not None, relu=relu,
+                  device=lin.weight.device, dtype=lin.weight.dtype)
+        new.weight, new.bias = lin.weight, lin.bias
+        return new

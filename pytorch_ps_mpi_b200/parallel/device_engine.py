@@ -189,6 +189,7 @@ class DeviceEngine:
         self._first_flush_done = False
         self.launches = 0                     # kernels of OURS launched (bench 'gpu_launches')
         self._closed = False
+        self._gates: list = []
         self._epoch = 0                       # completed engine steps (the epoch-flag clock)
         # async bookkeeping
         self.version = 0
@@ -398,9 +399,11 @@ class DeviceEngine:
             done.record(cs)
         t3 = time.time()
         if self.size > 1 and self.mode == "ps" and self.rank != 0:
-            # the req.Wait() of mpi_comms.py:121 — a one-thread kernel on the compute stream
-            self.m.wait_flags(sig_base[self.rank], self.m.SIG_PARAMS_READY, 1, epoch, self.timeout_s)
-            self.launches += 1
+            if not self._gates:
+                # the req.Wait() of mpi_comms.py:121 — a one-thread kernel on the compute stream
+                self.m.wait_flags(sig_base[self.rank], self.m.SIG_PARAMS_READY, 1, epoch, self.timeout_s)
+                self.launches += 1
+            # else: the first forward GEMM (BcastLinear) acquires the flag inside its TMA producer
         else:
             cur.wait_event(done)
         data["comm_wait"] = time.time() - t3
@@ -483,6 +486,22 @@ class DeviceEngine:
         self._epoch += 1
         data["engine"] = "device"
         return data
+
+    # -------------------------------------------------------------- broadcast-gated GEMM support
+    def register_gate(self, layer) -> None:
+        """A :class:`~pytorch_ps_mpi_b200.ops.linear.BcastLinear` will acquire ``PARAMS_READY`` itself,
+        so worker ``step()`` stops queueing the separate wait kernel (the GEMM is the Wait)."""
+        self._gates.append(layer)
+
+    def gate(self):
+        """``(flag_ptr, epoch)`` the next forward must observe before reading broadcast weights."""
+        if self.size == 1 or self.mode != "ps" or self.rank == 0 or self._epoch == 0:
+            return 0, 0
+        return self.arena.local_ptr + self.off_signal + 8 * self.m.SIG_PARAMS_READY, self._epoch
+
+    def peer_param_ptr(self, param: torch.Tensor, rank: int) -> int:
+        """Address of ``param`` inside rank ``rank``'s parameter arena as mapped in this process."""
+        return self.arena.ptrs[rank] + (param.data_ptr() - self.arena.local_ptr)
 
     # ------------------------------------------------------------------------------ diagnostics
     def check(self):
