@@ -52,7 +52,11 @@ def test_gate_flag_blocks_until_published():
     sig = torch.zeros(512, dtype=torch.int64, device=dev)
     x = torch.randn(128, 64, device=dev).bfloat16()
     w = torch.zeros(128, 64, device=dev).bfloat16()
-    w_new = torch.randn(128, 64, device=dev).bfloat16()   # allocate BEFORE the spinning kernel: a cudaMalloc
+    # Everything the "server" side needs must exist BEFORE the spinning kernel starts: a cudaMalloc or the
+    # lazy loading of a not-yet-used kernel synchronises the context and would wait for the spinner.
+    m.signal([sig.data_ptr()], m.SIG_PARAMS_READY + 1, 1)
+    torch.empty(8, device=dev).copy_(torch.empty(8, device=dev))
+    w_new = torch.randn(128, 64, device=dev).bfloat16()
     side = torch.cuda.Stream()                             # would device-sync against it
     torch.cuda.synchronize()
     flag_ptr = sig.data_ptr() + 8 * m.SIG_PARAMS_READY
