@@ -77,9 +77,71 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   return y;
 }
 
+void check_nhwc(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.dim() == 4, name, " must be a 4-D CUDA bf16 tensor");
+  TORCH_CHECK(t.is_contiguous(at::MemoryFormat::ChannelsLast), name, " must be channels_last contiguous");
+}
+
+// y = act(BN(x) [+ res]);  returns (y, mean, rstd)
+std::vector<at::Tensor> bn_forward(const at::Tensor& x, c10::optional<at::Tensor> res, const at::Tensor& gamma,
+                                   const at::Tensor& beta, at::Tensor running_mean, at::Tensor running_var, double eps,
+                                   double momentum, bool relu, bool training) {
+  check_nhwc(x, "x");
+  const int C = (int)x.size(1);
+  TORCH_CHECK(C % 8 == 0 && C <= 2048, "channels must be a multiple of 8 and <= 2048");
+  const long long pixels = x.numel() / C;
+  const void* rp = nullptr;
+  if (res.has_value() && res->defined()) {
+    check_nhwc(*res, "residual");
+    TORCH_CHECK(res->sizes() == x.sizes(), "residual shape mismatch");
+    rp = res->data_ptr();
+  }
+  TORCH_CHECK(running_mean.scalar_type() == at::kFloat && running_var.scalar_type() == at::kFloat, "running stats must be fp32");
+  auto y = at::empty_like(x);
+  auto fo = x.options().dtype(at::kFloat);
+  auto scratch = at::empty({6 * C}, fo);   // sums[2C] | mean | rstd | scale | shift
+  float* sp = scratch.data_ptr<float>();
+  at::Tensor mean = scratch.narrow(0, 2 * C, C), rstd = scratch.narrow(0, 3 * C, C);
+  if (!training) {   // inference: scale/shift from the running statistics
+    auto r = (running_var + eps).rsqrt();
+    auto sc = gamma.to(at::kFloat) * r;
+    scratch.narrow(0, 4 * C, C).copy_(sc);
+    scratch.narrow(0, 5 * C, C).copy_(beta.to(at::kFloat) - running_mean * sc);
+  }
+  psb_bn_forward(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), rp, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                 sp, sp + 2 * C, sp + 3 * C, sp + 4 * C, sp + 5 * C, running_mean.data_ptr<float>(),
+                 running_var.data_ptr<float>(), pixels, C, (float)eps, (float)momentum, relu ? 1 : 0, training ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_bn_forward: ", cudaGetErrorString(e));
+  return {y, mean, rstd};
+}
+
+// returns (dx, dres or undefined, dgamma, dbeta)
+std::vector<at::Tensor> bn_backward(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& y, const at::Tensor& gamma,
+                                    const at::Tensor& mean, const at::Tensor& rstd, bool relu, bool has_res) {
+  check_nhwc(dy, "dy");
+  check_nhwc(x, "x");
+  const int C = (int)x.size(1);
+  const long long pixels = x.numel() / C;
+  auto dx = at::empty_like(x);
+  at::Tensor dres;
+  if (has_res) dres = at::empty_like(x);
+  auto dgamma = at::empty_like(gamma), dbeta = at::empty_like(gamma);
+  auto scratch = at::empty({5 * C}, x.options().dtype(at::kFloat));
+  float* sp = scratch.data_ptr<float>();
+  psb_bn_backward(c10::cuda::getCurrentCUDAStream().stream(), dy.data_ptr(), x.data_ptr(), relu ? y.data_ptr() : nullptr,
+                  gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), sp, sp + 2 * C, dx.data_ptr(),
+                  has_res ? dres.data_ptr() : nullptr, dgamma.data_ptr(), dbeta.data_ptr(), pixels, C, relu ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_bn_backward: ", cudaGetErrorString(e));
+  return {dx, dres, dgamma, dbeta};
+}
+
 }  // namespace
 
 void bind_gemm(py::module_& m) {
+  m.def("bn_forward", &bn_forward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) forward");
+  m.def("bn_backward", &bn_backward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");
   m.def("bcast_gemm", &bcast_gemm, py::arg("x"), py::arg("w_ptr"), py::arg("N"), py::arg("K"), py::arg("bias"),
         py::arg("relu"), py::arg("flag_ptr") = 0, py::arg("epoch") = 0, py::arg("timeout_s") = 30.0,
         "tcgen05/TMEM/TMA GEMM whose weight tiles are gated on the PS broadcast epoch flag");

@@ -87,3 +87,11 @@ struct BcastGemmArgs {
   unsigned long long timeout_ns;
 };
 void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms);
+
+// bn_kernels.cu — fused channels-last bf16 BatchNorm (+residual, +ReLU), forward and backward
+void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y, float* sums,
+                    float* mean, float* rstd, float* scale, float* shift, float* running_mean, float* running_var,
+                    long long pixels, int C, float eps, float momentum, int relu, int training);
+void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* y, const void* gamma, const float* mean,
+                     const float* rstd, float* sums, float* coef, void* dx, void* dres, void* dgamma, void* dbeta,
+                     long long pixels, int C, int relu);

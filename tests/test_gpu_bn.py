@@ -1,0 +1,89 @@
+"""Fused channels-last bf16 BatchNorm(+residual)(+ReLU) kernels vs a plain PyTorch fp32 reference."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pytorch_ps_mpi_b200.ops.batchnorm import FusedBatchNormAct2d
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, res, w, b, eps, relu):
+    xf = x.float()
+    mean = xf.mean((0, 2, 3), keepdim=True)
+    var = xf.var((0, 2, 3), unbiased=False, keepdim=True)
+    y = (xf - mean) * torch.rsqrt(var + eps) * w.float().view(1, -1, 1, 1) + b.float().view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res.float()
+    return F.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 28, 28), (4, 512, 7, 7), (3, 24, 5, 9), (2, 192, 14, 14), (16, 128, 16, 16)])
+@pytest.mark.parametrize("relu,has_res", [(False, False), (True, False), (True, True), (False, True)])
+def test_bn_forward_backward(shape, relu, has_res):
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    N, C, H, W = shape
+    bn = FusedBatchNormAct2d(C, relu=relu).to(dev).bfloat16()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C) + 0.5)
+        bn.bias.copy_(torch.randn(C) * 0.2)
+    assert bn.running_mean.dtype == torch.float32
+    x = (torch.randn(shape, device=dev) * 2 + 0.5).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    res = torch.randn(shape, device=dev).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True) if has_res else None
+    y = bn(x, res)
+    assert y.is_contiguous(memory_format=torch.channels_last) and y.dtype == torch.bfloat16
+    # fp32 reference through autograd
+    xr = x.detach().float().requires_grad_(True)
+    rr = res.detach().float().requires_grad_(True) if has_res else None
+    wr = bn.weight.detach().float().requires_grad_(True)
+    br = bn.bias.detach().float().requires_grad_(True)
+    z = _ref(xr, rr, wr, br, bn.eps, False)
+    yr = F.relu(z) if relu else z
+    assert torch.allclose(y.float(), yr, rtol=2e-2, atol=3e-2), (y.float() - yr).abs().max()
+    if relu:   # backward with the kernel's own mask: bf16 rounding may put an output on the other side of 0
+        yr = z * (y.detach().float() > 0).float()
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    y.backward(g.bfloat16().contiguous(memory_format=torch.channels_last))
+    scale = max(1.0, xr.grad.abs().max().item())
+    assert torch.allclose(x.grad.float(), xr.grad, rtol=5e-2, atol=5e-2 * scale), (x.grad.float() - xr.grad).abs().max()
+    if has_res:
+        assert torch.allclose(res.grad.float(), rr.grad, rtol=2e-2, atol=2e-2)
+    gs = max(1.0, wr.grad.abs().max().item())
+    assert torch.allclose(bn.weight.grad.float(), wr.grad, rtol=3e-2, atol=3e-2 * gs)
+    assert torch.allclose(bn.bias.grad.float(), br.grad, rtol=3e-2, atol=3e-2 * gs)
+    # running statistics follow nn.BatchNorm2d's rule
+    ref_bn = torch.nn.BatchNorm2d(C).to(dev)
+    ref_bn(x.detach().float())
+    assert torch.allclose(bn.running_mean, ref_bn.running_mean, rtol=1e-2, atol=1e-2)
+    assert torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-2, atol=1e-2)
+
+
+def test_bn_eval_mode_and_fallback():
+    dev = torch.device("cuda", 0)
+    bn = FusedBatchNormAct2d(32, relu=True).to(dev).bfloat16()
+    x = torch.randn(4, 32, 6, 6, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    bn.train()
+    bn(x)
+    bn.eval()
+    y = bn(x)
+    ref = F.relu(F.batch_norm(x.float(), bn.running_mean, bn.running_var, bn.weight.float(), bn.bias.float(), False, 0.1, bn.eps))
+    assert torch.allclose(y.float(), ref, rtol=2e-2, atol=2e-2)
+    # NCHW-contiguous input takes the stock path with the same semantics
+    y2 = bn(x.contiguous())
+    assert torch.allclose(y2.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+def test_resnet18_fused_matches_stock_math():
+    from pytorch_ps_mpi_b200 import models
+    import torchvision
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    m = models.resnet18(num_classes=10).to(dev).to(memory_format=torch.channels_last).bfloat16()
+    tv = torchvision.models.resnet18(num_classes=10).to(dev).to(memory_format=torch.channels_last)
+    tv.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+    x = torch.randn(8, 3, 64, 64, device=dev)
+    y = m(x.bfloat16().contiguous(memory_format=torch.channels_last))
+    yr = tv(x.contiguous(memory_format=torch.channels_last))
+    assert torch.allclose(y.float(), yr, rtol=0.1, atol=0.15), (y.float() - yr).abs().max()
