@@ -137,9 +137,35 @@ std::vector<at::Tensor> bn_backward(const at::Tensor& dy, const at::Tensor& x, c
   return {dx, dres, dgamma, dbeta};
 }
 
+std::vector<at::Tensor> maxpool_forward(const at::Tensor& x) {
+  check_nhwc(x, "x");
+  const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+  TORCH_CHECK(C % 8 == 0, "channels must be a multiple of 8");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  auto y = at::empty({N, C, OH, OW}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+  auto arg = at::empty({N, C, OH, OW}, x.options().dtype(at::kByte).memory_format(at::MemoryFormat::ChannelsLast));
+  psb_maxpool3x3s2_forward(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), y.data_ptr(), arg.data_ptr(), N, H, W, C);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_maxpool_fwd: ", cudaGetErrorString(e));
+  return {y, arg};
+}
+
+at::Tensor maxpool_backward(const at::Tensor& dy, const at::Tensor& arg, int64_t H, int64_t W) {
+  check_nhwc(dy, "dy");
+  const int N = (int)dy.size(0), C = (int)dy.size(1);
+  auto dx = at::empty({N, C, H, W}, dy.options().memory_format(at::MemoryFormat::ChannelsLast));
+  psb_maxpool3x3s2_backward(c10::cuda::getCurrentCUDAStream().stream(), dy.data_ptr(), arg.data_ptr(), dx.data_ptr(), N, (int)H,
+                            (int)W, C);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_maxpool_bwd: ", cudaGetErrorString(e));
+  return dx;
+}
+
 }  // namespace
 
 void bind_gemm(py::module_& m) {
+  m.def("maxpool_forward", &maxpool_forward, "channels-last bf16 3x3/s2/p1 max pool → (y, argpos)");
+  m.def("maxpool_backward", &maxpool_backward, "gather-style backward of maxpool_forward");
   m.def("bn_forward", &bn_forward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) forward");
   m.def("bn_backward", &bn_backward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");
   m.def("bcast_gemm", &bcast_gemm, py::arg("x"), py::arg("w_ptr"), py::arg("N"), py::arg("K"), py::arg("bias"),

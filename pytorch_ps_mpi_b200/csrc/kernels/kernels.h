@@ -95,3 +95,7 @@ void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* 
 void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* y, const void* gamma, const float* mean,
                      const float* rstd, float* sums, float* coef, void* dx, void* dres, void* dgamma, void* dbeta,
                      long long pixels, int C, int relu);
+
+// pool_kernels.cu — channels-last bf16 3x3/s2/p1 max pooling
+void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg, int N, int H, int W, int C);
+void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, void* dx, int N, int H, int W, int C);

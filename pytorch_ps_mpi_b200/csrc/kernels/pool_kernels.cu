@@ -1,0 +1,124 @@
+// 3x3 / stride-2 / pad-1 max pooling for channels-last bf16 activations, forward + backward.
+// ATen's max_pool_{forward,backward}_nhwc take 0.76 ms + 1.73 ms of a ResNet-18 step on B200
+// (profiles/resnet18_step_launches_n1.txt) for ~0.6 GB of traffic; these move 16 bytes per thread,
+// keep a 1-byte window position per output element for the backward, and the backward GATHERS
+// (each input pixel looks at the <= 4 windows covering it) so it needs no atomics and writes dx once.
+#include <cuda_bf16.h>
+
+#include "kernels.h"
+
+namespace {
+using namespace psb;
+
+struct PoolGeom {
+  int N, H, W, C, OH, OW, groups;
+};
+
+__global__ void __launch_bounds__(256) psb_maxpool_fwd(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                       uint8_t* __restrict__ arg, PoolGeom g) {
+  const long long total = (long long)g.N * g.OH * g.OW * g.groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % g.groups);
+    long long p = i / g.groups;
+    const int ow = (int)(p % g.OW);
+    p /= g.OW;
+    const int oh = (int)(p % g.OH);
+    const int n = (int)(p / g.OH);
+    float best[8];
+    uint32_t pos[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY, pos[j] = 255;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = oh * 2 - 1 + kh;
+      if (h < 0 || h >= g.H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = ow * 2 - 1 + kw;
+        if (w < 0 || w >= g.W) continue;
+        float v[8];
+        uint4 raw = *reinterpret_cast<const uint4*>(x + (((long long)n * g.H + h) * g.W + w) * g.C + cg * 8);
+        unpack_bf16x8(raw, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j]) {          // strictly greater: the first maximum wins ties (ATen's rule)
+            best[j] = v[j];
+            pos[j] = kh * 3 + kw;
+          }
+      }
+    }
+    const long long o = (((long long)n * g.OH + oh) * g.OW + ow) * g.C + cg * 8;
+    *reinterpret_cast<uint4*>(y + o) = make_uint4(pack_bf16x2(best[0], best[1]), pack_bf16x2(best[2], best[3]),
+                                                  pack_bf16x2(best[4], best[5]), pack_bf16x2(best[6], best[7]));
+    *reinterpret_cast<uint2*>(arg + o) =
+        make_uint2(pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24), pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24));
+  }
+}
+
+__global__ void __launch_bounds__(256) psb_maxpool_bwd(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ arg,
+                                                       __nv_bfloat16* __restrict__ dx, PoolGeom g) {
+  const long long total = (long long)g.N * g.H * g.W * g.groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % g.groups);
+    long long p = i / g.groups;
+    const int w = (int)(p % g.W);
+    p /= g.W;
+    const int h = (int)(p % g.H);
+    const int n = (int)(p / g.H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // windows covering (h, w): oh*2-1 <= h <= oh*2+1
+    const int oh0 = h >> 1 /* floor(h/2) covers h = 2oh or 2oh+1 */, ow0 = w >> 1;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int oh = oh0 + a;
+      const int kh = h - (oh * 2 - 1);
+      if (oh >= g.OH || kh < 0 || kh > 2) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ow = ow0 + b;
+        const int kw = w - (ow * 2 - 1);
+        if (ow >= g.OW || kw < 0 || kw > 2) continue;
+        const long long o = (((long long)n * g.OH + oh) * g.OW + ow) * g.C + cg * 8;
+        const uint2 pr = *reinterpret_cast<const uint2*>(arg + o);
+        float d[8];
+        uint4 raw = *reinterpret_cast<const uint4*>(dy + o);
+        unpack_bf16x8(raw, d);
+        const uint32_t want = (uint32_t)(kh * 3 + kw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t pj = ((j < 4 ? pr.x : pr.y) >> (8 * (j & 3))) & 0xffu;
+          if (pj == want) acc[j] += d[j];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + (((long long)n * g.H + h) * g.W + w) * g.C + cg * 8) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+int pool_grid(long long total) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long want = (total + 255) / 256;
+  long long cap = (long long)sms * 16;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg, int N, int H, int W, int C) {
+  PoolGeom g{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
+  const long long total = (long long)N * g.OH * g.OW * g.groups;
+  psb_maxpool_fwd<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                                                   reinterpret_cast<uint8_t*>(arg), g);
+}
+
+void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, void* dx, int N, int H, int W, int C) {
+  PoolGeom g{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
+  const long long total = (long long)N * H * W * g.groups;
+  psb_maxpool_bwd<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const uint8_t*>(arg),
+                                                   reinterpret_cast<__nv_bfloat16*>(dx), g);
+}

@@ -281,8 +281,103 @@ __device__ __forceinline__ void decode_dense(const uint4& v0, const uint4& v1, f
   }
 }
 
-template <int KIND, int WIRE, int OPT>
-__global__ void __launch_bounds__(PSB_THREADS, 3) psb_update_kernel(const __grid_constant__ UpdateArgs a) {
+// Optimizer + publication for ONE tile whose summed gradient is already in `acc` (and whose state
+// `w`, `b0`, `b1`, `b2` has been loaded): the epilogue shared by every gather flavour.
+template <int OPT>
+__device__ __forceinline__ void apply_and_publish(const UpdateArgs& a, const TileInfo& ti, size_t e0, float inv_count,
+                                                  const float* acc, float* w, float* m, float* v, float* vm) {
+  const GroupHyper h = a.groups[ti.group];
+  float g[PSB_EPT];
+#pragma unroll
+  for (int j = 0; j < PSB_EPT; ++j) g[j] = acc[j] * inv_count;
+  if (h.weight_decay != 0.f) {
+#pragma unroll
+    for (int j = 0; j < PSB_EPT; ++j) g[j] = fmaf(h.weight_decay, w[j], g[j]);
+  }
+  if constexpr (OPT == OPT_SGD) {   // /root/reference/ps.py:197-214
+    if (h.momentum != 0.f) {
+#pragma unroll
+      for (int j = 0; j < PSB_EPT; ++j) {
+        m[j] = h.first_step ? g[j] : fmaf(h.momentum, m[j], (1.f - h.dampening) * g[j]);
+        g[j] = h.nesterov ? fmaf(h.momentum, m[j], g[j]) : m[j];
+      }
+      float4* bp = reinterpret_cast<float4*>(a.buf0 + e0);
+      bp[0] = make_float4(m[0], m[1], m[2], m[3]);
+      bp[1] = make_float4(m[4], m[5], m[6], m[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < PSB_EPT; ++j) w[j] = fmaf(-h.lr, g[j], w[j]);
+  } else {                          // /root/reference/ps.py:218-261
+#pragma unroll
+    for (int j = 0; j < PSB_EPT; ++j) {
+      m[j] = fmaf(h.beta1, m[j], (1.f - h.beta1) * g[j]);
+      v[j] = fmaf(h.beta2, v[j], (1.f - h.beta2) * g[j] * g[j]);
+      float den_src = v[j];
+      if (h.amsgrad) {
+        vm[j] = fmaxf(vm[j], v[j]);
+        den_src = vm[j];
+      }
+      const float denom = __fsqrt_rn(den_src) + h.eps;
+      w[j] = fmaf(-h.step_size, __fdiv_rn(m[j], denom), w[j]);
+    }
+    float4* mp = reinterpret_cast<float4*>(a.buf0 + e0);
+    mp[0] = make_float4(m[0], m[1], m[2], m[3]);
+    mp[1] = make_float4(m[4], m[5], m[6], m[7]);
+    float4* vp = reinterpret_cast<float4*>(a.buf1 + e0);
+    vp[0] = make_float4(v[0], v[1], v[2], v[3]);
+    vp[1] = make_float4(v[4], v[5], v[6], v[7]);
+    if (h.amsgrad) {
+      float4* xp = reinterpret_cast<float4*>(a.buf2 + e0);
+      xp[0] = make_float4(vm[0], vm[1], vm[2], vm[3]);
+      xp[1] = make_float4(vm[4], vm[5], vm[6], vm[7]);
+    }
+  }
+  if (a.master != nullptr) {
+    float4* wp = reinterpret_cast<float4*>(a.master + e0);
+    wp[0] = make_float4(w[0], w[1], w[2], w[3]);
+    wp[1] = make_float4(w[4], w[5], w[6], w[7]);
+  }
+  // publish the fresh parameter tile (the Ibcast of mpi_comms.py:132)
+  uint4 out[2];
+  const int nv = pack8(a.param_dt, w, out);
+  const size_t pbytes = e0 * (a.param_dt == DT_F32 ? 4 : 2);
+  if (a.bcast == BCAST_MULTICAST) {
+    uint8_t* p = reinterpret_cast<uint8_t*>(a.param_mc) + pbytes;
+    multimem_st_v4(p, out[0]);
+    if (nv == 2) multimem_st_v4(p + 16, out[1]);
+  } else if (a.bcast == BCAST_UNICAST) {
+    for (int r = 0; r < a.world; ++r) {
+      uint8_t* p = reinterpret_cast<uint8_t*>(a.param_dst[r]) + pbytes;
+      st_sys_v4(p, out[0]);
+      if (nv == 2) st_sys_v4(p + 16, out[1]);
+    }
+  } else {
+    uint8_t* p = reinterpret_cast<uint8_t*>(a.param_local) + pbytes;
+    st_v4(p, out[0]);
+    if (nv == 2) st_v4(p + 16, out[1]);
+  }
+}
+
+// Issue the (local, independent) optimizer-state loads for one tile: they fly while the peer loads do.
+template <int OPT>
+__device__ __forceinline__ void load_state(const UpdateArgs& a, const TileInfo& ti, size_t e0, float* w, float* m, float* v,
+                                           float* vm) {
+  if (a.master != nullptr) load8_local(a.master, DT_F32, e0, w);
+  else load8_local(a.param_local, a.param_dt, e0, w);
+  const GroupHyper& h = a.groups[ti.group];
+  if constexpr (OPT == OPT_SGD) {
+    if (h.momentum != 0.f) load8_local(a.buf0, DT_F32, e0, m);
+  } else {
+    load8_local(a.buf0, DT_F32, e0, m);
+    load8_local(a.buf1, DT_F32, e0, v);
+    if (h.amsgrad) load8_local(a.buf2, DT_F32, e0, vm);
+  }
+}
+
+// U = tiles a thread keeps in flight.  Few ranks → few peer loads per tile → take more tiles at once so
+// enough bytes are outstanding to cover the ~2 µs NVLink round trip (B300_MICROARCH: peer LDG ≈ 1.8-2k cycles).
+template <int KIND, int WIRE, int OPT, int U>
+__global__ void __launch_bounds__(PSB_THREADS, U == 1 ? 3 : 2) psb_update_kernel(const __grid_constant__ UpdateArgs a) {
   __shared__ float s_acc[KIND == KIND_TOPK ? PSB_TILE : 1];
   __shared__ int s_flag;
   const int tid = threadIdx.x;
@@ -293,7 +388,7 @@ __global__ void __launch_bounds__(PSB_THREADS, 3) psb_update_kernel(const __grid
     contrib = (uint32_t)a.select_out[0];
     ack = contrib;
     const uint32_t cnt = (uint32_t)a.select_out[1];
-    if (cnt == 0) return;          // the select kernel timed out
+    if (cnt == 0) return;          // nothing to apply (all workers finished, or the select timed out)
     if (a.average_dynamic) inv_count = 1.f / (float)cnt;
   }
 
@@ -305,18 +400,15 @@ __global__ void __launch_bounds__(PSB_THREADS, 3) psb_update_kernel(const __grid
     if (!__syncthreads_and(ok)) return;
   }
 
-  constexpr int CH = 4;   // ranks whose loads are in flight together
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const TileInfo ti = a.tiles[tile];
-    if (a.active != nullptr && a.active[ti.param] == 0) continue;
-    const size_t e0 = (size_t)tile * PSB_TILE + tid * PSB_EPT;
-    const size_t tile_off = (size_t)tile * a.bytes_per_tile;
-    float acc[PSB_EPT];
-#pragma unroll
-    for (int j = 0; j < PSB_EPT; ++j) acc[j] = 0.f;
-
-    // ---- 2. gather + decode + sum (fixed rank order → deterministic) ----
-    if constexpr (KIND == KIND_TOPK) {
+  if constexpr (KIND == KIND_TOPK) {
+    // ---- block-wise top-k: scatter-add every rank's (index, value) entries into a shared-memory tile ----
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const TileInfo ti = a.tiles[tile];
+      if (a.active != nullptr && a.active[ti.param] == 0) continue;
+      const size_t e0 = (size_t)tile * PSB_TILE + tid * PSB_EPT;
+      const size_t tile_off = (size_t)tile * a.bytes_per_tile;
+      float w[PSB_EPT], m[PSB_EPT], v[PSB_EPT], vm[PSB_EPT];
+      load_state<OPT>(a, ti, e0, w, m, v, vm);
       for (int j = tid; j < PSB_TILE; j += PSB_THREADS) s_acc[j] = 0.f;
       __syncthreads();
       for (int r = 0; r < a.world; ++r) {
@@ -326,156 +418,118 @@ __global__ void __launch_bounds__(PSB_THREADS, 3) psb_update_kernel(const __grid
           uint32_t idx;
           float val;
           if constexpr (WIRE == WIRE_BF16) {
-            uint32_t w;
-            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(w) : "l"(base + 4 * (size_t)p) : "memory");
-            idx = w >> 16;
-            val = __uint_as_float(w << 16);
+            uint32_t wd;
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(wd) : "l"(base + 4 * (size_t)p) : "memory");
+            idx = wd >> 16;
+            val = __uint_as_float(wd << 16);
           } else {
-            uint2 w = ld_sys_v2(base + 8 * (size_t)p);
-            idx = w.x;
-            val = __uint_as_float(w.y);
+            uint2 wd = ld_sys_v2(base + 8 * (size_t)p);
+            idx = wd.x;
+            val = __uint_as_float(wd.y);
           }
           if (idx < PSB_TILE) s_acc[idx] += val;   // indices are unique within one rank's tile
         }
-        __syncthreads();
+        __syncthreads();                            // rank order is the summation order
       }
+      float acc[PSB_EPT];
 #pragma unroll
       for (int j = 0; j < PSB_EPT; ++j) acc[j] = s_acc[tid * PSB_EPT + j];
       __syncthreads();
-    } else {
-      bool done = false;
-      if constexpr (KIND == KIND_DENSE && (WIRE == WIRE_F32 || WIRE == WIRE_BF16 || WIRE == WIRE_F16)) {
-        if (a.reduce == REDUCE_NVLS) {   // the switch adds all ranks: PS ingress is 1x, not (N-1)x
-          const uint8_t* p = reinterpret_cast<const uint8_t*>(a.wire_mc) + tile_off +
-                             (size_t)tid * PSB_EPT * wire_elem_bytes(WIRE);
-          if constexpr (WIRE == WIRE_F32) {
-            uint4 v0 = multimem_ld_reduce_f32x4(p), v1 = multimem_ld_reduce_f32x4(p + 16);
-            decode_dense<WIRE_F32>(v0, v1, acc);
-          } else if constexpr (WIRE == WIRE_BF16) {
-            uint4 v0 = multimem_ld_reduce_bf16x8(p);
-            unpack_bf16x8(v0, acc);
-          } else {
-            uint4 v0 = multimem_ld_reduce_f16x8(p);
-            unpack_f16x8(v0, acc);
-          }
-          done = true;
-        }
-      }
-      if (!done) {
-        for (int r0 = 0; r0 < a.world; r0 += CH) {
-          uint4 v0[CH], v1[CH];
-          float sc[CH];
+      apply_and_publish<OPT>(a, ti, e0, inv_count, acc, w, m, v, vm);
+    }
+  } else {
+    // ---- dense / scaled wires: U tiles x up-to-CH ranks of 16-byte peer loads in flight per thread ----
+    constexpr int CH = 4;
+    const bool nvls = (KIND == KIND_DENSE && (WIRE == WIRE_F32 || WIRE == WIRE_BF16 || WIRE == WIRE_F16)) &&
+                      a.reduce == REDUCE_NVLS;
+    for (int tile0 = blockIdx.x; tile0 < a.ntiles; tile0 += U * gridDim.x) {
+      TileInfo ti[U];
+      bool live[U];
+      float acc[U][PSB_EPT], w[1][PSB_EPT], m[1][PSB_EPT], v[1][PSB_EPT], vm[1][PSB_EPT];
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const int r = r0 + c;
-            sc[c] = 1.f;
-            if (r < a.world && (contrib >> r & 1u)) {
-              issue_dense<WIRE>(a.wire[r], tile_off, v0[c], v1[c]);
-              if constexpr (KIND == KIND_SCALED) sc[c] = ld_sys_f32(a.scales[r] + ti.param);
+      for (int u = 0; u < U; ++u) {
+        const int tile = tile0 + u * gridDim.x;
+        live[u] = tile < a.ntiles;
+        if (live[u]) {
+          ti[u] = a.tiles[tile];
+          if (a.active != nullptr && a.active[ti[u].param] == 0) live[u] = false;
+        }
+#pragma unroll
+        for (int j = 0; j < PSB_EPT; ++j) acc[u][j] = 0.f;
+      }
+      // U == 1: local optimizer state first — independent of the gather, so it overlaps the NVLink latency.
+      // U > 1: the register budget goes to peer loads in flight instead; state is loaded after the sum.
+      if constexpr (U == 1) {
+        if (live[0]) load_state<OPT>(a, ti[0], (size_t)tile0 * PSB_TILE + tid * PSB_EPT, w[0], m[0], v[0], vm[0]);
+      }
+
+      if (nvls) {
+        if constexpr (KIND == KIND_DENSE && (WIRE == WIRE_F32 || WIRE == WIRE_BF16 || WIRE == WIRE_F16)) {
+          // the switch adds all ranks: server ingress is 1x the vector, not (N-1)x
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(a.wire_mc) + (size_t)(tile0 + u * gridDim.x) * a.bytes_per_tile +
+                               (size_t)tid * PSB_EPT * wire_elem_bytes(WIRE);
+            if constexpr (WIRE == WIRE_F32) {
+              uint4 v0 = multimem_ld_reduce_f32x4(p), v1 = multimem_ld_reduce_f32x4(p + 16);
+              decode_dense<WIRE_F32>(v0, v1, acc[u]);
+            } else if constexpr (WIRE == WIRE_BF16) {
+              uint4 v0 = multimem_ld_reduce_bf16x8(p);
+              unpack_bf16x8(v0, acc[u]);
+            } else {
+              uint4 v0 = multimem_ld_reduce_f16x8(p);
+              unpack_f16x8(v0, acc[u]);
             }
           }
+        }
+      } else {
+        for (int r0 = 0; r0 < a.world; r0 += CH) {
+          uint4 v0[U][CH], v1[U][CH];
+          float sc[U][CH];
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const int r = r0 + c;
-            if (r < a.world && (contrib >> r & 1u)) {
-              float f[PSB_EPT];
-              decode_dense<WIRE>(v0[c], v1[c], f);
+          for (int u = 0; u < U; ++u)
 #pragma unroll
-              for (int j = 0; j < PSB_EPT; ++j) {
-                if constexpr (KIND == KIND_SCALED) acc[j] += f[j] * sc[c];
-                else acc[j] += f[j];
+            for (int c = 0; c < CH; ++c) {
+              const int r = r0 + c;
+              sc[u][c] = 1.f;
+              if (live[u] && r < a.world && (contrib >> r & 1u)) {
+                issue_dense<WIRE>(a.wire[r], (size_t)(tile0 + u * gridDim.x) * a.bytes_per_tile, v0[u][c], v1[u][c]);
+                if constexpr (KIND == KIND_SCALED) sc[u][c] = ld_sys_f32(a.scales[r] + ti[u].param);
               }
             }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {       // fixed rank order → deterministic fp32 sum
+              const int r = r0 + c;
+              if (live[u] && r < a.world && (contrib >> r & 1u)) {
+                float f[PSB_EPT];
+                decode_dense<WIRE>(v0[u][c], v1[u][c], f);
+#pragma unroll
+                for (int j = 0; j < PSB_EPT; ++j) {
+                  if constexpr (KIND == KIND_SCALED) acc[u][j] += f[j] * sc[u][c];
+                  else acc[u][j] += f[j];
+                }
+              }
+            }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (live[u]) {
+          const size_t e0 = (size_t)(tile0 + u * gridDim.x) * PSB_TILE + tid * PSB_EPT;
+          if constexpr (U == 1) {
+            apply_and_publish<OPT>(a, ti[u], e0, inv_count, acc[u], w[0], m[0], v[0], vm[0]);
+          } else {
+            load_state<OPT>(a, ti[u], e0, w[0], m[0], v[0], vm[0]);
+            apply_and_publish<OPT>(a, ti[u], e0, inv_count, acc[u], w[0], m[0], v[0], vm[0]);
           }
         }
-      }
-    }
-
-    // ---- 3. optimizer on fp32 state (ps.py:197-214 SGD, ps.py:218-261 Adam) ----
-    const GroupHyper h = a.groups[ti.group];
-    float w[PSB_EPT];
-    if (a.master != nullptr) load8_local(a.master, DT_F32, e0, w);
-    else load8_local(a.param_local, a.param_dt, e0, w);
-    float g[PSB_EPT];
-#pragma unroll
-    for (int j = 0; j < PSB_EPT; ++j) g[j] = acc[j] * inv_count;
-    if (h.weight_decay != 0.f) {
-#pragma unroll
-      for (int j = 0; j < PSB_EPT; ++j) g[j] = fmaf(h.weight_decay, w[j], g[j]);
-    }
-    if constexpr (OPT == OPT_SGD) {
-      if (h.momentum != 0.f) {
-        float b[PSB_EPT];
-        load8_local(a.buf0, DT_F32, e0, b);
-#pragma unroll
-        for (int j = 0; j < PSB_EPT; ++j) {
-          b[j] = h.first_step ? g[j] : fmaf(h.momentum, b[j], (1.f - h.dampening) * g[j]);
-          g[j] = h.nesterov ? fmaf(h.momentum, b[j], g[j]) : b[j];
-        }
-        float4* bp = reinterpret_cast<float4*>(a.buf0 + e0);
-        bp[0] = make_float4(b[0], b[1], b[2], b[3]);
-        bp[1] = make_float4(b[4], b[5], b[6], b[7]);
-      }
-#pragma unroll
-      for (int j = 0; j < PSB_EPT; ++j) w[j] = fmaf(-h.lr, g[j], w[j]);
-    } else {
-      float m[PSB_EPT], v[PSB_EPT];
-      load8_local(a.buf0, DT_F32, e0, m);
-      load8_local(a.buf1, DT_F32, e0, v);
-      float vm[PSB_EPT];
-      if (h.amsgrad) load8_local(a.buf2, DT_F32, e0, vm);
-#pragma unroll
-      for (int j = 0; j < PSB_EPT; ++j) {
-        m[j] = fmaf(h.beta1, m[j], (1.f - h.beta1) * g[j]);
-        v[j] = fmaf(h.beta2, v[j], (1.f - h.beta2) * g[j] * g[j]);
-        float den_src = v[j];
-        if (h.amsgrad) {
-          vm[j] = fmaxf(vm[j], v[j]);
-          den_src = vm[j];
-        }
-        const float denom = __fsqrt_rn(den_src) + h.eps;
-        w[j] = fmaf(-h.step_size, __fdiv_rn(m[j], denom), w[j]);
-      }
-      float4* mp = reinterpret_cast<float4*>(a.buf0 + e0);
-      mp[0] = make_float4(m[0], m[1], m[2], m[3]);
-      mp[1] = make_float4(m[4], m[5], m[6], m[7]);
-      float4* vp = reinterpret_cast<float4*>(a.buf1 + e0);
-      vp[0] = make_float4(v[0], v[1], v[2], v[3]);
-      vp[1] = make_float4(v[4], v[5], v[6], v[7]);
-      if (h.amsgrad) {
-        float4* xp = reinterpret_cast<float4*>(a.buf2 + e0);
-        xp[0] = make_float4(vm[0], vm[1], vm[2], vm[3]);
-        xp[1] = make_float4(vm[4], vm[5], vm[6], vm[7]);
-      }
-    }
-    if (a.master != nullptr) {
-      float4* wp = reinterpret_cast<float4*>(a.master + e0);
-      wp[0] = make_float4(w[0], w[1], w[2], w[3]);
-      wp[1] = make_float4(w[4], w[5], w[6], w[7]);
-    }
-
-    // ---- 4. publish the fresh parameter tile (the Ibcast of mpi_comms.py:132) ----
-    uint4 out[2];
-    const int nv = pack8(a.param_dt, w, out);
-    const size_t pbytes = e0 * (a.param_dt == DT_F32 ? 4 : 2);
-    if (a.bcast == BCAST_MULTICAST) {
-      uint8_t* p = reinterpret_cast<uint8_t*>(a.param_mc) + pbytes;
-      multimem_st_v4(p, out[0]);
-      if (nv == 2) multimem_st_v4(p + 16, out[1]);
-    } else if (a.bcast == BCAST_UNICAST) {
-      for (int r = 0; r < a.world; ++r) {
-        uint8_t* p = reinterpret_cast<uint8_t*>(a.param_dst[r]) + pbytes;
-        st_sys_v4(p, out[0]);
-        if (nv == 2) st_sys_v4(p + 16, out[1]);
-      }
-    } else {
-      uint8_t* p = reinterpret_cast<uint8_t*>(a.param_local) + pbytes;
-      st_v4(p, out[0]);
-      if (nv == 2) st_v4(p + 16, out[1]);
     }
   }
 
-  // ---- 5. completion: the last CTA raises the epoch flags ----
+  // ---- completion: the last CTA raises the epoch flags ----
   __syncthreads();
   if (tid == 0) {
     __threadfence_system();
@@ -593,7 +647,14 @@ __global__ void psb_select_kernel(const uint64_t* signal_local, uint64_t* consum
 
 template <int KIND, int WIRE, int OPT>
 void launch_update_t(cudaStream_t s, const UpdateArgs& a, int grid) {
-  psb_update_kernel<KIND, WIRE, OPT><<<grid, PSB_THREADS, 0, s>>>(a);
+  if constexpr (KIND == KIND_TOPK) {
+    psb_update_kernel<KIND, WIRE, OPT, 1><<<grid, PSB_THREADS, 0, s>>>(a);
+  } else {
+    // fewer ranks → fewer peer loads per tile → more tiles in flight per thread
+    const int tiles_per_cta = (a.ntiles + grid - 1) / grid;
+    if (a.world <= 4 && tiles_per_cta >= 2) psb_update_kernel<KIND, WIRE, OPT, 2><<<grid, PSB_THREADS, 0, s>>>(a);
+    else psb_update_kernel<KIND, WIRE, OPT, 1><<<grid, PSB_THREADS, 0, s>>>(a);
+  }
 }
 template <int KIND, int WIRE>
 void launch_update_o(cudaStream_t s, int opt, const UpdateArgs& a, int grid) {

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from ..ops.batchnorm import FusedBatchNormAct2d
+from ..ops.pooling import FusedMaxPool2d
 
 
 def _conv3x3(i, o, stride=1):
@@ -66,7 +67,7 @@ class ResNet(nn.Module):
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = FusedBatchNormAct2d(64, relu=True)
-        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.maxpool = FusedMaxPool2d(3, 2, 1)
         self.layer1 = self._make_layer(block, 64, layers[0])
         self.layer2 = self._make_layer(block, 128, layers[1], 2)
         self.layer3 = self._make_layer(block, 256, layers[2], 2)

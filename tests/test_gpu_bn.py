@@ -87,3 +87,19 @@ def test_resnet18_fused_matches_stock_math():
     y = m(x.bfloat16().contiguous(memory_format=torch.channels_last))
     yr = tv(x.contiguous(memory_format=torch.channels_last))
     assert torch.allclose(y.float(), yr, rtol=0.1, atol=0.15), (y.float() - yr).abs().max()
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 112, 112), (3, 16, 7, 9), (2, 8, 1, 1)])
+def test_maxpool_matches_torch(shape):
+    from pytorch_ps_mpi_b200.ops.pooling import FusedMaxPool2d
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    x = torch.randn(shape, device=dev).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xr = x.detach().float().requires_grad_(True)
+    y = FusedMaxPool2d()(x)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    assert y.shape == yr.shape and torch.equal(y.float(), yr)
+    g = torch.randn_like(yr)
+    y.backward(g.bfloat16().contiguous(memory_format=torch.channels_last))
+    yr.backward(g.bfloat16().float())
+    assert torch.allclose(x.grad.float(), xr.grad, rtol=1e-2, atol=1e-2)
