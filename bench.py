@@ -84,8 +84,10 @@ def build(args, device, ps):
         mean = torch.tensor([0.485, 0.456, 0.406], device=device).view(1, 3, 1, 1) * 255
         std = torch.tensor([0.229, 0.224, 0.225], device=device).view(1, 3, 1, 1) * 255
 
+        from pytorch_ps_mpi_b200.ops.preprocess import normalize_pad8
+
         def loss_fn(x, y):
-            xb = ((x.float() - mean) / std).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            xb = normalize_pad8(x)          # uint8 NCHW → normalised bf16 NHWC(8): one kernel of ours
             return torch.nn.functional.cross_entropy(model(xb).float(), y)
         cfg = {"global_batch": None, "image": "3x224x224 uint8"}
     elif args.model == "mlp":

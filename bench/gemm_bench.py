@@ -47,10 +47,11 @@ def main():
     for name, M, N, K in shapes:
         x = (torch.randn(M, K, device=dev) / K ** 0.5).bfloat16()
         w = torch.randn(N, K, device=dev).bfloat16()
-        t_ours = bench(lambda: bcast_linear(x, w), flush)
+        t_ours = bench(lambda: bcast_linear(x, w, variant=2), flush)
+        t_1cta = bench(lambda: bcast_linear(x, w, variant=1), flush)
         t_lib = bench(lambda: torch.nn.functional.linear(x, w), flush)
         fl = 2.0 * M * N * K
-        print(json.dumps({"shape": name, "M": M, "N": N, "K": K, "ours_us": t_ours * 1e6, "cublas_us": t_lib * 1e6,
+        print(json.dumps({"shape": name, "M": M, "N": N, "K": K, "ours_us": t_ours * 1e6, "ours_1cta_us": t_1cta * 1e6, "cublas_us": t_lib * 1e6,
                           "ours_tflops": fl / t_ours / 1e12, "cublas_tflops": fl / t_lib / 1e12,
                           "ours_frac_of_peak": fl / t_ours / 1e12 / peak, "peak_tflops": peak, "peak_source": how}), flush=True)
 

@@ -45,15 +45,17 @@ CUtensorMap make_map(uint64_t ptr, int64_t rows, int64_t cols, int64_t row_strid
 // weight (this rank's parameter arena, or the server's arena over NVLink).  `flag_ptr` (optional) is
 // the SIG_PARAMS_READY slot the TMA producer acquires before its first weight load.
 at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K, c10::optional<at::Tensor> bias, bool relu,
-                      uint64_t flag_ptr, uint64_t epoch, double timeout_s) {
+                      uint64_t flag_ptr, uint64_t epoch, double timeout_s, int variant) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous(), "x must be [M,K] bf16 contiguous");
   TORCH_CHECK(x.size(1) == K && K % 8 == 0, "K mismatch / K must be a multiple of 8");
   TORCH_CHECK(reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0 && w_ptr % 16 == 0, "operands must be 16-byte aligned");
   const int64_t M = x.size(0);
   auto y = at::empty({M, N}, x.options());
   if (M == 0) return y;
+  // cta_group::2 (two SMs per 256x256 tile) whenever there are at least 256 rows; `variant` forces it (tests)
+  const bool two_cta = variant == 2 || (variant == 0 && M >= 256);
   CUtensorMap ma = make_map(reinterpret_cast<uint64_t>(x.data_ptr()), M, K, K, 128);
-  CUtensorMap mb = make_map(w_ptr, N, K, K, 128);
+  CUtensorMap mb = make_map(w_ptr, N, K, K, two_cta ? 128 : 256);   // B box: half tile per CTA (2-CTA) or BN rows
   BcastGemmArgs a{};
   a.tmap_a = &ma;
   a.tmap_b = &mb;
@@ -69,6 +71,7 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   a.ready_epoch = epoch;
   a.M = (int)M, a.N = (int)N, a.K = (int)K;
   a.relu = relu ? 1 : 0;
+  a.two_cta = two_cta ? 1 : 0;
   a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   psb_launch_bcast_gemm(c10::cuda::getCurrentCUDAStream().stream(), a, sms);
@@ -161,15 +164,32 @@ at::Tensor maxpool_backward(const at::Tensor& dy, const at::Tensor& arg, int64_t
   return dx;
 }
 
+// uint8 [N,3,H,W] (NCHW) → bf16 [N,8,H,W] channels_last, (x - mean) / std, channels 3..7 zero
+at::Tensor normalize_pad8(const at::Tensor& x, std::vector<double> mean, std::vector<double> std) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kByte && x.dim() == 4 && x.size(1) == 3 && x.is_contiguous(),
+              "x must be a contiguous uint8 [N,3,H,W] CUDA tensor");
+  TORCH_CHECK(mean.size() == 3 && std.size() == 3, "mean/std need 3 entries");
+  const int N = (int)x.size(0);
+  const long long HW = x.size(2) * x.size(3);
+  auto y = at::empty({N, 8, x.size(2), x.size(3)}, x.options().dtype(at::kBFloat16).memory_format(at::MemoryFormat::ChannelsLast));
+  float m[3] = {(float)mean[0], (float)mean[1], (float)mean[2]};
+  float is[3] = {(float)(1.0 / std[0]), (float)(1.0 / std[1]), (float)(1.0 / std[2])};
+  psb_normalize_pad8_launch(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), y.data_ptr(), m, is, N, HW);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_normalize_pad8: ", cudaGetErrorString(e));
+  return y;
+}
+
 }  // namespace
 
 void bind_gemm(py::module_& m) {
+  m.def("normalize_pad8", &normalize_pad8, "uint8 NCHW image → normalised bf16 NHWC padded to 8 channels");
   m.def("maxpool_forward", &maxpool_forward, "channels-last bf16 3x3/s2/p1 max pool → (y, argpos)");
   m.def("maxpool_backward", &maxpool_backward, "gather-style backward of maxpool_forward");
   m.def("bn_forward", &bn_forward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) forward");
   m.def("bn_backward", &bn_backward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");
   m.def("bcast_gemm", &bcast_gemm, py::arg("x"), py::arg("w_ptr"), py::arg("N"), py::arg("K"), py::arg("bias"),
-        py::arg("relu"), py::arg("flag_ptr") = 0, py::arg("epoch") = 0, py::arg("timeout_s") = 30.0,
+        py::arg("relu"), py::arg("flag_ptr") = 0, py::arg("epoch") = 0, py::arg("timeout_s") = 30.0, py::arg("variant") = 0,
         "tcgen05/TMEM/TMA GEMM whose weight tiles are gated on the PS broadcast epoch flag");
   m.def("bcast_gemm_smem_bytes", &psb_bcast_gemm_smem_bytes);
 }

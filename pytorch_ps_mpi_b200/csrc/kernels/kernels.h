@@ -84,6 +84,7 @@ struct BcastGemmArgs {
   uint64_t ready_epoch;
   int32_t M, N, K;
   int32_t relu;
+  int32_t two_cta;      // 1 → cta_group::2 kernel (256x256 tiles per CTA pair; B box = 128 rows)
   unsigned long long timeout_ns;
 };
 void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms);
@@ -99,3 +100,4 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
 // pool_kernels.cu — channels-last bf16 3x3/s2/p1 max pooling
 void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg, int N, int H, int W, int C);
 void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, void* dx, int N, int H, int W, int C);
+void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW);

@@ -122,3 +122,27 @@ void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, 
   psb_maxpool_bwd<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const uint8_t*>(arg),
                                                    reinterpret_cast<__nv_bfloat16*>(dx), g);
 }
+
+// ---- input pre-processing: uint8 NCHW image → normalised bf16 NHWC padded to 8 channels --------------
+// One pass instead of ATen's float() / sub / div / to(bf16) / contiguous(channels_last) chain, and the
+// 8-channel (16-byte) pixel lets cuDNN run the 7x7 stem convolution on its aligned tensor-core kernels
+// (the 3-channel stem was 23 % of the step: profiles/resnet18_step_launches_fused.txt).
+namespace {
+__global__ void __launch_bounds__(256) psb_normalize_pad8(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          float m0, float m1, float m2, float s0, float s1, float s2, int N,
+                                                          long long HW) {
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i % HW;
+    const uint8_t* base = x + n * 3 * HW + p;
+    const float a = ((float)base[0] - m0) * s0, b = ((float)base[HW] - m1) * s1, c = ((float)base[2 * HW] - m2) * s2;
+    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(psb::pack_bf16x2(a, b), psb::pack_bf16x2(c, 0.f), 0u, 0u);
+  }
+}
+}  // namespace
+
+void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW) {
+  const long long total = (long long)N * HW;
+  psb_normalize_pad8<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                                                      mean[0], mean[1], mean[2], inv_std[0], inv_std[1], inv_std[2], N, HW);
+}

@@ -10,6 +10,7 @@ from typing import List, Optional, Type, Union
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ..ops.batchnorm import FusedBatchNormAct2d
 from ..ops.pooling import FusedMaxPool2d
@@ -97,8 +98,20 @@ class ResNet(nn.Module):
         layers += [block(self.inplanes, planes) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
+    def stem(self, x):
+        """7x7/2 stem.  An 8-channel input (3 real + 5 zero channels, see ``ops.preprocess``) runs the same
+        convolution with the weight zero-padded to 8 input channels: identical math, but the 16-byte pixel
+        lets cuDNN use its aligned tensor-core kernels (the 3-channel stem was 23 % of the step)."""
+        c = self.conv1
+        if x.shape[1] == c.in_channels:
+            return c(x)
+        w = F.pad(c.weight, (0, 0, 0, 0, 0, x.shape[1] - c.in_channels))
+        if x.is_contiguous(memory_format=torch.channels_last):
+            w = w.contiguous(memory_format=torch.channels_last)
+        return F.conv2d(x, w, c.bias, c.stride, c.padding, c.dilation, c.groups)
+
     def forward(self, x):
-        x = self.maxpool(self.bn1(self.conv1(x)))
+        x = self.maxpool(self.bn1(self.stem(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 

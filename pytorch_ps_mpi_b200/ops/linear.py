@@ -26,10 +26,10 @@ from . import ext
 
 class _BcastLinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2d, weight, bias, relu, w_ptr, flag_ptr, epoch):
+    def forward(ctx, x2d, weight, bias, relu, w_ptr, flag_ptr, epoch, variant):
         m = ext.cuda()
         N, K = weight.shape
-        y = m.bcast_gemm(x2d, w_ptr or weight.data_ptr(), N, K, bias, relu, flag_ptr, epoch, 30.0)
+        y = m.bcast_gemm(x2d, w_ptr or weight.data_ptr(), N, K, bias, relu, flag_ptr, epoch, 30.0, variant)
         ctx.save_for_backward(x2d, weight, y if relu else None)
         ctx.relu, ctx.has_bias = relu, bias is not None
         return y
@@ -42,12 +42,14 @@ class _BcastLinearFn(torch.autograd.Function):
         gx = gy @ weight if ctx.needs_input_grad[0] else None
         gw = gy.t() @ x2d if ctx.needs_input_grad[1] else None
         gb = gy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
 def bcast_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
-                 w_ptr: int = 0, flag_ptr: int = 0, epoch: int = 0) -> torch.Tensor:
-    """``act(x @ weight.T + bias)`` on tcgen05 (bf16 in, fp32 accumulate, bf16 out)."""
+                 w_ptr: int = 0, flag_ptr: int = 0, epoch: int = 0, variant: int = 0) -> torch.Tensor:
+    """``act(x @ weight.T + bias)`` on tcgen05 (bf16 in, fp32 accumulate, bf16 out).
+
+    ``variant``: 0 = auto (2-CTA ``cta_group::2`` 256x256 tiles when M >= 256), 1 = 1-CTA, 2 = 2-CTA."""
     if not (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
             and weight.shape[1] % 8 == 0):
         y = F.linear(x, weight, bias)          # shapes/dtypes the kernel does not cover
@@ -56,7 +58,7 @@ def bcast_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     x2d = x.reshape(-1, shp[-1])
     if not x2d.is_contiguous() or x2d.data_ptr() % 16:
         x2d = x2d.contiguous()
-    y = _BcastLinearFn.apply(x2d, weight, bias, relu, w_ptr, flag_ptr, epoch)
+    y = _BcastLinearFn.apply(x2d, weight, bias, relu, w_ptr, flag_ptr, epoch, variant)
     return y.view(*shp[:-1], weight.shape[0])
 
 

@@ -36,6 +36,7 @@ import torch
 from .. import runtime
 from ..codings import KIND_DENSE, KIND_SCALED, KIND_TOPK, TILE, WIRE_BF16, WIRE_F16, WIRE_F32, wire_code_of
 from ..ops import ext
+from ..utils.misc import CudaStepTimer
 from .layout import FlatLayout
 from .symmetric import SymmetricArena
 
@@ -190,6 +191,7 @@ class DeviceEngine:
         self.launches = 0                     # kernels of OURS launched (bench 'gpu_launches')
         self._closed = False
         self._gates: list = []
+        self._prof = CudaStepTimer(bool(getattr(opt, "profile", False)))
         self._epoch = 0                       # completed engine steps (the epoch-flag clock)
         # async bookkeeping
         self.version = 0
@@ -379,12 +381,14 @@ class DeviceEngine:
                 self._first_flush_done = True
                 self._before_first_encode()
             active_ptr = self._handle_inactive()
+            ev_a = self._prof.mark(cs)
             if self.size > 1:
                 targets = [sig_base[0]] if self.mode == "ps" else sig_base
                 self.m.signal(targets, self.m.SIG_GRAD_READY + self.rank, epoch)
                 self.launches += 1
             data["isend_time"] = time.time() - t1
             t2 = time.time()
+            ev_b = self._prof.mark(cs)
             if self.is_server:
                 n = self.size
                 inv = (1.0 / n) if o.average else 1.0
@@ -395,6 +399,9 @@ class DeviceEngine:
             else:
                 self._hypers()               # keep per-group step counters aligned with the server
             data["optim_step_time"] = time.time() - t2
+            ev_c = self._prof.mark(cs)
+            self._prof.span("dev_signal_time", ev_a, ev_b)
+            self._prof.span("dev_gather_update_bcast_time", ev_b, ev_c)
             done = torch.cuda.Event()
             done.record(cs)
         t3 = time.time()
@@ -407,6 +414,10 @@ class DeviceEngine:
         else:
             cur.wait_event(done)
         data["comm_wait"] = time.time() - t3
+        if self._prof.enabled:
+            ev_d = self._prof.mark(cur)
+            self._prof.span("dev_step_tail_time", ev, ev_d)     # backward-done → parameters usable, on the compute stream
+            data.update(self._prof.harvest())                   # device timings of the most recent COMPLETED step
         self._end_of_step(data)
         return data
 

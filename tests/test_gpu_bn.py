@@ -103,3 +103,23 @@ def test_maxpool_matches_torch(shape):
     y.backward(g.bfloat16().contiguous(memory_format=torch.channels_last))
     yr.backward(g.bfloat16().float())
     assert torch.allclose(x.grad.float(), xr.grad, rtol=1e-2, atol=1e-2)
+
+
+def test_normalize_pad8_and_padded_stem():
+    from pytorch_ps_mpi_b200.ops.preprocess import normalize_pad8, IMAGENET_MEAN, IMAGENET_STD
+    from pytorch_ps_mpi_b200 import models
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    x = torch.randint(0, 256, (4, 3, 32, 40), dtype=torch.uint8, device=dev)
+    y = normalize_pad8(x)
+    assert y.shape == (4, 8, 32, 40) and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    m = torch.tensor(IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
+    s = torch.tensor(IMAGENET_STD, device=dev).view(1, 3, 1, 1)
+    ref = (x.float() - m) / s
+    assert torch.allclose(y[:, :3].float(), ref, rtol=1e-2, atol=1e-2) and float(y[:, 3:].abs().max()) == 0.0
+    net = models.resnet18(num_classes=10).to(dev).to(memory_format=torch.channels_last).bfloat16()
+    a = net.stem(y)                                             # 8-channel path, zero-padded weight
+    b = net.stem(ref.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))   # stock 3-channel path
+    assert torch.allclose(a.float(), b.float(), rtol=3e-2, atol=3e-2)
+    a.float().square().mean().backward()
+    assert net.conv1.weight.grad is not None and net.conv1.weight.grad.shape == net.conv1.weight.shape

@@ -10,13 +10,14 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 784), (1000, 3072, 768), (77, 10, 512), (4096, 768, 3072),
                                    (8, 136, 72)])
 @pytest.mark.parametrize("bias,relu", [(False, False), (True, True)])
-def test_bcast_gemm_matches_fp32(M, N, K, bias, relu):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_bcast_gemm_matches_fp32(M, N, K, bias, relu, variant):
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     x = (torch.randn(M, K, device=dev) / K ** 0.5).bfloat16()
     w = torch.randn(N, K, device=dev).bfloat16()
     b = torch.randn(N, device=dev).bfloat16() if bias else None
-    y = bcast_linear(x, w, b, relu)
+    y = bcast_linear(x, w, b, relu, variant=variant)
     ref = x.float() @ w.float().t()
     if bias:
         ref = ref + b.float()
@@ -61,7 +62,7 @@ def test_gate_flag_blocks_until_published():
     torch.cuda.synchronize()
     flag_ptr = sig.data_ptr() + 8 * m.SIG_PARAMS_READY
     with torch.cuda.stream(side):
-        y = m.bcast_gemm(x, w.data_ptr(), 128, 64, None, False, flag_ptr, 7, 20.0)   # spins on the flag
+        y = m.bcast_gemm(x, w.data_ptr(), 128, 64, None, False, flag_ptr, 7, 20.0, 0)   # spins on the flag
     # "the server": write the real weight, then publish epoch 7
     w.copy_(w_new)
     m.signal([sig.data_ptr()], m.SIG_PARAMS_READY, 7)
