@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--optim", default="sgd", choices=["sgd", "adam"])
     ap.add_argument("--seq", type=int, default=128, help="sequence length (bert_base)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="CUDA-event section timings of the PS path (stderr)")
     return ap.parse_args()
 
 
@@ -139,7 +140,7 @@ def main():
         hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-4) if args.optim == "sgd" else dict(lr=1e-4, weight_decay=0.01)
         cls = ps.SGD if args.optim == "sgd" else ps.Adam
         opt = cls(named, [p for _, p in named], code=make_code(ps, args.code), mode=args.mode, engine="device",
-                  average=True, **hyper)
+                  average=True, profile=args.profile, **hyper)
     eng = getattr(opt, "_engine", None)
 
     # distinct batches so no step re-reads a cached input; pinned host copies for the e2e arm
@@ -232,6 +233,11 @@ def main():
 
     if eng is not None:
         eng.check()
+    if args.profile and getattr(opt, "timings", None):
+        keys = ("dev_signal_time", "dev_gather_update_bcast_time", "dev_step_tail_time", "code_wait", "isend_time",
+                "optim_step_time", "comm_wait")
+        last = opt.timings[-1]
+        print(f"[rank {w.rank}] " + " ".join(f"{k}={last[k] * 1e3:.3f}ms" for k in keys if k in last), file=sys.stderr, flush=True)
     if w.rank == 0:
         out = {
             "metric": "samples/sec (whole box, device-timed, max over ranks), ResNet-18 PS-SGD" if args.model == "resnet18"

@@ -186,6 +186,8 @@ class DeviceEngine:
         self._pending_bytes = 0
         self._fired: set = set()
         self._keep: List[torch.Tensor] = []
+        self._keep_prev: List[torch.Tensor] = []   # last step's gradients: freed one step late (see _flush)
+        self._prev_done = None                      # comm-stream completion of the last step
         self._raw_bytes = 0
         self._first_flush_done = False
         self.launches = 0                     # kernels of OURS launched (bench 'gpu_launches')
@@ -289,13 +291,16 @@ class DeviceEngine:
         cs = self.comm_stream
         cs.wait_event(ev)
         batch, self._pending, self._pending_bytes = self._pending, [], 0
+        if not self._first_flush_done and self._prev_done is not None:
+            # Bound the comm stream's lag to one step: gradients are kept alive (not record_stream'ed, which
+            # would make the caching allocator grow and cudaMalloc for several steps) until the step after
+            # they were encoded, so the compute stream must not run further ahead than that.
+            cur.wait_event(self._prev_done)
         with torch.cuda.stream(cs):
             if not self._first_flush_done:
                 self._first_flush_done = True
                 self._before_first_encode()
             grads = [g for _, g in batch]
-            for g in grads:
-                g.record_stream(cs)
             self.m.encode(self.kind, self.wire, grads, [s.first_tile for s, _ in batch],
                           [s.ntiles for s, _ in batch], [s.index for s, _ in batch],
                           self.tiles.data_ptr(), self.arena.local_ptr + self.off_wire,
@@ -370,7 +375,7 @@ class DeviceEngine:
         data["code_wait"] = time.time() - t0
         epoch = self._epoch + 1
         cur = torch.cuda.current_stream(self.device)
-        ev = torch.cuda.Event()
+        ev = torch.cuda.Event(enable_timing=self._prof.enabled)
         ev.record(cur)                       # backward is complete up to here
         cs = self.comm_stream
         cs.wait_event(ev)
@@ -430,7 +435,9 @@ class DeviceEngine:
         data["engine"] = "device"
         self._epoch += 1
         self._fired = set()
-        self._keep = []
+        self._keep_prev, self._keep = self._keep, []
+        self._prev_done = torch.cuda.Event()
+        self._prev_done.record(self.comm_stream)
         self._raw_bytes = 0
         self._first_flush_done = False
         if os.environ.get("PSB200_CHECK") == "1":
