@@ -85,10 +85,12 @@ def build(args, device, ps):
         mean = torch.tensor([0.485, 0.456, 0.406], device=device).view(1, 3, 1, 1) * 255
         std = torch.tensor([0.229, 0.224, 0.225], device=device).view(1, 3, 1, 1) * 255
 
+        from pytorch_ps_mpi_b200.ops.preprocess import normalize_nhwc
+
         def loss_fn(x, y):
             # (the 8-channel padded stem of ops.preprocess.normalize_pad8 measured SLOWER under cuDNN on B200:
             #  3.45 ms vs 2.51 ms fwd+wgrad — scratch/stem_bench.py — so the stock 3-channel stem stays)
-            xb = ((x.float() - mean) / std).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            xb = normalize_nhwc(x)          # uint8 NCHW → normalised bf16 NHWC: one kernel of ours
             return torch.nn.functional.cross_entropy(model(xb).float(), y)
         cfg = {"global_batch": None, "image": "3x224x224 uint8"}
     elif args.model == "mlp":

@@ -180,9 +180,39 @@ at::Tensor normalize_pad8(const at::Tensor& x, std::vector<double> mean, std::ve
   return y;
 }
 
+// bf16 NHWC [N,3,H,W] (channels_last) → patch matrix [N*OH*OW, 160] for the 7x7/s2/p3 stem
+at::Tensor im2col_stem(const at::Tensor& x) {
+  check_nhwc(x, "x");
+  TORCH_CHECK(x.size(1) == 3, "stem input must have 3 channels");
+  const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3);
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  auto a = at::empty({(int64_t)N * OH * OW, 160}, x.options());
+  psb_im2col_stem_launch(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), a.data_ptr(), N, H, W);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_im2col_stem: ", cudaGetErrorString(e));
+  return a;
+}
+
+// uint8 [N,3,H,W] NCHW → bf16 [N,3,H,W] channels_last, (x - mean) / std
+at::Tensor normalize_nhwc3(const at::Tensor& x, std::vector<double> mean, std::vector<double> std) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kByte && x.dim() == 4 && x.size(1) == 3 && x.is_contiguous(),
+              "x must be a contiguous uint8 [N,3,H,W] CUDA tensor");
+  const int N = (int)x.size(0);
+  const long long HW = x.size(2) * x.size(3);
+  auto y = at::empty({N, 3, x.size(2), x.size(3)}, x.options().dtype(at::kBFloat16).memory_format(at::MemoryFormat::ChannelsLast));
+  float m[3] = {(float)mean[0], (float)mean[1], (float)mean[2]};
+  float is[3] = {(float)(1.0 / std[0]), (float)(1.0 / std[1]), (float)(1.0 / std[2])};
+  psb_normalize_nhwc3_launch(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), y.data_ptr(), m, is, N, HW);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_normalize_nhwc3: ", cudaGetErrorString(e));
+  return y;
+}
+
 }  // namespace
 
 void bind_gemm(py::module_& m) {
+  m.def("im2col_stem", &im2col_stem, "bf16 NHWC(3) image → [N*OH*OW,160] patch matrix of the 7x7/s2/p3 stem");
+  m.def("normalize_nhwc3", &normalize_nhwc3, "uint8 NCHW image → normalised bf16 NHWC (3 channels)");
   m.def("normalize_pad8", &normalize_pad8, "uint8 NCHW image → normalised bf16 NHWC padded to 8 channels");
   m.def("maxpool_forward", &maxpool_forward, "channels-last bf16 3x3/s2/p1 max pool → (y, argpos)");
   m.def("maxpool_backward", &maxpool_backward, "gather-style backward of maxpool_forward");

@@ -101,3 +101,5 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
 void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg, int N, int H, int W, int C);
 void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, void* dx, int N, int H, int W, int C);
 void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW);
+void psb_im2col_stem_launch(cudaStream_t s, const void* x, void* a, int N, int H, int W);
+void psb_normalize_nhwc3_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW);

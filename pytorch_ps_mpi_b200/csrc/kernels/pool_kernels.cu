@@ -146,3 +146,69 @@ void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const flo
   psb_normalize_pad8<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(x), reinterpret_cast<__nv_bfloat16*>(y),
                                                       mean[0], mean[1], mean[2], inv_std[0], inv_std[1], inv_std[2], N, HW);
 }
+
+// ---- ResNet stem as an implicit GEMM on OUR tcgen05 kernel ----------------------------------------------
+// cuDNN's 7x7/stride-2 convolution with 3 input channels takes 1.5 ms (fprop) + 1.0 ms (wgrad) of the
+// 10.5 ms ResNet-18 step on B200 (23 %, sm80-era kernels: C=3 defeats its tensor-core paths, and padding
+// C to 4/8 is slower still — scratch/stem_bench.py).  We lower it ourselves: psb_im2col_stem writes the
+// [N*OH*OW, 160] patch matrix (147 = 7*7*3 real columns in (kh,kw,c) order + 13 zero columns, 16-byte
+// rows), the forward is psb_bcast_gemm (tcgen05/TMEM/TMA) against the [64,160] weight matrix and lands
+// directly in NHWC, and the weight gradient is one library GEMM dY^T · A.
+namespace {
+constexpr int STEM_K = 160;   // 7*7*3 = 147 padded to a multiple of 8 (TMA row pitch) and 16 (UMMA_K)
+
+__global__ void __launch_bounds__(256) psb_im2col_stem(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a,
+                                                       int N, int H, int W, int OH, int OW) {
+  // one thread = one 16-byte vector (8 consecutive k) of one patch row
+  const long long total = (long long)N * OH * OW * (STEM_K / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int vec = (int)(i % (STEM_K / 8));
+    long long p = i / (STEM_K / 8);
+    const int ow = (int)(p % OW);
+    p /= OW;
+    const int oh = (int)(p % OH);
+    const int n = (int)(p / OH);
+    const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+    unsigned short v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = vec * 8 + j;
+      unsigned short val = 0;
+      if (k < 147) {
+        const int kh = k / 21, rem = k - kh * 21, kw = rem / 3, c = rem - kw * 3;
+        const int ih = oh * 2 - 3 + kh, iw = ow * 2 - 3 + kw;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = xs[(((long long)n * H + ih) * W + iw) * 3 + c];
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<uint4*>(a + (i * 8)) = make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16),
+                                                        v[4] | ((uint32_t)v[5] << 16), v[6] | ((uint32_t)v[7] << 16));
+  }
+}
+
+// uint8 NCHW image → normalised bf16 NHWC (3 channels), one pass
+__global__ void __launch_bounds__(256) psb_normalize_nhwc3(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y, float m0,
+                                                           float m1, float m2, float s0, float s1, float s2, int N, long long HW) {
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i % HW;
+    const uint8_t* base = x + n * 3 * HW + p;
+    y[i * 3 + 0] = __float2bfloat16_rn(((float)base[0] - m0) * s0);
+    y[i * 3 + 1] = __float2bfloat16_rn(((float)base[HW] - m1) * s1);
+    y[i * 3 + 2] = __float2bfloat16_rn(((float)base[2 * HW] - m2) * s2);
+  }
+}
+}  // namespace
+
+void psb_im2col_stem_launch(cudaStream_t s, const void* x, void* a, int N, int H, int W) {
+  const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+  const long long total = (long long)N * OH * OW * (STEM_K / 8);
+  psb_im2col_stem<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(a), N,
+                                                   H, W, OH, OW);
+}
+
+void psb_normalize_nhwc3_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW) {
+  const long long total = (long long)N * HW;
+  psb_normalize_nhwc3<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                                                       mean[0], mean[1], mean[2], inv_std[0], inv_std[1], inv_std[2], N, HW);
+}

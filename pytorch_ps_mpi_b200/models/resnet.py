@@ -14,6 +14,7 @@ import torch.nn.functional as F
 
 from ..ops.batchnorm import FusedBatchNormAct2d
 from ..ops.pooling import FusedMaxPool2d
+from ..ops.stem import stem_conv, stem_supported
 
 
 def _conv3x3(i, o, stride=1):
@@ -63,8 +64,9 @@ class Bottleneck(nn.Module):
 
 class ResNet(nn.Module):
     def __init__(self, block: Type[Union[BasicBlock, Bottleneck]], layers: List[int],
-                 num_classes: int = 1000, zero_init_residual: bool = False):
+                 num_classes: int = 1000, zero_init_residual: bool = False, gemm_stem: bool = True):
         super().__init__()
+        self.gemm_stem = gemm_stem
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = FusedBatchNormAct2d(64, relu=True)
@@ -104,6 +106,8 @@ class ResNet(nn.Module):
         lets cuDNN use its aligned tensor-core kernels (the 3-channel stem was 23 % of the step)."""
         c = self.conv1
         if x.shape[1] == c.in_channels:
+            if self.gemm_stem and stem_supported(x, c):
+                return stem_conv(x, c.weight)          # im2col + our tcgen05 GEMM (cuDNN: 2.5 ms/step here)
             return c(x)
         w = F.pad(c.weight, (0, 0, 0, 0, 0, x.shape[1] - c.in_channels))
         if x.is_contiguous(memory_format=torch.channels_last):

@@ -94,3 +94,17 @@ class BcastLinear(nn.Linear):
                   device=lin.weight.device, dtype=lin.weight.dtype)
         new.weight, new.bias = lin.weight, lin.bias
         return new
+
+
+def convert_first_linear(model: nn.Module, optimizer=None, relu: bool = False, pull: bool = False) -> Optional[BcastLinear]:
+    """Swap the FIRST ``nn.Linear`` of ``model`` (the first forward GEMM) for a :class:`BcastLinear`
+    sharing the same parameters, and — given a device-engine optimizer — gate it on the broadcast."""
+    for parent in model.modules():
+        for name, child in list(parent.named_children()):
+            if isinstance(child, nn.Linear) and not isinstance(child, BcastLinear):
+                new = BcastLinear.from_linear(child, relu=relu)
+                setattr(parent, name, new)
+                if optimizer is not None and getattr(optimizer, "_engine", None) is not None:
+                    new.attach(optimizer, pull=pull)
+                return new
+    return None

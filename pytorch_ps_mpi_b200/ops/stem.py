@@ -1,0 +1,48 @@
+"""ResNet stem (7x7 / stride 2 / pad 3, 3 → 64 channels) lowered to OUR tcgen05 GEMM.
+
+``stem_conv(x, weight)``: ``psb_im2col_stem`` builds the ``[N*OH*OW, 160]`` patch matrix, the forward
+product with the ``[64, 160]`` weight matrix runs on ``psb_bcast_gemm`` (TMA + ``tcgen05.mma`` + TMEM)
+and its ``[N*OH*OW, 64]`` output *is* the NHWC activation; the weight gradient is one library GEMM.
+cuDNN needs 2.5 ms per step for this layer on B200 (C=3 defeats its tensor-core kernels).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import ext
+from .linear import bcast_linear
+
+STEM_K = 160
+
+
+class _StemGemm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, w2d):
+        y = bcast_linear(a, w2d)                       # [M,160] x [64,160]^T on tcgen05
+        ctx.save_for_backward(a)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (a,) = ctx.saved_tensors
+        gw = gy.t().contiguous() @ a if ctx.needs_input_grad[1] else None     # [64,M] x [M,160]
+        return None, gw
+
+
+def stem_supported(x: torch.Tensor, conv: torch.nn.Conv2d) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 3
+            and x.is_contiguous(memory_format=torch.channels_last) and not x.requires_grad
+            and conv.weight.dtype == torch.bfloat16 and conv.bias is None and conv.kernel_size == (7, 7)
+            and conv.stride == (2, 2) and conv.padding == (3, 3) and conv.dilation == (1, 1) and conv.groups == 1)
+
+
+def stem_conv(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``F.conv2d(x, weight, stride=2, padding=3)`` for a 3-channel channels-last bf16 ``x`` (no input grad)."""
+    n, _, h, w = x.shape
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    cout = weight.shape[0]
+    a = ext.cuda().im2col_stem(x)                                             # [n*oh*ow, 160]
+    w2d = F.pad(weight.permute(0, 2, 3, 1).reshape(cout, 147), (0, STEM_K - 147))   # (kh,kw,c) order, zero padded
+    y = _StemGemm.apply(a, w2d.contiguous())                                  # [n*oh*ow, cout] == NHWC
+    return y.view(n, oh, ow, cout).permute(0, 3, 1, 2)                        # logical NCHW, channels_last memory

@@ -233,18 +233,21 @@ class DeviceEngine:
         if not self.is_server:
             return
         o = self.opt
-        if o.optim == "adam":
-            for s in self.layout.slots:
-                o.state[s.param]["step"] = self._group_steps[s.group]
+        for s in self.layout.slots:   # SGD too: the first-step momentum rule (ps.py:203-205) needs it on resume
+            o.state[s.param]["step"] = self._group_steps[s.group]
 
-    def sync_state_from_torch(self):
-        """After ``load_state_dict``: copy loaded tensors back into the flat state."""
+    def sync_state_from_torch(self, original=None):
+        """After ``load_state_dict``: copy loaded tensors back into the flat (fp32) state.
+
+        ``original`` maps ``id(param)`` → the un-cast saved state of that parameter."""
         if not self.is_server:
             return
         o = self.opt
         with torch.no_grad():
             for s in self.layout.slots:
                 st = o.state.get(s.param, {})
+                if original is not None and id(s.param) in original:
+                    st = original[id(s.param)]
                 sl = slice(s.offset, s.offset + s.numel)
                 for key, buf in (("momentum_buffer", self.buf0 if o.optim == "sgd" else None),
                                  ("exp_avg", self.buf0 if o.optim == "adam" else None),
@@ -253,12 +256,13 @@ class DeviceEngine:
                     if buf is not None and key in st and st[key] is not None:
                         if st[key].data_ptr() != buf[sl].data_ptr():
                             self._like(buf[sl], s.param).copy_(st[key].to(buf.dtype))
-                if o.optim == "adam" and "step" in st:
+                if "step" in st:
                     self._group_steps[s.group] = max(self._group_steps[s.group], int(st["step"]))
             if self.master is not None:
                 # parameters may have been re-loaded by the user: re-seed masters that lack a saved copy
                 for s in self.layout.slots:
-                    if "master_param" not in o.state.get(s.param, {}):
+                    src = original.get(id(s.param), {}) if original is not None else o.state.get(s.param, {})
+                    if "master_param" not in src:
                         self._like(self.master[s.offset: s.offset + s.numel], s.param).copy_(s.param.data.float())
         self._expose_state()
 

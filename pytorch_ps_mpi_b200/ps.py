@@ -491,7 +491,12 @@ class MPI_PS(torch.optim.Optimizer):
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         if self._engine is not None:
-            self._engine.sync_state_from_torch()
+            # torch casts loaded state to the parameter dtype (bf16); the engine's state is fp32, so hand
+            # it the ORIGINAL tensors, keyed by parameter position
+            params = [p for g in self.param_groups for p in g["params"]]
+            saved = state_dict.get("state", {})
+            original = {id(params[int(i)]): st for i, st in saved.items() if int(i) < len(params)}
+            self._engine.sync_state_from_torch(original)
 
 
 # ---------------------------------------------------------------------------------------

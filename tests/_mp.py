@@ -186,7 +186,7 @@ def mlp_async(rank, size, transport):
 
 
 # --- device engine, spawned ranks (1 GPU shared by all ranks, or one GPU per rank) ----------
-def gpu_train(rank, size, mode, optim, coding, dtype_name):
+def gpu_train(rank, size, mode, optim, coding, dtype_name, reduce="auto"):
     import math
     ps, w = _world(rank, size)
     from pytorch_ps_mpi_b200.models import mnist_mlp
@@ -199,9 +199,11 @@ def gpu_train(rank, size, mode, optim, coding, dtype_name):
     torch.manual_seed(0)
     model = mnist_mlp(hidden=32).to(dev).to(dtype)
     cls = ps.SGD if optim == "sgd" else ps.Adam
-    opt = cls(model.named_parameters(), model.parameters(), code=factory(), mode=mode, engine="device", **hyper)
+    opt = cls(model.named_parameters(), model.parameters(), code=factory(), mode=mode, engine="device", reduce=reduce, **hyper)
     eng = opt._engine
     assert eng is not None and eng.arena.provider in ("native", "torch")
+    if reduce == "nvls":
+        assert eng.reduce == 1 and eng.arena.has_multicast
     steps = 3
     for s in range(steps):
         x, y = _mlp_data(rank, s)
@@ -300,3 +302,107 @@ def symm_arena(rank, size):
     if rank == 0:
         print("symm_arena ok", A.provider, "multicast" if A.has_multicast else "no-multicast", A.nbytes, flush=True)
     A.close()
+
+
+def gpu_bcast_linear(rank, size, pull):
+    """MLP whose first GEMM is the tcgen05 kernel gated on the PS broadcast (and optionally PULLING the
+    weight tiles from the server's arena over NVLink)."""
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    from pytorch_ps_mpi_b200.ops.linear import convert_first_linear, BcastLinear
+    dev = w.device
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=256).to(dev).bfloat16()
+    ref = mnist_mlp(hidden=256).to(dev).bfloat16()
+    ref.load_state_dict(model.state_dict())
+    opt = ps.SGD(model.named_parameters(), model.parameters(), lr=0.05, momentum=0.9, mode="ps", engine="device")
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9)
+    layer = convert_first_linear(model, opt, relu=True, pull=bool(pull))
+    assert isinstance(model.fc1, BcastLinear) and layer is model.fc1 and opt._engine._gates
+    for s in range(4):
+        xs = [_mlp_data(r, s, batch=128) for r in range(size)]
+        x, y = xs[rank]
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(x.to(dev).bfloat16()).float(), y.to(dev))
+        loss.backward()
+        opt.step()
+        # single-process reference on the summed gradient (stock cuBLAS linear)
+        ropt.zero_grad()
+        for xr, yr in xs:
+            torch.nn.functional.cross_entropy(ref(xr.to(dev).bfloat16()).float(), yr.to(dev)).backward()
+        ropt.step()
+    opt._engine.check()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).item()
+    flat = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()]).cpu()
+    allp = w.all_gather_object(flat)
+    for f in allp:
+        assert torch.equal(f, allp[0]), "ranks diverged"
+    want = torch.cat([p.detach().float().reshape(-1) for p in ref.parameters()]).cpu()
+    assert torch.allclose(flat, want, rtol=5e-2, atol=2e-2), (flat - want).abs().max()
+    if rank == 0:
+        print("gpu_bcast_linear ok pull=", pull, flush=True)
+    opt.close()
+
+
+
+def gpu_checkpoint(rank, size):
+    """state_dict()/load_state_dict() of the device engine: resume must continue bit-identically."""
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    dev = w.device
+
+    def make():
+        torch.manual_seed(0)
+        m = mnist_mlp(hidden=32).to(dev).bfloat16()
+        o = ps.SGD(m.named_parameters(), m.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4, mode="ps", engine="device")
+        return m, o
+
+    def run(m, o, steps, start=0):
+        for s in range(start, start + steps):
+            x, y = _mlp_data(rank, s)
+            o.zero_grad()
+            torch.nn.functional.cross_entropy(m(x.to(dev).bfloat16()).float(), y.to(dev)).backward()
+            o.step()
+        torch.cuda.synchronize()
+
+    m1, o1 = make()
+    run(m1, o1, 4)
+    want = torch.cat([p.detach().float().reshape(-1) for p in m1.parameters()]).cpu()
+    m2, o2 = make()
+    run(m2, o2, 2)
+    sd_model = {k: v.clone() for k, v in m2.state_dict().items()}
+    sd_opt = o2.state_dict()
+    if rank == 0:
+        assert any("momentum_buffer" in s and "master_param" in s for s in sd_opt["state"].values())
+    m3, o3 = make()
+    with torch.no_grad():
+        for k, v in m3.state_dict().items():
+            v.copy_(sd_model[k])
+    o3.load_state_dict(sd_opt)
+    run(m3, o3, 2, start=2)
+    got = torch.cat([p.detach().float().reshape(-1) for p in m3.parameters()]).cpu()
+    assert torch.equal(got, want), (got - want).abs().max()
+    for o in (o1, o2, o3):
+        o.close()
+
+
+def gpu_dead_peer(rank, size):
+    """Failure detection: a worker that never posts its gradient must surface as an error, not a hang."""
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    dev = w.device
+    torch.manual_seed(0)
+    m = mnist_mlp(hidden=32).to(dev)
+    o = ps.SGD(m.named_parameters(), m.parameters(), lr=0.05, mode="ps", engine="device")
+    x, y = _mlp_data(rank, 0)
+    if rank == 0:
+        o.zero_grad()
+        torch.nn.functional.cross_entropy(m(x.to(dev)), y.to(dev)).backward()
+        o.step()                     # rank 1 never steps: the bounded spin must time out
+        try:
+            o._engine.check()
+            raise AssertionError("expected a device-side timeout")
+        except RuntimeError as e:
+            assert "timed out" in str(e)
+    w.barrier()

@@ -123,3 +123,27 @@ def test_normalize_pad8_and_padded_stem():
     assert torch.allclose(a.float(), b.float(), rtol=3e-2, atol=3e-2)
     a.float().square().mean().backward()
     assert net.conv1.weight.grad is not None and net.conv1.weight.grad.shape == net.conv1.weight.shape
+
+
+def test_gemm_stem_matches_conv2d():
+    from pytorch_ps_mpi_b200.ops.stem import stem_conv, stem_supported
+    from pytorch_ps_mpi_b200.ops.preprocess import normalize_nhwc, IMAGENET_MEAN, IMAGENET_STD
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    raw = torch.randint(0, 256, (6, 3, 64, 96), dtype=torch.uint8, device=dev)
+    x = normalize_nhwc(raw)
+    m = torch.tensor(IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
+    s = torch.tensor(IMAGENET_STD, device=dev).view(1, 3, 1, 1)
+    assert torch.allclose(x.float(), (raw.float() - m) / s, rtol=1e-2, atol=1e-2)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).to(dev).to(memory_format=torch.channels_last).bfloat16()
+    assert stem_supported(x, conv)
+    y = stem_conv(x, conv.weight)
+    ref = F.conv2d(x.float(), conv.weight.float(), None, 2, 3)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(y.float(), ref, rtol=3e-2, atol=3e-2), (y.float() - ref).abs().max()
+    g = torch.randn_like(ref)
+    (gw,) = torch.autograd.grad(y, [conv.weight], g.bfloat16())
+    wref = conv.weight.detach().float().requires_grad_(True)
+    (gr,) = torch.autograd.grad(F.conv2d(x.float(), wref, None, 2, 3), [wref], g.bfloat16().float())
+    assert gw.shape == conv.weight.shape
+    assert torch.allclose(gw.float(), gr, rtol=5e-2, atol=5e-2 * gr.abs().max().item())

@@ -131,6 +131,32 @@ def test_engine_multi_gpu(mode, optim, coding, dtype):
     spawn(_mp.gpu_train, n, (mode, optim, coding, dtype), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
 
 
+def test_checkpoint_resume_two_ranks_one_gpu():
+    spawn(_mp.gpu_checkpoint, 2, env=ONE_GPU, timeout=240)
+
+
+def test_dead_peer_times_out_one_gpu():
+    spawn(_mp.gpu_dead_peer, 2, env=dict(ONE_GPU, PSB200_DEVICE_TIMEOUT="3"), timeout=120)
+
+
+@pytest.mark.multigpu
+def test_nvls_switch_reduce_multi_gpu():
+    n = min(torch.cuda.device_count(), 4)
+    spawn(_mp.gpu_train, n, ("ps", "sgd", "identity", "fp32", "nvls"), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
+    spawn(_mp.gpu_train, n, ("allgather", "adam", "cast", "bf16", "nvls"), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
+
+
+@pytest.mark.parametrize("pull", [0, 1])
+def test_bcast_linear_gated_two_ranks_one_gpu(pull):
+    spawn(_mp.gpu_bcast_linear, 2, (pull,), env=ONE_GPU, timeout=240)
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("pull", [0, 1])
+def test_bcast_linear_gated_multi_gpu(pull):
+    spawn(_mp.gpu_bcast_linear, 2, (pull,), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
+
+
 @pytest.mark.multigpu
 def test_async_multi_gpu():
     spawn(_mp.gpu_async, min(torch.cuda.device_count(), 4), ("topk",), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
