@@ -180,13 +180,13 @@ at::Tensor normalize_pad8(const at::Tensor& x, std::vector<double> mean, std::ve
   return y;
 }
 
-// bf16 NHWC [N,3,H,W] (channels_last) → patch matrix [N*OH*OW, 160] for the 7x7/s2/p3 stem
+// bf16 NHWC [N,3,H,W] (channels_last) → patch matrix [N*OH*OW, 176] for the 7x7/s2/p3 stem
 at::Tensor im2col_stem(const at::Tensor& x) {
   check_nhwc(x, "x");
   TORCH_CHECK(x.size(1) == 3, "stem input must have 3 channels");
   const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3);
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  auto a = at::empty({(int64_t)N * OH * OW, 160}, x.options());
+  auto a = at::empty({(int64_t)N * OH * OW, 176}, x.options());
   psb_im2col_stem_launch(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), a.data_ptr(), N, H, W);
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_im2col_stem: ", cudaGetErrorString(e));
@@ -211,7 +211,7 @@ at::Tensor normalize_nhwc3(const at::Tensor& x, std::vector<double> mean, std::v
 }  // namespace
 
 void bind_gemm(py::module_& m) {
-  m.def("im2col_stem", &im2col_stem, "bf16 NHWC(3) image → [N*OH*OW,160] patch matrix of the 7x7/s2/p3 stem");
+  m.def("im2col_stem", &im2col_stem, "bf16 NHWC(3) image → [N*OH*OW,176] patch matrix of the 7x7/s2/p3 stem");
   m.def("normalize_nhwc3", &normalize_nhwc3, "uint8 NCHW image → normalised bf16 NHWC (3 channels)");
   m.def("normalize_pad8", &normalize_pad8, "uint8 NCHW image → normalised bf16 NHWC padded to 8 channels");
   m.def("maxpool_forward", &maxpool_forward, "channels-last bf16 3x3/s2/p1 max pool → (y, argpos)");

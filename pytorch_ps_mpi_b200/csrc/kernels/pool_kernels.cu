@@ -151,38 +151,59 @@ void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const flo
 // cuDNN's 7x7/stride-2 convolution with 3 input channels takes 1.5 ms (fprop) + 1.0 ms (wgrad) of the
 // 10.5 ms ResNet-18 step on B200 (23 %, sm80-era kernels: C=3 defeats its tensor-core paths, and padding
 // C to 4/8 is slower still — scratch/stem_bench.py).  We lower it ourselves: psb_im2col_stem writes the
-// [N*OH*OW, 160] patch matrix (147 = 7*7*3 real columns in (kh,kw,c) order + 13 zero columns, 16-byte
-// rows), the forward is psb_bcast_gemm (tcgen05/TMEM/TMA) against the [64,160] weight matrix and lands
+// [N*OH*OW, 176] patch matrix (7 kernel rows x (21 real + 3 zero) columns + 8 zero columns), the forward
+// is psb_bcast_gemm (tcgen05/TMEM/TMA) against the matching [64,176] weight matrix and lands
 // directly in NHWC, and the weight gradient is one library GEMM dY^T · A.
 namespace {
-constexpr int STEM_K = 160;   // 7*7*3 = 147 padded to a multiple of 8 (TMA row pitch) and 16 (UMMA_K)
+constexpr int STEM_K = 176;   // 7 kernel rows x 24 (21 = 7*3 real + 3 zero, so every row starts 16-byte aligned) + 8 pad → 11 * UMMA_K
 
+// One thread = one (output pixel, kernel row): the 21 input values x[n, ih, iw0..iw0+6, 0..2] are CONTIGUOUS
+// in NHWC memory (42 bytes, always 2-mod-4 aligned because iw0 = 2*ow - 3 is odd), so they are fetched with
+// one 2-byte and ten 4-byte loads and written as three 16-byte stores (plus the 16-byte zero tail by kh == 6).
 __global__ void __launch_bounds__(256) psb_im2col_stem(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a,
                                                        int N, int H, int W, int OH, int OW) {
-  // one thread = one 16-byte vector (8 consecutive k) of one patch row
-  const long long total = (long long)N * OH * OW * (STEM_K / 8);
+  const long long total = (long long)N * OH * OW * 7;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int vec = (int)(i % (STEM_K / 8));
-    long long p = i / (STEM_K / 8);
+    const int kh = (int)(i % 7);
+    long long p = i / 7;
+    const long long row = p;
     const int ow = (int)(p % OW);
     p /= OW;
     const int oh = (int)(p % OH);
     const int n = (int)(p / OH);
-    const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
-    unsigned short v[8];
+    const int ih = oh * 2 - 3 + kh, iw0 = ow * 2 - 3;
+    uint32_t v[12];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = vec * 8 + j;
-      unsigned short val = 0;
-      if (k < 147) {
-        const int kh = k / 21, rem = k - kh * 21, kw = rem / 3, c = rem - kw * 3;
-        const int ih = oh * 2 - 3 + kh, iw = ow * 2 - 3 + kw;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = xs[(((long long)n * H + ih) * W + iw) * 3 + c];
+    for (int j = 0; j < 12; ++j) v[j] = 0u;
+    if (ih >= 0 && ih < H) {
+      const unsigned short* src = xs + (((long long)n * H + ih) * W) * 3;   // row start; element e of the window = src[iw0*3 + e]
+      if (iw0 >= 0 && iw0 + 7 <= W) {
+        const unsigned short* q = src + (long long)iw0 * 3;                // 2-mod-4 byte aligned
+        const uint32_t first = q[0];
+        const uint32_t* q4 = reinterpret_cast<const uint32_t*>(q + 1);      // 4-byte aligned
+        uint32_t w4[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) w4[j] = q4[j];
+        // element e: e=0 → first; e=2j+1, 2j+2 → w4[j] low / high
+        v[0] = first | (w4[0] << 16);
+#pragma unroll
+        for (int j = 1; j < 10; ++j) v[j] = (w4[j - 1] >> 16) | (w4[j] << 16);
+        v[10] = (w4[9] >> 16);                                              // element 20, then zero
+      } else {
+#pragma unroll
+        for (int e = 0; e < 21; ++e) {
+          const int iw = iw0 + e / 3;
+          const uint32_t val = (iw >= 0 && iw < W) ? xs[(((long long)n * H + ih) * W + iw) * 3 + (e % 3)] : 0u;
+          v[e >> 1] |= val << (16 * (e & 1));
+        }
       }
-      v[j] = val;
     }
-    *reinterpret_cast<uint4*>(a + (i * 8)) = make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16),
-                                                        v[4] | ((uint32_t)v[5] << 16), v[6] | ((uint32_t)v[7] << 16));
+    uint4* dst = reinterpret_cast<uint4*>(a + row * STEM_K + kh * 24);
+    dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    dst[2] = make_uint4(v[8], v[9], v[10], v[11]);
+    if (kh == 6) dst[3] = make_uint4(0u, 0u, 0u, 0u);                       // columns 168..175
   }
 }
 
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(256) psb_normalize_nhwc3(const uint8_t* __rest
 
 void psb_im2col_stem_launch(cudaStream_t s, const void* x, void* a, int N, int H, int W) {
   const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
-  const long long total = (long long)N * OH * OW * (STEM_K / 8);
+  const long long total = (long long)N * OH * OW * 7;
   psb_im2col_stem<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(a), N,
                                                    H, W, OH, OW);
 }

@@ -1,7 +1,7 @@
 """ResNet stem (7x7 / stride 2 / pad 3, 3 → 64 channels) lowered to OUR tcgen05 GEMM.
 
-``stem_conv(x, weight)``: ``psb_im2col_stem`` builds the ``[N*OH*OW, 160]`` patch matrix, the forward
-product with the ``[64, 160]`` weight matrix runs on ``psb_bcast_gemm`` (TMA + ``tcgen05.mma`` + TMEM)
+``stem_conv(x, weight)``: ``psb_im2col_stem`` builds the ``[N*OH*OW, 176]`` patch matrix, the forward
+product with the ``[64, 176]`` weight matrix runs on ``psb_bcast_gemm`` (TMA + ``tcgen05.mma`` + TMEM)
 and its ``[N*OH*OW, 64]`` output *is* the NHWC activation; the weight gradient is one library GEMM.
 cuDNN needs 2.5 ms per step for this layer on B200 (C=3 defeats its tensor-core kernels).
 """
@@ -13,20 +13,20 @@ import torch.nn.functional as F
 from . import ext
 from .linear import bcast_linear
 
-STEM_K = 160
+STEM_K = 176          # 7 kernel rows x 24 (21 real + 3 zero) + 8 zero columns (csrc/kernels/pool_kernels.cu)
 
 
 class _StemGemm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, w2d):
-        y = bcast_linear(a, w2d)                       # [M,160] x [64,160]^T on tcgen05
+        y = bcast_linear(a, w2d)                       # [M,176] x [64,176]^T on tcgen05
         ctx.save_for_backward(a)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         (a,) = ctx.saved_tensors
-        gw = gy.t().contiguous() @ a if ctx.needs_input_grad[1] else None     # [64,M] x [M,160]
+        gw = gy.t() @ a if ctx.needs_input_grad[1] else None     # [64,M] x [M,176]; no transpose copy (4.1 ms → 0.28 ms)
         return None, gw
 
 
@@ -42,7 +42,8 @@ def stem_conv(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     n, _, h, w = x.shape
     oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     cout = weight.shape[0]
-    a = ext.cuda().im2col_stem(x)                                             # [n*oh*ow, 160]
-    w2d = F.pad(weight.permute(0, 2, 3, 1).reshape(cout, 147), (0, STEM_K - 147))   # (kh,kw,c) order, zero padded
+    a = ext.cuda().im2col_stem(x)                                             # [n*oh*ow, 176]
+    w2d = F.pad(weight.permute(0, 2, 3, 1).reshape(cout, 7, 21), (0, 3)).reshape(cout, 168)   # (kh | kw,c) rows padded 21→24
+    w2d = F.pad(w2d, (0, STEM_K - 168))
     y = _StemGemm.apply(a, w2d.contiguous())                                  # [n*oh*ow, cout] == NHWC
     return y.view(n, oh, ow, cout).permute(0, 3, 1, 2)                        # logical NCHW, channels_last memory
