@@ -1,0 +1,148 @@
+"""L2 wire format + helpers: ``serialization`` (the finished form of the reference's
+``serialization.py:8-50``), ``compress``/``decompress`` (``mpi_comms.py:18-30``), ``to_np``/``to_torch``
+(``mpi_comms.py:32-58``), ``trim_msg``, ``print_summary``, ``_bytes_of`` — and the coding oracles."""
+import numpy as np
+import pytest
+import torch
+
+import pytorch_ps_mpi_b200 as ps
+from pytorch_ps_mpi_b200 import serialization as ser
+from pytorch_ps_mpi_b200.codings import TILE, tile_k
+
+comms = ps.comms
+
+
+def _obj():
+    n = 1000
+    x = torch.linspace(0, 6.28, n)
+    return {"x": x, "y": (torch.sin(x) + 0.25).bfloat16(), "n": n, "fp8": torch.randn(33).to(torch.float8_e4m3fn),
+            "nested": [torch.arange(5), {"np": np.arange(6, dtype=np.float64).reshape(2, 3)}], "s": "str", "t": (1, 2.5)}
+
+
+def _same(a, b):
+    if isinstance(a, torch.Tensor):
+        return a.dtype == b.dtype and a.shape == b.shape and torch.equal(a.view(torch.uint8) if a.dtype.itemsize == 1 else a, b.view(torch.uint8) if b.dtype.itemsize == 1 else b)
+    if isinstance(a, np.ndarray):
+        return a.dtype == b.dtype and np.array_equal(a, b)
+    if isinstance(a, dict):
+        return a.keys() == b.keys() and all(_same(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)):
+        return len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    return a == b
+
+
+@pytest.mark.parametrize("level", [0, 1, 5])
+def test_dumps_loads_roundtrip_all_dtypes(level):
+    obj = _obj()
+    raw = ser.dumps(obj)
+    msg = ser.compress(raw, level=level)
+    back = ser.loads(ser.decompress(msg))
+    assert _same(obj, back)
+    assert back["y"].dtype == torch.bfloat16            # the reference cast everything to float32 (mpi_comms.py:48)
+    if level == 0:
+        assert len(msg) == len(raw) + ser.HEADER_BYTES  # level 0 = framing only (blosc clevel-0 analogue)
+    else:
+        assert len(msg) < len(raw)
+
+
+def test_compress_api_parity():
+    with pytest.raises(ValueError):
+        ser.compress(b"abc", name="lz4")                 # the reference refuses lz4 / snappy (mpi_comms.py:22-24)
+    with pytest.raises(ValueError):
+        ser.compress(b"abc", name="snappy")
+    assert bytes(ser.decompress(ser.compress(b"hello world" * 100, level=2, name="zlib"))) == b"hello world" * 100
+
+
+def test_unframe_detects_truncation_and_garbage():
+    msg = ser.compress(ser.dumps({"a": torch.arange(100)}))
+    with pytest.raises(ValueError):
+        ser.decompress(msg[: len(msg) // 2])             # the reference's sentinel scan becomes an explicit length check
+    with pytest.raises(ValueError):
+        ser.decompress(b"\x00" * 64)
+
+
+def test_native_and_python_paths_agree(monkeypatch):
+    obj = _obj()
+    a = bytes(ser.dumps(obj))
+    monkeypatch.setattr(ser, "_native", lambda: None)
+    b = bytes(ser.dumps(obj))
+    assert a == b
+    assert _same(ser.loads(bytearray(b)), obj)
+    raw = bytes(range(256)) * 5
+    assert bytes(ser._unshuffle(ser._shuffle(raw, 4), 4)) == raw
+
+
+def test_to_np_to_torch():
+    d = {"a": torch.ones(3, dtype=torch.float64), "b": [torch.zeros(2, dtype=torch.int32)], "c": 5,
+         "h": torch.ones(2).bfloat16()}
+    n = comms.to_np(d)
+    assert isinstance(n["a"], np.ndarray) and n["a"].dtype == np.float64 and isinstance(n["b"][0], np.ndarray) and n["c"] == 5
+    assert n["h"].dtype == np.float32                    # numpy has no bf16: exact upcast
+    t = comms.to_torch(n)
+    assert t["a"].dtype == torch.float64 and t["b"][0].dtype == torch.int32        # dtype preserving
+
+
+def test_trim_msg():
+    payload = bytearray(b"abcdef")
+    assert comms.trim_msg(payload + bytearray(b"\x29" * 32) + bytearray(10)) == payload
+    with pytest.raises(Exception):
+        comms.trim_msg(bytearray(b"no sentinel here"))
+
+
+def test_print_summary(capsys):
+    s = comms.print_summary({"w": torch.zeros(2, 3), "a": np.zeros(4), "lr": 0.1})
+    out = capsys.readouterr().out
+    assert "(2, 3)" in out and "(4,)" in out and "lr: 0.1" in out and s.strip().startswith("{")
+
+
+def test_bytes_of():
+    t = torch.zeros(4, 5)                                 # 2-D: the reference's comment admits it mis-sized these
+    assert ps._bytes_of(t) == 80
+    assert ps._bytes_of({"a": t, "b": [np.zeros(3), t]}) == 80 + 24 + 80
+    p = torch.nn.Parameter(torch.zeros(10))
+    p.grad = torch.zeros(10)
+    assert ps._bytes_of(p) == 80
+
+
+# ---- coding oracles ----------------------------------------------------------------------------------
+def test_identity_cast_scale_roundtrip():
+    g = torch.randn(1000) * 3
+    assert torch.equal(ps.Identity().decode(ps.Identity().encode(g)), g)
+    c = ps.Cast("bf16")
+    assert torch.equal(c.decode(c.encode(g)), g.bfloat16().float())
+    for dt, tol in (("int8", 1 / 127), ("fp8_e4m3", 1 / 8), ("fp16", 1e-3)):
+        s = ps.Scale(dt)
+        back = s.decode(s.encode(g))
+        assert (back - g).abs().max() <= tol * g.abs().max() + 1e-6
+    big = torch.tensor([1e6, -1e6, 3.0])
+    assert torch.isfinite(ps.Cast("fp8_e4m3").decode(ps.Cast("fp8_e4m3").encode(big))).all()     # saturating, not NaN
+
+
+def test_topk_blockwise_semantics():
+    torch.manual_seed(0)
+    n = TILE * 2 + 100
+    g = torch.randn(n)
+    t = ps.TopK(ratio=0.1)
+    code = t.encode(g)
+    want = tile_k(0.1, TILE) * 2 + tile_k(0.1, 100)
+    assert code["idx"].numel() == want
+    dense = t.decode(code)
+    nz = dense != 0
+    assert nz.sum() == want and torch.equal(dense[nz], g[nz])
+    for b in range(3):                                   # every kept entry beats every dropped one inside its block
+        lo, hi = b * TILE, min((b + 1) * TILE, n)
+        blk, keep = g[lo:hi].abs(), nz[lo:hi]
+        assert blk[keep].min() >= blk[~keep].max()
+    e = ps.TopK(k=7, exact=True)
+    assert e.encode(g)["idx"].numel() == 7 and e.device_spec() is None
+    with pytest.raises(ValueError):
+        ps.TopK(ratio=0.1, k=3)
+
+
+def test_topk_error_feedback_accumulates():
+    t = ps.TopK(ratio=0.01, error_feedback=True)
+    g = torch.ones(1000)
+    total = torch.zeros(1000)
+    for _ in range(100):
+        total += t.decode(t.encode(g, name="w"))
+    assert torch.allclose(total + t._residual["w"], torch.full((1000,), 100.0))
