@@ -147,6 +147,7 @@ class DeviceEngine:
                     self.buf2 = torch.zeros(n_pad, dtype=torch.float32, device=self.device)
             self._expose_state()
         self._group_steps = [0] * len(opt.param_groups)
+        self._hyper_cache = None
 
         # ---- publication / reduction strategy ----
         mc = A.has_multicast
@@ -335,8 +336,17 @@ class DeviceEngine:
     def _hypers(self) -> List[List[float]]:
         o = self.opt
         out = []
+        if o.optim == "sgd":
+            # SGD's tuple only changes with lr schedules / the first step: reuse the cached list otherwise
+            key = tuple((g["lr"], g["weight_decay"], g["momentum"], g["dampening"], g["nesterov"]) for g in o.param_groups)
+            for gi in range(len(o.param_groups)):
+                self._group_steps[gi] += 1
+            first = any(t == 1 for t in self._group_steps)
+            if not first and self._hyper_cache is not None and self._hyper_cache[0] == key:
+                return self._hyper_cache[1]
         for gi, g in enumerate(o.param_groups):
-            self._group_steps[gi] += 1
+            if o.optim != "sgd":
+                self._group_steps[gi] += 1
             t = self._group_steps[gi]
             if o.optim == "sgd":
                 out.append([float(g["lr"]), float(g["weight_decay"]), float(g["momentum"]), float(g["dampening"]),
@@ -346,6 +356,8 @@ class DeviceEngine:
                 step_size = float(g["lr"]) * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)     # ps.py:257-259
                 out.append([float(g["lr"]), float(g["weight_decay"]), 0.0, 0.0, float(b1), float(b2),
                             float(g["eps"]), step_size, 0.0, float(bool(g.get("amsgrad", False))), float(t == 1)])
+        if o.optim == "sgd" and not any(t == 1 for t in self._group_steps):
+            self._hyper_cache = (key, out)
         return out
 
     def _handle_inactive(self):
