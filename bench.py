@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--optim", default="sgd", choices=["sgd", "adam"])
     ap.add_argument("--seq", type=int, default=128, help="sequence length (bert_base)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--comparator-kind", default="host", choices=["host", "nccl"])
     ap.add_argument("--profile", action="store_true", help="CUDA-event section timings of the PS path (stderr)")
     return ap.parse_args()
 
@@ -147,7 +148,7 @@ def main():
 
     if args.impl == "comparator":
         from baseline.comparator import ComparatorSGD
-        opt = ComparatorSGD(model.named_parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+        opt = ComparatorSGD(model.named_parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4, kind=args.comparator_kind)
     else:
         named = list(model.named_parameters())
         hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-4) if args.optim == "sgd" else dict(lr=1e-4, weight_decay=0.01)
@@ -258,7 +259,7 @@ def main():
             "value": value, "unit": "samples/sec", "n_gpus": w.size, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.model != "mlp" else "fp32", "data": "synthetic (random images/labels, random-init weights)",
-            "impl": args.impl,
+            "impl": args.impl if args.impl != "comparator" else f"comparator-{args.comparator_kind}",
             "config": {"model": args.model, "global_batch": global_batch, "per_gpu_batch": args.batch,
                        "seq_len": cfg.get("seq_len"), "parallelism": f"dp{w.size} (rank-0 parameter server, mode={args.mode})",
                        "optimizer": args.optim, "coding": args.code, "memory_format": "channels_last",

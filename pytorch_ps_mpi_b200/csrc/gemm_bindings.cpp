@@ -55,7 +55,8 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   // cta_group::2 (two SMs per 256x256 tile) whenever there are at least 256 rows; `variant` forces it (tests)
   const bool two_cta = variant == 2 || (variant == 0 && M >= 256);
   CUtensorMap ma = make_map(reinterpret_cast<uint64_t>(x.data_ptr()), M, K, K, 128);
-  CUtensorMap mb = make_map(w_ptr, N, K, K, two_cta ? 128 : 256);   // B box: half tile per CTA (2-CTA) or BN rows
+  const int bnt2 = N <= 64 ? 64 : (N <= 128 ? 128 : 256);          // must match psb_launch_bcast_gemm's choice
+  CUtensorMap mb = make_map(w_ptr, N, K, K, two_cta ? bnt2 / 2 : 256);   // B box: half tile per CTA (2-CTA) or BN rows
   BcastGemmArgs a{};
   a.tmap_a = &ma;
   a.tmap_b = &mb;

@@ -297,13 +297,17 @@ psb_bcast_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 //   * tcgen05.commit ... .multicast::cluster releases the smem slot / publishes the accumulator in BOTH
 //     CTAs; each CTA's epilogue drains its own 128 TMEM lanes and arrives on the leader's tmem_empty.
 // ==========================================================================================
-constexpr int BN2 = 256;
-constexpr int STAGES2 = 6;
-constexpr int A2_BYTES = BM * BK * 2;            // 16 KB: this CTA's 128 rows of A
-constexpr int B2_BYTES = (BN2 / 2) * BK * 2;     // 16 KB: this CTA's half of the B tile
-constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
-constexpr int TMEM_COLS2 = ACC_STAGES * BN2;     // 512
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+// BNT (the N extent of the pair tile) is a template parameter: 256 for big layers, 128 / 64 for narrow
+// outputs (the ResNet stem GEMM has N = 64: a 256-wide tile would waste 3/4 of the MMA work).
+template <int BNT>
+struct Cfg2 {
+  static constexpr int A_BYTES = BM * BK * 2;              // this CTA's 128 rows of A (16 KB)
+  static constexpr int B_BYTES = (BNT / 2) * BK * 2;       // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BNT == 256 ? 6 : 8;
+  static constexpr int TMEM_COLS = ACC_STAGES * BNT;       // 512 / 256 / 128 (power of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // cute::Sm100MmaPeerBitMask: address of the same object in CTA 0 of the pair
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -341,15 +345,20 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
-__host__ __device__ constexpr uint32_t make_idesc2() {   // M = 256 (cta_group::2), N = 256
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+template <int BNT>
+__host__ __device__ constexpr uint32_t make_idesc2() {   // M = 256 (cta_group::2), N = BNT
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
+template <int BNT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 psb_bcast_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using C = Cfg2<BNT>;
+  constexpr int STAGES2 = C::STAGES, STAGE2_BYTES = C::STAGE_BYTES, A2_BYTES = C::A_BYTES, TMEM_COLS2 = C::TMEM_COLS;
+  constexpr int BN2 = BNT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
   uint64_t* full = bars;                        // [STAGES2]  (only the leader's are waited on)
   uint64_t* empty = bars + STAGES2;             // [STAGES2]  (each CTA's own; the commit multicasts to both)
@@ -415,7 +424,7 @@ psb_bcast_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      const uint32_t idesc = make_idesc2();
+      const uint32_t idesc = make_idesc2<BNT>();
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = cl; tile < num_tiles; tile += ncl) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -500,7 +509,9 @@ void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms) 
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(psb_bcast_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(psb_bcast_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64>::SMEM_BYTES);
+    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128>::SMEM_BYTES);
+    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256>::SMEM_BYTES);
     configured = true;
   }
   GemmParams p{};
@@ -512,11 +523,15 @@ void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms) 
   p.M = a.M, p.N = a.N, p.K = a.K, p.relu = a.relu;
   p.timeout_ns = a.timeout_ns;
   if (a.two_cta) {
-    const int tiles = ((a.M + 255) / 256) * ((a.N + BN2 - 1) / BN2);
+    const int bnt = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
+    const int tiles = ((a.M + 255) / 256) * ((a.N + bnt - 1) / bnt);
     int clusters = num_sms / 2;
     if (tiles < clusters) clusters = tiles;
-    psb_bcast_gemm2_kernel<<<2 * clusters, THREADS, SMEM2_BYTES, s>>>(*reinterpret_cast<const CUtensorMap*>(a.tmap_a),
-                                                                       *reinterpret_cast<const CUtensorMap*>(a.tmap_b), p);
+    const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(a.tmap_a);
+    const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(a.tmap_b);
+    if (bnt == 64) psb_bcast_gemm2_kernel<64><<<2 * clusters, THREADS, Cfg2<64>::SMEM_BYTES, s>>>(ta, tb, p);
+    else if (bnt == 128) psb_bcast_gemm2_kernel<128><<<2 * clusters, THREADS, Cfg2<128>::SMEM_BYTES, s>>>(ta, tb, p);
+    else psb_bcast_gemm2_kernel<256><<<2 * clusters, THREADS, Cfg2<256>::SMEM_BYTES, s>>>(ta, tb, p);
     return;
   }
   const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);

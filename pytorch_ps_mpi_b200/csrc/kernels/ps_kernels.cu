@@ -13,6 +13,8 @@
 //     (multimem.st through the switch, or unicast peer stores), then raises the epoch flag.
 //   * MPI requests / req.Wait() (ps.py:146, mpi_comms.py:110,121)  → monotonically increasing epoch
 //     flags in the symmetric signal pad (st.release.sys / ld.acquire.sys), bounded spins.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace {
@@ -650,10 +652,18 @@ void launch_update_t(cudaStream_t s, const UpdateArgs& a, int grid) {
   if constexpr (KIND == KIND_TOPK) {
     psb_update_kernel<KIND, WIRE, OPT, 1><<<grid, PSB_THREADS, 0, s>>>(a);
   } else {
-    // fewer ranks → fewer peer loads per tile → more tiles in flight per thread
+    // U = 2 (two tiles in flight per thread, no state prefetch, 2 CTAs/SM) measured SLOWER than U = 1 (state
+    // prefetch, 3 CTAs/SM) on the ResNet-18 arena at N = 1: 72.6 us vs 52.5 us (profiles/psb_update_kernel_*.ncu.txt).
+    // It stays available for experiments (PSB200_UPDATE_U=2) but is not the default.
+    static const int force_u = [] {
+      const char* e = getenv("PSB200_UPDATE_U");
+      return e ? atoi(e) : 1;
+    }();
     const int tiles_per_cta = (a.ntiles + grid - 1) / grid;
-    if (a.world <= 4 && tiles_per_cta >= 2) psb_update_kernel<KIND, WIRE, OPT, 2><<<grid, PSB_THREADS, 0, s>>>(a);
-    else psb_update_kernel<KIND, WIRE, OPT, 1><<<grid, PSB_THREADS, 0, s>>>(a);
+    if (force_u == 2 && a.world >= 2 && a.world <= 4 && tiles_per_cta >= 2)
+      psb_update_kernel<KIND, WIRE, OPT, 2><<<grid, PSB_THREADS, 0, s>>>(a);
+    else
+      psb_update_kernel<KIND, WIRE, OPT, 1><<<grid, PSB_THREADS, 0, s>>>(a);
   }
 }
 template <int KIND, int WIRE>

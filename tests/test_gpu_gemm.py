@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 784), (1000, 3072, 768), (77, 10, 512), (4096, 768, 3072),
-                                   (8, 136, 72)])
+                                   (8, 136, 72), (5000, 64, 176), (700, 128, 256)])
 @pytest.mark.parametrize("bias,relu", [(False, False), (True, True)])
 @pytest.mark.parametrize("variant", [1, 2])
 def test_bcast_gemm_matches_fp32(M, N, K, bias, relu, variant):
