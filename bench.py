@@ -203,10 +203,11 @@ def main():
             train_step(x, y)
 
     loop_device(max(args.warmup, 3))
-    launches0 = eng.launches if eng is not None else 0
+    from pytorch_ps_mpi_b200.ops import ext as _ext
+    launches0 = _ext.cuda().launch_count()
     with ClockSampler(device.index or 0) as clk:
         ms = timed(args.steps, loop_device)
-    launches = (eng.launches - launches0) if eng is not None else 0
+    launches = _ext.cuda().launch_count() - launches0      # every psb_* kernel launched in the timed region (C++ counter)
     clocks = clk.summary()
     contributors = (w.size - 1) if (args.mode == "async" and w.size > 1) else w.size
     global_batch = args.batch * contributors

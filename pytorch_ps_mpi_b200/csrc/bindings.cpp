@@ -222,6 +222,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("timeout_s") = 30.0);
 
   m.def("update_max_grid", &psb_update_max_grid);
+  m.def("launch_count", []() { return (uint64_t)psb_launch_count(); }, "kernels of ours launched by this process so far");
   m.def("encode", &encode);
   m.def("signal", &signal, py::arg("targets"), py::arg("slot"), py::arg("value"), py::arg("extra_slot") = -1,
         py::arg("extra_value") = 0);

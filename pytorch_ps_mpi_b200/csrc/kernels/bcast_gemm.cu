@@ -522,6 +522,7 @@ void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms) 
   p.err_slot = a.ready_flag != nullptr ? const_cast<uint64_t*>(a.ready_flag) - SIG_PARAMS_READY + SIG_ERROR : nullptr;
   p.M = a.M, p.N = a.N, p.K = a.K, p.relu = a.relu;
   p.timeout_ns = a.timeout_ns;
+  psb_count_launch(1);
   if (a.two_cta) {
     const int bnt = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
     const int tiles = ((a.M + 255) / 256) * ((a.N + bnt - 1) / bnt);

@@ -291,6 +291,7 @@ void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* 
   auto X = reinterpret_cast<const __nv_bfloat16*>(x);
   auto R = reinterpret_cast<const __nv_bfloat16*>(res);
   auto Y = reinterpret_cast<__nv_bfloat16*>(y);
+  psb_count_launch(training ? 3 : 1);
   if (training) {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
     psb_bn_stats<<<grid, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
@@ -315,6 +316,7 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
   auto DY = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto X = reinterpret_cast<const __nv_bfloat16*>(x);
   auto Y = reinterpret_cast<const __nv_bfloat16*>(y);
+  psb_count_launch(3);
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
   const size_t sm = sizeof(float) * g.lanes * C;
   if (relu) psb_bn_bwd_reduce<true><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, mean, rstd, sums, g);

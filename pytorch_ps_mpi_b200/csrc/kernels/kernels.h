@@ -103,3 +103,7 @@ void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, 
 void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW);
 void psb_im2col_stem_launch(cudaStream_t s, const void* x, void* a, int N, int H, int W);
 void psb_normalize_nhwc3_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW);
+
+// process-wide count of OUR kernel launches (every psb_* launcher adds to it; bench.py reports the delta)
+void psb_count_launch(int n);
+unsigned long long psb_launch_count();

@@ -110,6 +110,7 @@ int pool_grid(long long total) {
 }  // namespace
 
 void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg, int N, int H, int W, int C) {
+  psb_count_launch(1);
   PoolGeom g{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
   const long long total = (long long)N * g.OH * g.OW * g.groups;
   psb_maxpool_fwd<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
@@ -117,6 +118,7 @@ void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg,
 }
 
 void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, void* dx, int N, int H, int W, int C) {
+  psb_count_launch(1);
   PoolGeom g{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
   const long long total = (long long)N * H * W * g.groups;
   psb_maxpool_bwd<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const uint8_t*>(arg),
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) psb_normalize_pad8(const uint8_t* __restr
 }  // namespace
 
 void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW) {
+  psb_count_launch(1);
   const long long total = (long long)N * HW;
   psb_normalize_pad8<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(x), reinterpret_cast<__nv_bfloat16*>(y),
                                                       mean[0], mean[1], mean[2], inv_std[0], inv_std[1], inv_std[2], N, HW);
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(256) psb_normalize_nhwc3(const uint8_t* __rest
 }  // namespace
 
 void psb_im2col_stem_launch(cudaStream_t s, const void* x, void* a, int N, int H, int W) {
+  psb_count_launch(1);
   const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
   const long long total = (long long)N * OH * OW * 7;
   psb_im2col_stem<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(a), N,
@@ -229,6 +233,7 @@ void psb_im2col_stem_launch(cudaStream_t s, const void* x, void* a, int N, int H
 }
 
 void psb_normalize_nhwc3_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW) {
+  psb_count_launch(1);
   const long long total = (long long)N * HW;
   psb_normalize_nhwc3<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(x), reinterpret_cast<__nv_bfloat16*>(y),
                                                        mean[0], mean[1], mean[2], inv_std[0], inv_std[1], inv_std[2], N, HW);

@@ -677,14 +677,23 @@ void launch_update_o(cudaStream_t s, int opt, const UpdateArgs& a, int grid) {
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+#include <atomic>
+static std::atomic<unsigned long long> g_psb_launches{0};
+void psb_count_launch(int n) { g_psb_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long psb_launch_count() { return g_psb_launches.load(std::memory_order_relaxed); }
+
 void psb_launch_absmax(cudaStream_t s, const EncodeArgs& a) {
   const int ctas = a.batch.cum[a.batch.n];
-  if (ctas > 0) psb_absmax_kernel<<<ctas, PSB_THREADS, 0, s>>>(a);
+  if (ctas > 0) {
+    psb_absmax_kernel<<<ctas, PSB_THREADS, 0, s>>>(a);
+    psb_count_launch(1);
+  }
 }
 
 void psb_launch_encode(cudaStream_t s, int kind, int wire, const EncodeArgs& a) {
   const int ctas = a.batch.cum[a.batch.n];
   if (ctas <= 0) return;
+  psb_count_launch(1);
 #define ENC(K, W)                                            \
   if (kind == K && wire == W) {                              \
     psb_encode_kernel<K, W><<<ctas, PSB_THREADS, 0, s>>>(a); \
@@ -697,6 +706,7 @@ void psb_launch_encode(cudaStream_t s, int kind, int wire, const EncodeArgs& a) 
 }
 
 void psb_launch_update(cudaStream_t s, int kind, int wire, int opt, const UpdateArgs& a, int grid) {
+  psb_count_launch(1);
 #define UPD(K, W)                                \
   if (kind == K && wire == W) {                  \
     launch_update_o<K, W>(s, opt, a, grid);      \
@@ -727,14 +737,17 @@ void psb_launch_signal(cudaStream_t s, uint64_t* const* targets, int ntargets, i
   a.extra_slot = extra_slot;
   a.extra_value = extra_value;
   psb_signal_kernel<<<1, 32, 0, s>>>(a);
+  psb_count_launch(1);
 }
 
 void psb_launch_wait(cudaStream_t s, const uint64_t* signal_local, int slot0, uint32_t mask, uint64_t want,
                      unsigned long long timeout_ns) {
   psb_wait_kernel<<<1, 32, 0, s>>>(signal_local, slot0, mask, want, timeout_ns);
+  psb_count_launch(1);
 }
 
 void psb_launch_select(cudaStream_t s, const uint64_t* signal_local, uint64_t* consumed, uint32_t cand_mask,
                        int quota, uint64_t* out, unsigned long long timeout_ns) {
   psb_select_kernel<<<1, 32, 0, s>>>(signal_local, consumed, cand_mask, quota, out, timeout_ns);
+  psb_count_launch(1);
 }
