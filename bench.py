@@ -54,7 +54,8 @@ def reference_unavailable():
     why = ("reference is not installable: /root/reference has no setup.py/pyproject.toml (pip: 'not installable'), "
            "its deps mpi4py/blosc/toolz/distributed/codings are absent offline, and mpi_comms.py:50 "
            "(d.cuda(async=True)) is a SyntaxError on Python 3.12")
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if os.environ.get("RANK", "0") == "0":          # under torchrun only rank 0 reports
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 

@@ -1,0 +1,44 @@
+"""The native extensions exist, import on a CPU-only box, and the CUDA objects really are sm_100a code
+using the Blackwell paths (SASS mnemonics, B200_PROFILING.md §"What proves a Blackwell-native kernel")."""
+import shutil
+import subprocess
+
+import pytest
+
+from pytorch_ps_mpi_b200.ops import ext
+
+
+def test_host_extension_imports_and_works():
+    h = ext.host()
+    assert h.ANY_SOURCE == -1
+    raw = bytes(range(64))
+    assert bytes(h.byteunshuffle(h.byteshuffle(raw, 4), 4)) == raw
+
+
+def test_cuda_extension_imports_without_a_gpu():
+    if not ext.CUDA_SO.exists():
+        pytest.skip("CUDA extension not built yet (run __graft_entry__.build())")
+    m = ext.cuda()
+    for name in ("SymmBlock", "UpdatePlan", "encode", "signal", "wait_flags", "select_ready", "bcast_gemm",
+                 "bn_forward", "bn_backward", "maxpool_forward", "im2col_stem", "normalize_nhwc3", "launch_count"):
+        assert hasattr(m, name), name
+    assert m.TILE == 2048 and m.MAX_RANKS >= 8
+
+
+def _sass(obj):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    return subprocess.run([exe, "-sass", str(obj)], stdout=subprocess.PIPE, text=True, check=True).stdout
+
+
+def test_sass_shows_blackwell_paths():
+    gemm, psk = ext.OBJ / "bcast_gemm.o", ext.OBJ / "ps_kernels.o"
+    if not gemm.exists() or not psk.exists():
+        pytest.skip("object files not present (built elsewhere)")
+    s = _sass(gemm)
+    assert "sm_100a" in s or "SM100" in s.upper() or "EF_CUDA_SM100" in s
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D", "UTMALDG.2D.2CTA", "LDTM", "UTCBAR.2CTA.MULTICAST"):
+        assert mnemonic in s, f"{mnemonic} missing from bcast_gemm SASS"
+    p = _sass(psk)
+    assert "STRONG.SYS" in p            # system-scope peer loads/stores of the gather / broadcast
+    ptx_like = subprocess.run(["strings", str(psk)], stdout=subprocess.PIPE, text=True).stdout
+    assert "HMMA" not in s.replace("UTCHMMA", "")      # no legacy mma.sync tensor path in the GEMM
