@@ -130,6 +130,7 @@ class DeviceEngine:
         self.active_dev = torch.ones(max(L.nparams, 1), dtype=torch.uint8, device=self.device)
         self.active_host = torch.ones(max(L.nparams, 1), dtype=torch.uint8).pin_memory()
         self._active_all = True
+        self._last_fired = None
         self.counters = torch.zeros(8, dtype=torch.int32, device=self.device)   # [0] done, [1] stats
         self.residual = None
         if self.kind == KIND_TOPK and self.spec.error_feedback:
@@ -368,7 +369,12 @@ class DeviceEngine:
                 self.active_host.fill_(1)
                 self.active_dev.copy_(self.active_host, non_blocking=True)
                 self._active_all = True
+                self._last_fired = None
             return 0
+        fired = frozenset(self._fired)
+        if fired == self._last_fired:        # same frozen / unused set as last step: mask and zeroed tiles still valid
+            return self.active_dev.data_ptr()
+        self._last_fired = fired
         self.active_host.zero_()
         for i in self._fired:
             self.active_host[i] = 1

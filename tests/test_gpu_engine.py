@@ -160,3 +160,27 @@ def test_bcast_linear_gated_multi_gpu(pull):
 @pytest.mark.multigpu
 def test_async_multi_gpu():
     spawn(_mp.gpu_async, min(torch.cuda.device_count(), 4), ("topk",), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
+
+
+def test_device_engine_with_lr_scheduler():
+    def run(factory):
+        dev = torch.device("cuda", 0)
+        torch.manual_seed(0)
+        model = mnist_mlp(hidden=32).to(dev)
+        opt = factory(model)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
+        for s in range(5):
+            g = torch.Generator().manual_seed(s)
+            x, y = torch.randn(8, 784, generator=g).to(dev), torch.randint(0, 10, (8,), generator=g).to(dev)
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            opt.step()
+            sched.step()
+        torch.cuda.synchronize()
+        return [p.detach().clone() for p in model.parameters()], opt
+
+    a, o = run(lambda m: ps.SGD(m.named_parameters(), m.parameters(), lr=0.2, momentum=0.9, engine="device"))
+    b, _ = run(lambda m: torch.optim.SGD(m.parameters(), lr=0.2, momentum=0.9))
+    for p, q in zip(a, b):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    o.close()

@@ -170,3 +170,26 @@ def test_user_coding_slow_path():
     opt.step()
     assert torch.allclose(p.detach(), torch.full((4,), -2.0))
     opt.close()
+
+
+def test_lr_scheduler_is_honoured():
+    def run(factory):
+        torch.manual_seed(0)
+        model = mnist_mlp(hidden=8)
+        opt = factory(model)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
+        for s in range(5):
+            g = torch.Generator().manual_seed(s)
+            x, y = torch.randn(4, 784, generator=g), torch.randint(0, 10, (4,), generator=g)
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            opt.step()
+            sched.step()
+        return [p.detach().clone() for p in model.parameters()], opt
+
+    a, o = run(lambda m: ps.SGD(m.named_parameters(), m.parameters(), lr=0.2, momentum=0.9))
+    b, _ = run(lambda m: torch.optim.SGD(m.parameters(), lr=0.2, momentum=0.9))
+    for p, q in zip(a, b):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+    assert abs(o.param_groups[0]["lr"] - 0.2 * 0.25) < 1e-12
+    o.close()
