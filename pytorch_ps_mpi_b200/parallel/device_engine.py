@@ -159,9 +159,17 @@ class DeviceEngine:
         nvls_ok = mc and self.kind == KIND_DENSE and self.wire in (WIRE_F32, WIRE_BF16, WIRE_F16) and self.size > 1
         if reduce == "nvls" and not nvls_ok:
             raise ValueError("reduce='nvls' needs multicast memory and a dense fp32/bf16/fp16 wire")
-        # 'auto' keeps the rank-ordered (bit-reproducible) P2P sum; 'nvls' lets the switch reduce
-        self.reduce = 1 if (reduce == "nvls" or (reduce == "auto" and nvls_ok and
-                                                 os.environ.get("PSB200_REDUCE", "") == "nvls")) else 0
+        # 'auto': the switch reduces (multimem.ld_reduce: server ingress 1x instead of (N-1)x, 1.9-2x faster than
+        # the P2P pull at 16-64 MB on 8 GPUs) when that is exact — fp32 wires, one reducer (ps / async), N >= 4;
+        # everything else keeps the rank-ordered P2P sum (bf16 wires would get a bf16-rounded switch sum, and in
+        # allgather mode every rank must produce bit-identical sums).  'nvls' / 'p2p' force either.
+        auto_nvls = (nvls_ok and self.wire == WIRE_F32 and self.mode in ("ps", "async") and self.size >= 4
+                     and os.environ.get("PSB200_REDUCE", "") != "p2p")
+        if reduce == "p2p":
+            self.reduce = 0
+        else:
+            self.reduce = 1 if (reduce == "nvls" or (reduce == "auto" and (auto_nvls or (
+                nvls_ok and os.environ.get("PSB200_REDUCE", "") == "nvls")))) else 0
 
         # ---- the launch plan ----
         self.plan = None
