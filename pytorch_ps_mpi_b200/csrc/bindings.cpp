@@ -62,7 +62,7 @@ struct UpdatePlan {
 
   void launch(uint64_t epoch, const std::vector<std::vector<double>>& groups, uint32_t contrib_mask, double inv_count,
               int wait_grads, int signal_mode, uint32_t ack_mask, uint64_t version, uint64_t select_out,
-              int average_dynamic, uint64_t active_ptr, double timeout_s) {
+              int average_dynamic, uint64_t active_ptr, double timeout_s, uint32_t wait_mask) {
     if (groups.size() > PSB_MAX_GROUPS) throw std::runtime_error("too many param groups for one launch");
     for (size_t i = 0; i < groups.size(); ++i) {
       const auto& g = groups[i];
@@ -74,6 +74,7 @@ struct UpdatePlan {
     }
     a.epoch = epoch;
     a.contrib_mask = contrib_mask;
+    a.wait_mask = wait_mask;
     a.inv_count = (float)inv_count;
     a.wait_grads = wait_grads;
     a.signal_mode = signal_mode;
@@ -219,7 +220,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("launch", &UpdatePlan::launch, py::arg("epoch"), py::arg("groups"), py::arg("contrib_mask"),
            py::arg("inv_count"), py::arg("wait_grads"), py::arg("signal_mode"), py::arg("ack_mask") = 0,
            py::arg("version") = 0, py::arg("select_out") = 0, py::arg("average_dynamic") = 0, py::arg("active_ptr") = 0,
-           py::arg("timeout_s") = 30.0);
+           py::arg("timeout_s") = 30.0, py::arg("wait_mask") = 0xffffffffu);
 
   m.def("update_max_grid", &psb_update_max_grid);
   m.def("launch_count", []() { return (uint64_t)psb_launch_count(); }, "kernels of ours launched by this process so far");

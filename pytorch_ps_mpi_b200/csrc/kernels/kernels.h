@@ -50,6 +50,8 @@ struct UpdateArgs {
   int32_t world, rank, ntiles, bytes_per_tile, cap;
   int32_t param_dt, bcast, reduce;
   uint32_t contrib_mask;               // ranks whose gradient is summed
+  uint32_t wait_mask;                  // ranks whose GRAD_READY flag is awaited (the launching rank's own gradient is
+                                       // ordered by the stream, so it is normally excluded)
   float inv_count;                     // 1 or 1/#contributors (average=True)
   uint64_t epoch;
   int32_t wait_grads;                  // spin on SIG_GRAD_READY of every contributor first

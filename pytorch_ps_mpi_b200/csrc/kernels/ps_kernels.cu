@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(PSB_THREADS, U == 1 ? 3 : 2) psb_update_kernel
   // ---- 1. the req.Wait() of the reference: every contributor's epoch flag ----
   if (a.wait_grads) {
     bool ok = true;
-    if (tid < a.world && (contrib >> tid & 1u))
+    if (tid < a.world && (contrib & a.wait_mask) >> tid & 1u)
       ok = spin_until_ge(a.signal_local + SIG_GRAD_READY + tid, a.epoch, err_slot, a.timeout_ns);
     if (!__syncthreads_and(ok)) return;
   }

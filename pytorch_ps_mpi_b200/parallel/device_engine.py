@@ -418,9 +418,11 @@ class DeviceEngine:
             active_ptr = self._handle_inactive()
             ev_a = self._prof.mark(cs)
             if self.size > 1:
-                targets = [sig_base[0]] if self.mode == "ps" else sig_base
-                self.m.signal(targets, self.m.SIG_GRAD_READY + self.rank, epoch)
-                self.launches += 1
+                # the launching rank's own gradient is ordered by the stream, so it neither signals nor waits itself
+                targets = [sig_base[0]] if self.mode == "ps" else [b for r, b in enumerate(sig_base) if r != self.rank]
+                if not (self.mode == "ps" and self.rank == 0):
+                    self.m.signal(targets, self.m.SIG_GRAD_READY + self.rank, epoch)
+                    self.launches += 1
             data["isend_time"] = time.time() - t1
             t2 = time.time()
             ev_b = self._prof.mark(cs)
@@ -429,7 +431,8 @@ class DeviceEngine:
                 inv = (1.0 / n) if o.average else 1.0
                 self.plan.launch(epoch, self._hypers(), (1 << n) - 1, inv, 1 if n > 1 else 0,
                                  0 if n == 1 else (1 if self.mode == "ps" else 2),
-                                 active_ptr=active_ptr, timeout_s=self.timeout_s)
+                                 active_ptr=active_ptr, timeout_s=self.timeout_s,
+                                 wait_mask=((1 << n) - 1) & ~(1 << self.rank))
                 self.launches += 1
             else:
                 self._hypers()               # keep per-group step counters aligned with the server
