@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--seq", type=int, default=128, help="sequence length (bert_base)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--comparator-kind", default="host", choices=["host", "nccl"])
+    ap.add_argument("--bcast-gemm", default="off", choices=["off", "gate", "pull"],
+                    help="first forward GEMM on the tcgen05 kernel, gated on the PS broadcast (pull: weight tiles TMA-loaded from the server over NVLink)")
     ap.add_argument("--profile", action="store_true", help="CUDA-event section timings of the PS path (stderr)")
     return ap.parse_args()
 
@@ -96,13 +98,13 @@ def build(args, device, ps):
             return torch.nn.functional.cross_entropy(model(xb).float(), y)
         cfg = {"global_batch": None, "image": "3x224x224 uint8"}
     elif args.model == "mlp":
-        model = models.mnist_mlp().to(device)
+        model = models.mnist_mlp(hidden=4096).to(device).bfloat16()
 
         def make_batch(gen):
-            return torch.randn(args.batch, 1, 28, 28, generator=gen), torch.randint(0, 10, (args.batch,), generator=gen)
+            return torch.randn(args.batch, 1, 28, 28, generator=gen).bfloat16(), torch.randint(0, 10, (args.batch,), generator=gen)
 
         def loss_fn(x, y):
-            return torch.nn.functional.cross_entropy(model(x), y)
+            return torch.nn.functional.cross_entropy(model(x).float(), y)
         cfg = {}
     else:
         model = models.bert_base().to(device).bfloat16()
@@ -157,6 +159,10 @@ def main():
         opt = cls(named, [p for _, p in named], code=make_code(ps, args.code), mode=args.mode, engine="device",
                   average=True, profile=args.profile, **hyper)
     eng = getattr(opt, "_engine", None)
+    if args.bcast_gemm != "off" and eng is not None:
+        from pytorch_ps_mpi_b200.ops.linear import convert_first_linear
+        layer = convert_first_linear(model, opt, relu=(args.model == "mlp"), pull=(args.bcast_gemm == "pull"))
+        assert layer is not None, "model has no nn.Linear to convert"
 
     # distinct batches so no step re-reads a cached input; pinned host copies for the e2e arm
     gen = torch.Generator().manual_seed(1234 + w.rank)
@@ -260,11 +266,11 @@ def main():
                       else f"samples/sec (whole box, device-timed, max over ranks), {args.model} PS-{args.optim.upper()}",
             "value": value, "unit": "samples/sec", "n_gpus": w.size, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.model != "mlp" else "fp32", "data": "synthetic (random images/labels, random-init weights)",
+            "dtype": "bf16", "data": "synthetic (random images/labels, random-init weights)",
             "impl": args.impl if args.impl != "comparator" else f"comparator-{args.comparator_kind}",
             "config": {"model": args.model, "global_batch": global_batch, "per_gpu_batch": args.batch,
                        "seq_len": cfg.get("seq_len"), "parallelism": f"dp{w.size} (rank-0 parameter server, mode={args.mode})",
-                       "optimizer": args.optim, "coding": args.code, "memory_format": "channels_last",
+                       "optimizer": args.optim, "coding": args.code, "bcast_gemm": args.bcast_gemm, "memory_format": "channels_last",
                        "l2": "inputs larger than L2: 4 rotating input batches; per-step activations+weights >> 126 MB, no explicit flush",
                        "symmetric_memory": getattr(getattr(eng, "arena", None), "provider", None),
                        "multicast": bool(getattr(getattr(eng, "arena", None), "has_multicast", False)),
