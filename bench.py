@@ -161,7 +161,9 @@ def main():
     eng = getattr(opt, "_engine", None)
     if args.bcast_gemm != "off" and eng is not None:
         from pytorch_ps_mpi_b200.ops.linear import convert_first_linear
-        layer = convert_first_linear(model, opt, relu=(args.model == "mlp"), pull=(args.bcast_gemm == "pull"))
+        # the in-kernel gate replaces the wait kernel only where the first linear is the first parameter consumer (MLP)
+        layer = convert_first_linear(model, opt, relu=(args.model == "mlp"), pull=(args.bcast_gemm == "pull"),
+                                     gate=(args.model == "mlp"))
         assert layer is not None, "model has no nn.Linear to convert"
 
     # distinct batches so no step re-reads a cached input; pinned host copies for the e2e arm

@@ -70,21 +70,29 @@ class BcastLinear(nn.Linear):
         self.relu = relu
         self._engine = None
         self._pull = False
+        self._gate = True
 
-    def attach(self, optimizer, pull: bool = False) -> "BcastLinear":
-        """Gate this layer's weight loads on ``optimizer``'s broadcast epoch (device engine only)."""
+    def attach(self, optimizer, pull: bool = False, gate: bool = True) -> "BcastLinear":
+        """Bind this layer to ``optimizer``'s device engine.
+
+        ``gate=True``: the kernel's TMA producer acquires the broadcast epoch itself and workers stop queueing
+        the separate wait kernel — only valid when this layer is the FIRST consumer of parameters in the
+        forward pass (an MLP's first layer; NOT BERT's first linear, whose embeddings are read earlier).
+        ``gate=False``: the engine keeps its wait kernel; the layer just runs on the tcgen05 GEMM.
+        ``pull=True``: weight tiles are TMA-loaded from the server's arena over NVLink."""
         eng = getattr(optimizer, "_engine", None)
         if eng is None:
             raise ValueError("attach() needs an optimizer running the device engine")
-        self._engine, self._pull = eng, pull
-        eng.register_gate(self)
+        self._engine, self._pull, self._gate = eng, pull, gate
+        if gate:
+            eng.register_gate(self)
         return self
 
     def forward(self, x):
         eng = self._engine
         if eng is None or not self.weight.is_cuda:
             return bcast_linear(x, self.weight, self.bias, self.relu)
-        flag_ptr, epoch = eng.gate()
+        flag_ptr, epoch = eng.gate() if self._gate else (0, 0)
         w_ptr = eng.peer_param_ptr(self.weight, 0) if (self._pull and eng.size > 1) else 0
         return bcast_linear(x, self.weight, self.bias, self.relu, w_ptr, flag_ptr, epoch)
 
@@ -96,7 +104,8 @@ class BcastLinear(nn.Linear):
         return new
 
 
-def convert_first_linear(model: nn.Module, optimizer=None, relu: bool = False, pull: bool = False) -> Optional[BcastLinear]:
+def convert_first_linear(model: nn.Module, optimizer=None, relu: bool = False, pull: bool = False,
+                         gate: bool = True) -> Optional[BcastLinear]:
     """Swap the FIRST ``nn.Linear`` of ``model`` (the first forward GEMM) for a :class:`BcastLinear`
     sharing the same parameters, and — given a device-engine optimizer — gate it on the broadcast."""
     for parent in model.modules():
@@ -105,6 +114,6 @@ def convert_first_linear(model: nn.Module, optimizer=None, relu: bool = False, p
                 new = BcastLinear.from_linear(child, relu=relu)
                 setattr(parent, name, new)
                 if optimizer is not None and getattr(optimizer, "_engine", None) is not None:
-                    new.attach(optimizer, pull=pull)
+                    new.attach(optimizer, pull=pull, gate=gate)
                 return new
     return None
