@@ -211,10 +211,13 @@ def main():
             x, y = dev[i % nbuf]
             train_step(x, y)
 
-    loop_device(max(args.warmup, 3))
     from pytorch_ps_mpi_b200.ops import ext as _ext
-    launches0 = _ext.cuda().launch_count()
+    # the sampler (an nvidia-smi child process) starts BEFORE the warm-up so that its NVML start-up cost does not
+    # land inside the timed region (it cost ~1 ms/step on a 160 ms region); it keeps polling through the timed steps
     with ClockSampler(device.index or 0) as clk:
+        loop_device(max(args.warmup, 3))
+        launches0 = _ext.cuda().launch_count()
+        clk.mark()
         ms = timed(args.steps, loop_device)
     launches = _ext.cuda().launch_count() - launches0      # every psb_* kernel launched in the timed region (C++ counter)
     clocks = clk.summary()

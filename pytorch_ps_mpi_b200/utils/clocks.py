@@ -21,6 +21,7 @@ class ClockSampler:
         self._proc: Optional[subprocess.Popen] = None
         self._lines: List[str] = []
         self._thread: Optional[threading.Thread] = None
+        self._mark = 0
 
     def __enter__(self):
         exe = shutil.which("nvidia-smi")
@@ -53,10 +54,14 @@ class ClockSampler:
                 self._thread.join(timeout=2)
         return False
 
+    def mark(self) -> None:
+        """Samples taken before this call (e.g. during warm-up) are ignored by :meth:`summary`."""
+        self._mark = max(0, len(self._lines) - 1)      # keep the most recent one so short regions still have a sample
+
     def summary(self) -> Dict:
         sm, smax, power = [], [], []
         reasons = set()
-        for ln in self._lines:
+        for ln in self._lines[self._mark:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
