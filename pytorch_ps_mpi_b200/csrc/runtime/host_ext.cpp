@@ -20,6 +20,7 @@
 #include <chrono>
 #include <csignal>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <fcntl.h>
@@ -377,11 +378,28 @@ class ShmComm {
 
   void abort() { hdr_->aborted.store(1); }
 
+  // A peer is gone if its pid no longer exists OR it is a zombie (exited, not yet reaped by its parent —
+  // kill(pid, 0) still succeeds for those).
+  static bool pid_alive(int32_t pid) {
+    if (kill(pid, 0) != 0 && errno == ESRCH) return false;
+    char path[64], buf[256];
+    snprintf(path, sizeof(path), "/proc/%d/stat", (int)pid);
+    FILE* f = fopen(path, "r");
+    if (!f) return errno != ENOENT;   // no /proc (or no permission): trust kill()
+    bool alive = true;
+    if (fgets(buf, sizeof(buf), f)) {
+      const char* rp = strrchr(buf, ')');           // "pid (comm) S ..."
+      if (rp && rp[1] == ' ' && (rp[2] == 'Z' || rp[2] == 'X')) alive = false;
+    }
+    fclose(f);
+    return alive;
+  }
+
   std::vector<int> dead_peers() const {
     std::vector<int> dead;
     for (int r = 0; r < world_; ++r) {
       int32_t pid = hdr_->pids[r].load();
-      if (r != rank_ && pid > 0 && kill(pid, 0) != 0 && errno == ESRCH) dead.push_back(r);
+      if (r != rank_ && pid > 0 && !pid_alive(pid)) dead.push_back(r);
     }
     return dead;
   }

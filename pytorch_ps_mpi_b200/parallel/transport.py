@@ -56,7 +56,10 @@ class _Done(Request):
 class Transport:
     rank: int = 0
     size: int = 1
-    default_timeout: float = float(os.environ.get("PSB200_COMM_TIMEOUT", "300"))
+    @property
+    def default_timeout(self) -> float:
+        """Seconds a blocking wait may take before it raises (``PSB200_COMM_TIMEOUT``, read at use)."""
+        return float(os.environ.get("PSB200_COMM_TIMEOUT", "300"))
 
     def isend(self, dst: int, data, tag: int = 0) -> Request:
         raise NotImplementedError

@@ -406,3 +406,71 @@ def gpu_dead_peer(rank, size):
         except RuntimeError as e:
             assert "timed out" in str(e)
     w.barrier()
+
+
+# --- host-path robustness ---------------------------------------------------------------------------
+def shm_dead_peer(rank, size):
+    """Failure detection on the CPU transport: a rank that dies must surface as an error on its peers."""
+    os.environ["PSB200_TRANSPORT"] = "shm"
+    os.environ["PSB200_COMM_TIMEOUT"] = "20"
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.parallel import transport as tp
+    tr = tp.get_transport()
+    assert isinstance(tr, tp.ShmTransport)
+    tr.barrier()
+    if rank == 1:
+        os._exit(0)                       # vanish without saying goodbye
+    import time
+    time.sleep(0.5)
+    req = tr.irecv(src=1, tag=5)
+    try:
+        req.Wait()
+        raise AssertionError("expected the dead peer to be detected")
+    except RuntimeError as e:
+        assert "no longer running" in str(e) or "timed out" in str(e), str(e)
+    assert tr.dead_peers() == [1]
+    os._exit(0)                           # skip the collective teardown: the peer is gone
+
+
+def mlp_average_and_groups(rank, size, transport):
+    """average=True divides by the number of contributions; several param groups keep their own hyper-parameters."""
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    torch.manual_seed(0)
+    a = torch.nn.Parameter(torch.ones(5))
+    b = torch.nn.Parameter(torch.ones(3))
+    opt = ps.SGD([("a", a), ("b", b)], [{"params": [a], "lr": 0.1}, {"params": [b], "lr": 1.0}], lr=0.01,
+                 mode="ps", average=True)
+    ((rank + 1) * a.sum() + 2 * (rank + 1) * b.sum()).backward()
+    opt.step()
+    mean = sum(r + 1 for r in range(size)) / size
+    assert torch.allclose(a.detach(), torch.full((5,), 1 - 0.1 * mean)), a
+    assert torch.allclose(b.detach(), torch.full((3,), 1 - 1.0 * 2 * mean)), b
+    opt.close()
+
+
+def mlp_async_consistent(rank, size):
+    """consistent=True (README.md:79-81): every worker step adopts a whole parameter snapshot from the server."""
+    os.environ["PSB200_TRANSPORT"] = "shm"
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=16)
+    opt = ps.SGD(model.named_parameters(), model.parameters(), lr=0.05, mode="async", quota=size - 1, consistent=True)
+    if rank == 0:
+        n = opt.serve()
+        assert n == 3
+    else:
+        versions = []
+        for s in range(3):
+            x, y = _mlp_data(rank, s)
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            _, data = opt.step()
+            versions.append(data["param_version"])
+        assert versions == [1, 2, 3], versions        # blocks for the snapshot that contains its own gradient
+    opt.close()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    allp = w.all_gather_object(flat)
+    for f in allp[1:]:
+        assert torch.equal(f, allp[1])

@@ -28,3 +28,19 @@ def test_mlp_sync_three_ranks():
 @pytest.mark.parametrize("transport", ["shm", "gloo"])
 def test_mlp_async(transport):
     spawn(_mp.mlp_async, 3, (transport,))
+
+
+def test_shm_transport_detects_dead_peer():
+    from pytorch_ps_mpi_b200.launch import spawn as _spawn
+    import multiprocessing
+    # rank 1 exits with os._exit(0) on purpose; rank 0 must notice instead of hanging
+    _spawn(_mp.shm_dead_peer, 2, timeout=90)
+
+
+@pytest.mark.parametrize("transport", ["shm", "gloo"])
+def test_average_and_param_groups(transport):
+    spawn(_mp.mlp_average_and_groups, 3, (transport,))
+
+
+def test_async_consistent_reads():
+    spawn(_mp.mlp_async_consistent, 3)
