@@ -91,7 +91,8 @@ struct UpdatePlan {
 
 void encode(int kind, int wire, const std::vector<at::Tensor>& grads, const std::vector<int>& first_tile,
             const std::vector<int>& ntiles, const std::vector<int>& param_idx, uint64_t tiles_ptr, uint64_t wire_ptr,
-            uint64_t scales_ptr, uint64_t amax_ptr, uint64_t residual_ptr, int bytes_per_tile, int cap, double ratio) {
+            uint64_t scales_ptr, uint64_t amax_ptr, uint64_t residual_ptr, int bytes_per_tile, int cap, double ratio,
+            const std::vector<uint64_t>& sig_targets, int sig_slot, uint64_t sig_value, uint64_t sig_counter) {
   const size_t n = grads.size();
   if (first_tile.size() != n || ntiles.size() != n || param_idx.size() != n) throw std::runtime_error("encode: length mismatch");
   if (n == 0) return;
@@ -123,6 +124,15 @@ void encode(int kind, int wire, const std::vector<at::Tensor>& grads, const std:
     if (kind == KIND_SCALED) {
       psb_launch_absmax(s, a);
       check_launch("psb_absmax_kernel launch");
+    }
+    a.nsig = 0;
+    if (!sig_targets.empty() && base + PSB_ENCODE_MAX >= n) {   // only the last launch of this call raises the flag
+      if (sig_targets.size() > PSB_MAX_RANKS) throw std::runtime_error("encode: too many signal targets");
+      a.nsig = (int)sig_targets.size();
+      for (size_t i = 0; i < sig_targets.size(); ++i) a.sig_targets[i] = reinterpret_cast<uint64_t*>(sig_targets[i]);
+      a.sig_slot = sig_slot;
+      a.sig_value = sig_value;
+      a.sig_counter = reinterpret_cast<unsigned int*>(sig_counter);
     }
     psb_launch_encode(s, kind, wire, a);
     check_launch("psb_encode_kernel launch");
@@ -224,7 +234,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 
   m.def("update_max_grid", &psb_update_max_grid);
   m.def("launch_count", []() { return (uint64_t)psb_launch_count(); }, "kernels of ours launched by this process so far");
-  m.def("encode", &encode);
+  m.def("encode", &encode, py::arg("kind"), py::arg("wire"), py::arg("grads"), py::arg("first_tile"), py::arg("ntiles"),
+        py::arg("param_idx"), py::arg("tiles_ptr"), py::arg("wire_ptr"), py::arg("scales_ptr"), py::arg("amax_ptr"),
+        py::arg("residual_ptr"), py::arg("bytes_per_tile"), py::arg("cap"), py::arg("ratio"),
+        py::arg("sig_targets") = std::vector<uint64_t>{}, py::arg("sig_slot") = 0, py::arg("sig_value") = 0,
+        py::arg("sig_counter") = 0);
   m.def("signal", &signal, py::arg("targets"), py::arg("slot"), py::arg("value"), py::arg("extra_slot") = -1,
         py::arg("extra_value") = 0);
   m.def("wait_flags", &wait_flags);

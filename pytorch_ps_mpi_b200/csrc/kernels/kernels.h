@@ -27,6 +27,13 @@ struct EncodeArgs {
   int32_t cap;           // top-k entries per tile
   double ratio;
   int32_t grad_dt;
+  // optional fused flag raise: when this is the LAST encode launch of the step, its last CTA publishes
+  // GRAD_READY itself (saves the separate psb_signal_kernel launch on the critical path)
+  uint64_t* sig_targets[PSB_MAX_RANKS];
+  int32_t nsig;
+  int32_t sig_slot;
+  uint64_t sig_value;
+  unsigned int* sig_counter;   // zero before launch; left zero
 };
 
 struct UpdateArgs {

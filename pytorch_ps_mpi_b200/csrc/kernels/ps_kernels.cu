@@ -247,6 +247,22 @@ __global__ void __launch_bounds__(PSB_THREADS) psb_encode_kernel(const __grid_co
       r[1] = make_float4(g[4], g[5], g[6], g[7]);
     }
   }
+
+  // ---- fused flag raise (last encode launch of the step): the last CTA to finish publishes GRAD_READY ----
+  if (a.nsig > 0) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();                       // this CTA's wire tile is visible system-wide
+      s_last = (atomicAdd(a.sig_counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      if (tid == 0) *a.sig_counter = 0;
+      __threadfence_system();
+      if (tid < a.nsig && a.sig_targets[tid] != nullptr) st_release_sys(a.sig_targets[tid] + a.sig_slot, a.sig_value);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -94,12 +94,19 @@ class DeviceEngine:
         self.off_wire = self.off_scales + _align(max(L.nparams, 1) * 4)
         self.off_param = self.off_wire + _align(nt * self.bpt)
         total = self.off_param + _align(n_pad * self.psz)
+        # consistent reads (README.md:79-81 "a buffered broadcast"): the server publishes into a STAGING copy of
+        # the parameter arena; workers adopt whole snapshots from it under a sequence lock (see _snapshot)
+        self.consistent = bool(getattr(opt, "consistent", False)) and self.mode == "async" and self.size > 1
+        self.off_stage = total
+        if self.consistent:
+            total += _align(n_pad * self.psz)
         self.arena = SymmetricArena(total, self.device, self.world)
         A = self.arena
         self.signal = A.tensor(self.off_signal, self.m.SIGNAL_SLOTS * 8, torch.int64)
         self.scales = A.tensor(self.off_scales, max(L.nparams, 1) * 4, torch.float32)
         self.wire_arena = A.tensor(self.off_wire, nt * self.bpt, torch.uint8)
         self.param_arena = A.tensor(self.off_param, n_pad * self.psz, self.dtype)
+        self.stage_arena = A.tensor(self.off_stage, n_pad * self.psz, self.dtype) if self.consistent else None
 
         # ---- move the model's parameters into the parameter arena (zero-copy from now on) ----
         with torch.no_grad():
@@ -122,6 +129,11 @@ class DeviceEngine:
             self.param_arena.copy_(src)
             torch.cuda.synchronize(self.device)
         self.world.barrier()
+
+        if self.consistent:
+            self.stage_arena.copy_(self.param_arena)
+            torch.cuda.synchronize(self.device)
+            self.world.barrier()
 
         # ---- server-side state ----
         self.is_server = (self.mode == "allgather") or self.rank == 0 or self.size == 1
@@ -177,13 +189,14 @@ class DeviceEngine:
             P = self.m.UpdatePlan()
             P.kind, P.wire, P.opt = self.kind, self.wire, (0 if opt.optim == "sgd" else 1)
             P.grid = min(nt, self.m.update_max_grid(self.kind, self.wire, P.opt))
+            pub = self.off_stage if self.consistent else self.off_param      # where fresh parameters are published
             for r in range(self.size):
                 base = A.ptrs[r]
-                P.set_rank_ptrs(r, base + self.off_wire, base + self.off_scales, base + self.off_param,
+                P.set_rank_ptrs(r, base + self.off_wire, base + self.off_scales, base + pub,
                                 base + self.off_signal)
             P.configure(self.size, self.rank, nt, self.bpt, self.cap, self.dt, self.bcast, self.reduce,
-                        (A.mc_ptr + self.off_param) if mc else 0, (A.mc_ptr + self.off_wire) if mc else 0,
-                        A.local_ptr + self.off_param,
+                        (A.mc_ptr + pub) if mc else 0, (A.mc_ptr + self.off_wire) if mc else 0,
+                        A.local_ptr + pub,
                         self.master.data_ptr() if self.master is not None else 0,
                         self.buf0.data_ptr() if self.buf0 is not None else 0,
                         self.buf1.data_ptr() if self.buf1 is not None else 0,
@@ -211,6 +224,7 @@ class DeviceEngine:
         self._select_out = torch.zeros(64, dtype=torch.int64, device=self.device)
         self._select_host = torch.zeros(64, dtype=torch.int64).pin_memory()
         self._async_done_workers: set = set()
+        self._snap_version = 0
         self.world.barrier()
 
     # ---------------------------------------------------------------------------------- state
@@ -296,7 +310,9 @@ class DeviceEngine:
         if self._pending_bytes >= self.bucket_bytes:
             self._flush()
 
-    def _flush(self):
+    def _flush(self, signal=None):
+        """Encode the pending bucket on the comm stream.  ``signal=(targets, slot, value)``: this is the step's last
+        encode launch, so its last CTA raises the GRAD_READY flag itself."""
         if not self._pending:
             return
         cur = torch.cuda.current_stream(self.device)
@@ -320,7 +336,8 @@ class DeviceEngine:
                           self.tiles.data_ptr(), self.arena.local_ptr + self.off_wire,
                           self.arena.local_ptr + self.off_scales, self.amax.data_ptr(),
                           self.residual.data_ptr() if self.residual is not None else 0,
-                          self.bpt, self.cap, float(self.spec.ratio))
+                          self.bpt, self.cap, float(self.spec.ratio),
+                          *((signal[0], signal[1], signal[2], self.counters.data_ptr() + 8) if signal else ()))
             nb = (len(batch) + 63) // 64
             self.launches += nb * (2 if self.kind == KIND_SCALED else 1)
         self._keep.extend(grads)
@@ -401,8 +418,6 @@ class DeviceEngine:
                 "iallgather_prepare_time": 0.0, "isend_time": 0.0}
         if self.mode == "async" and self.size > 1:
             return self._step_async(data)
-        self._flush()
-        data["code_wait"] = time.time() - t0
         epoch = self._epoch + 1
         cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event(enable_timing=self._prof.enabled)
@@ -410,19 +425,23 @@ class DeviceEngine:
         cs = self.comm_stream
         cs.wait_event(ev)
         sig_base = [p + self.off_signal for p in self.arena.ptrs]
-        t1 = time.time()
+        # the launching rank's own gradient is ordered by the stream, so it neither signals nor waits itself
+        must_signal = self.size > 1 and not (self.mode == "ps" and self.rank == 0)
+        targets = [sig_base[0]] if self.mode == "ps" else [b for r, b in enumerate(sig_base) if r != self.rank]
         with torch.cuda.stream(cs):
             if not self._first_flush_done:
                 self._first_flush_done = True
                 self._before_first_encode()
-            active_ptr = self._handle_inactive()
+            active_ptr = self._handle_inactive()      # before the flag: a tile the server reads must be final
+        fused = must_signal and bool(self._pending)
+        self._flush(signal=(targets, self.m.SIG_GRAD_READY + self.rank, epoch) if fused else None)
+        data["code_wait"] = time.time() - t0
+        t1 = time.time()
+        with torch.cuda.stream(cs):
             ev_a = self._prof.mark(cs)
-            if self.size > 1:
-                # the launching rank's own gradient is ordered by the stream, so it neither signals nor waits itself
-                targets = [sig_base[0]] if self.mode == "ps" else [b for r, b in enumerate(sig_base) if r != self.rank]
-                if not (self.mode == "ps" and self.rank == 0):
-                    self.m.signal(targets, self.m.SIG_GRAD_READY + self.rank, epoch)
-                    self.launches += 1
+            if must_signal and not fused:
+                self.m.signal(targets, self.m.SIG_GRAD_READY + self.rank, epoch)
+                self.launches += 1
             data["isend_time"] = time.time() - t1
             t2 = time.time()
             ev_b = self._prof.mark(cs)
@@ -496,8 +515,10 @@ class DeviceEngine:
                 # publish "gradient `epoch` is in my arena"
                 self.m.signal([sig_base[0]], self.m.SIG_GRAD_READY + self.rank, epoch)
                 self.launches += 1
+            if self.consistent:
+                data["param_version"] = self._snapshot()
             self._end_of_step(data)
-            return data                      # never waits for parameters: inconsistent reads
+            return data                      # never waits for NEW parameters (inconsistent reads unless consistent=True)
         # ---- rank 0: the server ----
         self._fired = set()
         self._pending, self._pending_bytes, self._keep = [], 0, []
@@ -514,6 +535,9 @@ class DeviceEngine:
             self.m.select_ready(sig_base[0], self._consumed.data_ptr(), cand, quota,
                                 self._select_out.data_ptr(), self.timeout_s)
             self.version += 1
+            if self.consistent:   # sequence lock: BEGIN(v) … stores … VERSION(v); a reader needs BEGIN == VERSION around its copy
+                self.m.signal(sig_base, self.m.SIG_VERSION + 1, self.version)
+                self.launches += 1
             self.plan.launch(o.steps, self._hypers(), 0, 1.0, 0, 1, 0, self.version,
                              self._select_out.data_ptr(), 1 if o.average else 0, 0, self.timeout_s)
             self.launches += 2
@@ -529,6 +553,9 @@ class DeviceEngine:
                 self._async_done_workers.add(r)
         data["contributors"] = [r for r in range(n) if mask >> r & 1]
         if not data["contributors"]:
+            if self.consistent:              # nothing was written: close the sequence lock again
+                with torch.cuda.stream(cs):
+                    self.m.signal(sig_base, self.m.SIG_VERSION + 1, self.version - 1)
             self.version -= 1                # nothing was applied
             for gi in range(len(self._group_steps)):
                 self._group_steps[gi] -= 1
@@ -537,6 +564,31 @@ class DeviceEngine:
         self._epoch += 1
         data["engine"] = "device"
         return data
+
+    # ------------------------------------------------------------------ consistent reads (async)
+    def _snapshot(self, max_tries: int = 1000) -> int:
+        """Adopt the newest COMPLETE parameter version from the staging copy (host-driven sequence lock).
+
+        The server writes ``BEGIN = v`` before and ``VERSION = v`` after publishing version ``v`` into the staging
+        arena.  A copy is a consistent snapshot iff ``BEGIN == VERSION`` before it starts and ``BEGIN`` is unchanged
+        after it finishes; otherwise it is retried.  Costs two tiny device→host reads per step — the price of
+        ``consistent=True`` (the default inconsistent mode never synchronises)."""
+        m = self.m
+        cs = self.comm_stream
+        for _ in range(max_tries):
+            v_end = int(self.signal[m.SIG_VERSION].item())
+            v_begin = int(self.signal[m.SIG_VERSION + 1].item())
+            if v_begin != v_end:                       # the server is in the middle of publishing v_begin
+                time.sleep(20e-6)
+                continue
+            if v_end == self._snap_version:
+                return v_end                           # nothing new since the last snapshot
+            self.param_arena.copy_(self.stage_arena)
+            torch.cuda.current_stream(self.device).synchronize()
+            if int(self.signal[m.SIG_VERSION + 1].item()) == v_end:
+                self._snap_version = v_end
+                return v_end
+        raise RuntimeError("consistent snapshot did not stabilise (server publishing faster than one copy)")
 
     # -------------------------------------------------------------- broadcast-gated GEMM support
     def register_gate(self, layer) -> None:
@@ -577,6 +629,8 @@ class DeviceEngine:
                                   self.m.SIG_GRAD_READY + self.rank, _DONE_EPOCH)
             torch.cuda.synchronize(self.device)
             self.world.barrier()
+            if self.consistent:              # everybody leaves with the server's final parameters
+                self._snapshot()
         finally:
             # parameters keep their arena views alive; detach them so the block can be freed
             with torch.no_grad():

@@ -255,7 +255,7 @@ def _oracle_sum_ref(size, steps, optim, hyper, coding_factory):
     return [p.detach().clone() for p in model.parameters()]
 
 
-def gpu_async(rank, size, coding):
+def gpu_async(rank, size, coding, consistent=0):
     import time
     ps, w = _world(rank, size)
     from pytorch_ps_mpi_b200.models import mnist_mlp
@@ -264,7 +264,9 @@ def gpu_async(rank, size, coding):
     model = mnist_mlp(hidden=32).to(dev)
     code = ps.Identity() if coding == "identity" else ps.TopK(ratio=0.25)
     opt = ps.SGD(model.named_parameters(), model.parameters(), lr=0.05, code=code, mode="async", quota=1,
-                 engine="device")
+                 engine="device", consistent=bool(consistent))
+    assert opt._engine.consistent == bool(consistent)
+    seen = []
     before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
     nsteps = 4
     if rank == 0:
@@ -275,8 +277,12 @@ def gpu_async(rank, size, coding):
             x, y = _mlp_data(rank, s)
             opt.zero_grad()
             torch.nn.functional.cross_entropy(model(x.to(dev)), y.to(dev)).backward()
-            opt.step()
+            _, data = opt.step()
+            if consistent:
+                seen.append(data["param_version"])
             time.sleep(0.01 * rank)
+        if consistent:
+            assert seen == sorted(seen) and seen[-1] >= 1, seen     # whole snapshots, monotonically newer
     opt._engine.check()
     opt.close()
     after = torch.cat([p.detach().reshape(-1) for p in model.parameters()])

@@ -123,6 +123,11 @@ def test_engine_async_one_gpu():
     spawn(_mp.gpu_async, 3, ("identity",), env=ONE_GPU, timeout=240)
 
 
+def test_engine_async_consistent_reads_one_gpu():
+    """consistent=True on the device engine: staging arena + sequence lock (README.md:79-81)."""
+    spawn(_mp.gpu_async, 3, ("identity", 1), env=ONE_GPU, timeout=240)
+
+
 @pytest.mark.multigpu
 @pytest.mark.parametrize("mode,optim,coding,dtype", [("ps", "sgd", "identity", "fp32"), ("ps", "adam", "cast", "bf16"),
                                                       ("allgather", "sgd", "topk", "fp32")])
