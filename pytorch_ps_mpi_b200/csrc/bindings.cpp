@@ -20,6 +20,9 @@ void check_launch(const char* what) {
 }
 
 cudaStream_t cur_stream() { return c10::cuda::getCurrentCUDAStream().stream(); }
+// explicit raw stream handle (torch.cuda.Stream.cuda_stream) or 0 = torch's current stream: lets the engine launch on its
+// side stream without the Python cost of switching the current stream
+cudaStream_t pick_stream(uint64_t s) { return s ? reinterpret_cast<cudaStream_t>(s) : cur_stream(); }
 
 int dt_code(at::ScalarType t) {
   switch (t) {
@@ -62,7 +65,7 @@ struct UpdatePlan {
 
   void launch(uint64_t epoch, const std::vector<std::vector<double>>& groups, uint32_t contrib_mask, double inv_count,
               int wait_grads, int signal_mode, uint32_t ack_mask, uint64_t version, uint64_t select_out,
-              int average_dynamic, uint64_t active_ptr, double timeout_s, uint32_t wait_mask) {
+              int average_dynamic, uint64_t active_ptr, double timeout_s, uint32_t wait_mask, uint64_t stream) {
     if (groups.size() > PSB_MAX_GROUPS) throw std::runtime_error("too many param groups for one launch");
     for (size_t i = 0; i < groups.size(); ++i) {
       const auto& g = groups[i];
@@ -84,7 +87,7 @@ struct UpdatePlan {
     a.average_dynamic = average_dynamic;
     a.active = reinterpret_cast<const uint8_t*>(active_ptr);
     a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
-    psb_launch_update(cur_stream(), kind, wire, opt, a, grid);
+    psb_launch_update(pick_stream(stream), kind, wire, opt, a, grid);
     check_launch("psb_update_kernel launch");
   }
 };
@@ -92,11 +95,12 @@ struct UpdatePlan {
 void encode(int kind, int wire, const std::vector<at::Tensor>& grads, const std::vector<int>& first_tile,
             const std::vector<int>& ntiles, const std::vector<int>& param_idx, uint64_t tiles_ptr, uint64_t wire_ptr,
             uint64_t scales_ptr, uint64_t amax_ptr, uint64_t residual_ptr, int bytes_per_tile, int cap, double ratio,
-            const std::vector<uint64_t>& sig_targets, int sig_slot, uint64_t sig_value, uint64_t sig_counter) {
+            const std::vector<uint64_t>& sig_targets, int sig_slot, uint64_t sig_value, uint64_t sig_counter,
+            uint64_t stream) {
   const size_t n = grads.size();
   if (first_tile.size() != n || ntiles.size() != n || param_idx.size() != n) throw std::runtime_error("encode: length mismatch");
   if (n == 0) return;
-  cudaStream_t s = cur_stream();
+  cudaStream_t s = pick_stream(stream);
   EncodeArgs a{};
   a.tiles = reinterpret_cast<const TileInfo*>(tiles_ptr);
   a.wire = reinterpret_cast<void*>(wire_ptr);
@@ -139,16 +143,17 @@ void encode(int kind, int wire, const std::vector<at::Tensor>& grads, const std:
   }
 }
 
-void signal(const std::vector<uint64_t>& targets, int slot, uint64_t value, int extra_slot, uint64_t extra_value) {
+void signal(const std::vector<uint64_t>& targets, int slot, uint64_t value, int extra_slot, uint64_t extra_value,
+            uint64_t stream) {
   std::vector<uint64_t*> t;
   for (auto p : targets) t.push_back(reinterpret_cast<uint64_t*>(p));
-  psb_launch_signal(cur_stream(), t.data(), (int)t.size(), slot, value,
+  psb_launch_signal(pick_stream(stream), t.data(), (int)t.size(), slot, value,
                     extra_slot >= 0 ? reinterpret_cast<uint64_t*>(1) : nullptr, extra_slot < 0 ? 0 : extra_slot, extra_value);
   check_launch("psb_signal_kernel launch");
 }
 
-void wait_flags(uint64_t signal_local, int slot0, uint32_t mask, uint64_t want, double timeout_s) {
-  psb_launch_wait(cur_stream(), reinterpret_cast<const uint64_t*>(signal_local), slot0, mask, want,
+void wait_flags(uint64_t signal_local, int slot0, uint32_t mask, uint64_t want, double timeout_s, uint64_t stream) {
+  psb_launch_wait(pick_stream(stream), reinterpret_cast<const uint64_t*>(signal_local), slot0, mask, want,
                   (unsigned long long)(timeout_s * 1e9));
   check_launch("psb_wait_kernel launch");
 }
@@ -230,7 +235,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("launch", &UpdatePlan::launch, py::arg("epoch"), py::arg("groups"), py::arg("contrib_mask"),
            py::arg("inv_count"), py::arg("wait_grads"), py::arg("signal_mode"), py::arg("ack_mask") = 0,
            py::arg("version") = 0, py::arg("select_out") = 0, py::arg("average_dynamic") = 0, py::arg("active_ptr") = 0,
-           py::arg("timeout_s") = 30.0, py::arg("wait_mask") = 0xffffffffu);
+           py::arg("timeout_s") = 30.0, py::arg("wait_mask") = 0xffffffffu, py::arg("stream") = 0);
 
   m.def("update_max_grid", &psb_update_max_grid);
   m.def("launch_count", []() { return (uint64_t)psb_launch_count(); }, "kernels of ours launched by this process so far");
@@ -238,10 +243,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("param_idx"), py::arg("tiles_ptr"), py::arg("wire_ptr"), py::arg("scales_ptr"), py::arg("amax_ptr"),
         py::arg("residual_ptr"), py::arg("bytes_per_tile"), py::arg("cap"), py::arg("ratio"),
         py::arg("sig_targets") = std::vector<uint64_t>{}, py::arg("sig_slot") = 0, py::arg("sig_value") = 0,
-        py::arg("sig_counter") = 0);
+        py::arg("sig_counter") = 0, py::arg("stream") = 0);
   m.def("signal", &signal, py::arg("targets"), py::arg("slot"), py::arg("value"), py::arg("extra_slot") = -1,
-        py::arg("extra_value") = 0);
-  m.def("wait_flags", &wait_flags);
+        py::arg("extra_value") = 0, py::arg("stream") = 0);
+  m.def("wait_flags", &wait_flags, py::arg("signal_local"), py::arg("slot0"), py::arg("mask"), py::arg("want"),
+        py::arg("timeout_s"), py::arg("stream") = 0);
   m.def("select_ready", &select_ready);
   bind_gemm(m);
 }

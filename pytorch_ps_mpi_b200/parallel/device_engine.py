@@ -205,6 +205,17 @@ class DeviceEngine:
                         self.counters.data_ptr(), self.counters.data_ptr() + 4)
             self.plan = P
         self.comm_stream = torch.cuda.Stream(device=self.device)
+        self._cs = self.comm_stream.cuda_stream            # raw handle for explicit-stream launches
+        self._ev_pool = [torch.cuda.Event() for _ in range(64)]
+        self._ev_i = 0
+        self._tiles_ptr = self.tiles.data_ptr()
+        self._wire_ptr = self.arena.local_ptr + self.off_wire
+        self._scales_ptr = self.arena.local_ptr + self.off_scales
+        self._amax_ptr = self.amax.data_ptr()
+        self._residual_ptr = self.residual.data_ptr() if self.residual is not None else 0
+        self._sigctr_ptr = self.counters.data_ptr() + 8
+        self._ratio = float(self.spec.ratio)
+        self._sig_base = [p + self.off_signal for p in self.arena.ptrs]
         self._pending: List[tuple] = []
         self._pending_bytes = 0
         self._fired: set = set()
@@ -310,52 +321,62 @@ class DeviceEngine:
         if self._pending_bytes >= self.bucket_bytes:
             self._flush()
 
-    def _flush(self, signal=None):
-        """Encode the pending bucket on the comm stream.  ``signal=(targets, slot, value)``: this is the step's last
-        encode launch, so its last CTA raises the GRAD_READY flag itself."""
+    def _event(self, timing: bool = False):
+        """A pooled CUDA event (creating one costs more than recording one)."""
+        if timing:
+            return torch.cuda.Event(enable_timing=True)
+        self._ev_i = (self._ev_i + 1) % len(self._ev_pool)
+        return self._ev_pool[self._ev_i]
+
+    def _flush(self, signal=None, joined: bool = False):
+        """Encode the pending bucket on the comm stream (launched with an explicit stream handle: no Python-side
+        stream switching).  ``signal=(targets, slot, value)``: this is the step's last encode launch, so its last
+        CTA raises the GRAD_READY flag itself.  ``joined``: the caller already made the comm stream wait for the
+        compute stream."""
         if not self._pending:
             return
         cur = torch.cuda.current_stream(self.device)
-        ev = torch.cuda.Event()
-        ev.record(cur)
         cs = self.comm_stream
-        cs.wait_event(ev)
+        if not joined:
+            ev = self._event()
+            ev.record(cur)
+            cs.wait_event(ev)
         batch, self._pending, self._pending_bytes = self._pending, [], 0
-        if not self._first_flush_done and self._prev_done is not None:
-            # Bound the comm stream's lag to one step: gradients are kept alive (not record_stream'ed, which
-            # would make the caching allocator grow and cudaMalloc for several steps) until the step after
-            # they were encoded, so the compute stream must not run further ahead than that.
-            cur.wait_event(self._prev_done)
-        with torch.cuda.stream(cs):
-            if not self._first_flush_done:
-                self._first_flush_done = True
-                self._before_first_encode()
-            grads = [g for _, g in batch]
-            self.m.encode(self.kind, self.wire, grads, [s.first_tile for s, _ in batch],
-                          [s.ntiles for s, _ in batch], [s.index for s, _ in batch],
-                          self.tiles.data_ptr(), self.arena.local_ptr + self.off_wire,
-                          self.arena.local_ptr + self.off_scales, self.amax.data_ptr(),
-                          self.residual.data_ptr() if self.residual is not None else 0,
-                          self.bpt, self.cap, float(self.spec.ratio),
-                          *((signal[0], signal[1], signal[2], self.counters.data_ptr() + 8) if signal else ()))
-            nb = (len(batch) + 63) // 64
-            self.launches += nb * (2 if self.kind == KIND_SCALED else 1)
+        if not self._first_flush_done:
+            if self._prev_done is not None:
+                # Bound the comm stream's lag to one step: gradients are kept alive (not record_stream'ed, which
+                # would make the caching allocator grow and cudaMalloc for several steps) until the step after
+                # they were encoded, so the compute stream must not run further ahead than that.
+                cur.wait_event(self._prev_done)
+            self._first_flush_done = True
+            self._before_first_encode()
+        grads = [g for _, g in batch]
+        self.m.encode(self.kind, self.wire, grads, [s.first_tile for s, _ in batch],
+                      [s.ntiles for s, _ in batch], [s.index for s, _ in batch],
+                      self._tiles_ptr, self._wire_ptr, self._scales_ptr, self._amax_ptr, self._residual_ptr,
+                      self.bpt, self.cap, self._ratio,
+                      *((signal[0], signal[1], signal[2], self._sigctr_ptr) if signal else ([], 0, 0, 0)),
+                      self._cs)
+        nb = (len(batch) + 63) // 64
+        self.launches += nb * (2 if self.kind == KIND_SCALED else 1)
         self._keep.extend(grads)
 
     def _before_first_encode(self):
-        """Runs on the comm stream before this step's first write into the wire arena."""
+        """Queued on the comm stream before this step's first write into the wire arena."""
         epoch = self._epoch + 1              # the step these gradients belong to
         if self.kind == KIND_SCALED:
-            self.amax.zero_()
+            with torch.cuda.stream(self.comm_stream):
+                self.amax.zero_()
         if self.size == 1:
             return
         sig = self.arena.local_ptr + self.off_signal
         if self.mode == "allgather" and epoch > 1:
             # every peer must have finished READING our previous wire tiles
-            self.m.wait_flags(sig, self.m.SIG_CONSUMED, (1 << self.size) - 1, epoch - 1, self.timeout_s)
+            self.m.wait_flags(sig, self.m.SIG_CONSUMED, ((1 << self.size) - 1) & ~(1 << self.rank), epoch - 1,
+                              self.timeout_s, self._cs)
             self.launches += 1
         elif self.mode == "async" and self.rank != 0 and epoch > 1:
-            self.m.wait_flags(sig, self.m.SIG_ACK, 1, epoch - 1, self.timeout_s)
+            self.m.wait_flags(sig, self.m.SIG_ACK, 1, epoch - 1, self.timeout_s, self._cs)
             self.launches += 1
 
     # ----------------------------------------------------------------------------------- step
@@ -419,66 +440,70 @@ class DeviceEngine:
         if self.mode == "async" and self.size > 1:
             return self._step_async(data)
         epoch = self._epoch + 1
+        m, cs, csh = self.m, self.comm_stream, self._cs
+        prof = self._prof.enabled
         cur = torch.cuda.current_stream(self.device)
-        ev = torch.cuda.Event(enable_timing=self._prof.enabled)
+        ev = self._event(timing=prof)
         ev.record(cur)                       # backward is complete up to here
-        cs = self.comm_stream
         cs.wait_event(ev)
-        sig_base = [p + self.off_signal for p in self.arena.ptrs]
+        sig_base = self._sig_base
         # the launching rank's own gradient is ordered by the stream, so it neither signals nor waits itself
         must_signal = self.size > 1 and not (self.mode == "ps" and self.rank == 0)
         targets = [sig_base[0]] if self.mode == "ps" else [b for r, b in enumerate(sig_base) if r != self.rank]
-        with torch.cuda.stream(cs):
-            if not self._first_flush_done:
-                self._first_flush_done = True
-                self._before_first_encode()
-            active_ptr = self._handle_inactive()      # before the flag: a tile the server reads must be final
+        if not self._first_flush_done:
+            self._first_flush_done = True
+            self._before_first_encode()
+        if len(self._fired) == self.layout.nparams and self._active_all:
+            active_ptr = 0                            # the common case: every parameter got a gradient
+        else:
+            with torch.cuda.stream(cs):
+                active_ptr = self._handle_inactive()  # before the flag: a tile the server reads must be final
         fused = must_signal and bool(self._pending)
-        self._flush(signal=(targets, self.m.SIG_GRAD_READY + self.rank, epoch) if fused else None)
+        self._flush(signal=(targets, m.SIG_GRAD_READY + self.rank, epoch) if fused else None, joined=True)
         data["code_wait"] = time.time() - t0
         t1 = time.time()
-        with torch.cuda.stream(cs):
-            ev_a = self._prof.mark(cs)
-            if must_signal and not fused:
-                self.m.signal(targets, self.m.SIG_GRAD_READY + self.rank, epoch)
-                self.launches += 1
-            data["isend_time"] = time.time() - t1
-            t2 = time.time()
-            ev_b = self._prof.mark(cs)
-            if self.is_server:
-                n = self.size
-                inv = (1.0 / n) if o.average else 1.0
-                self.plan.launch(epoch, self._hypers(), (1 << n) - 1, inv, 1 if n > 1 else 0,
-                                 0 if n == 1 else (1 if self.mode == "ps" else 2),
-                                 active_ptr=active_ptr, timeout_s=self.timeout_s,
-                                 wait_mask=((1 << n) - 1) & ~(1 << self.rank))
-                self.launches += 1
-            else:
-                self._hypers()               # keep per-group step counters aligned with the server
-            data["optim_step_time"] = time.time() - t2
+        ev_a = self._prof.mark(cs)
+        if must_signal and not fused:
+            m.signal(targets, m.SIG_GRAD_READY + self.rank, epoch, -1, 0, csh)
+            self.launches += 1
+        data["isend_time"] = time.time() - t1
+        t2 = time.time()
+        ev_b = self._prof.mark(cs)
+        if self.is_server:
+            n = self.size
+            inv = (1.0 / n) if o.average else 1.0
+            self.plan.launch(epoch, self._hypers(), (1 << n) - 1, inv, 1 if n > 1 else 0,
+                             0 if n == 1 else (1 if self.mode == "ps" else 2),
+                             active_ptr=active_ptr, timeout_s=self.timeout_s,
+                             wait_mask=((1 << n) - 1) & ~(1 << self.rank), stream=csh)
+            self.launches += 1
+        else:
+            self._hypers()                   # keep per-group step counters aligned with the server
+        data["optim_step_time"] = time.time() - t2
+        if prof:
             ev_c = self._prof.mark(cs)
             self._prof.span("dev_signal_time", ev_a, ev_b)
             self._prof.span("dev_gather_update_bcast_time", ev_b, ev_c)
-            done = torch.cuda.Event()
-            done.record(cs)
+        done = self._event()
+        done.record(cs)
         t3 = time.time()
         if self.size > 1 and self.mode == "ps" and self.rank != 0:
             if not self._gates:
                 # the req.Wait() of mpi_comms.py:121 — a one-thread kernel on the compute stream
-                self.m.wait_flags(sig_base[self.rank], self.m.SIG_PARAMS_READY, 1, epoch, self.timeout_s)
+                m.wait_flags(sig_base[self.rank], m.SIG_PARAMS_READY, 1, epoch, self.timeout_s)
                 self.launches += 1
             # else: the first forward GEMM (BcastLinear) acquires the flag inside its TMA producer
         else:
             cur.wait_event(done)
         data["comm_wait"] = time.time() - t3
-        if self._prof.enabled:
+        if prof:
             ev_d = self._prof.mark(cur)
             self._prof.span("dev_step_tail_time", ev, ev_d)     # backward-done → parameters usable, on the compute stream
             data.update(self._prof.harvest())                   # device timings of the most recent COMPLETED step
-        self._end_of_step(data)
+        self._end_of_step(data, done)
         return data
 
-    def _end_of_step(self, data):
+    def _end_of_step(self, data, done=None):
         L = self.layout
         nfired = max(len(self._fired), 1)
         data["msg_bytes"] = self._raw_bytes / nfired
@@ -488,8 +513,10 @@ class DeviceEngine:
         self._epoch += 1
         self._fired = set()
         self._keep_prev, self._keep = self._keep, []
-        self._prev_done = torch.cuda.Event()
-        self._prev_done.record(self.comm_stream)
+        if done is None:                     # comm-stream completion marker of this step (see _flush)
+            done = self._event()
+            done.record(self.comm_stream)
+        self._prev_done = done
         self._raw_bytes = 0
         self._first_flush_done = False
         if os.environ.get("PSB200_CHECK") == "1":
