@@ -68,12 +68,19 @@ def tensor_info(t: torch.Tensor) -> dict:
     return {"numel": t.numel(), "data_ptr": t.data_ptr(), "element_size": t.element_size()}
 
 
+_NATIVE = False   # False = not resolved yet; None = unavailable
+
+
 def _native():
-    try:
-        from .ops import ext
-        return ext.host() if ext.host_available() else None
-    except Exception:
-        return None
+    """The host extension (resolved once; ``None`` when it cannot be built/loaded)."""
+    global _NATIVE
+    if _NATIVE is False:
+        try:
+            from .ops import ext
+            _NATIVE = ext.host() if ext.host_available() else None
+        except Exception:
+            _NATIVE = None
+    return _NATIVE
 
 
 def _split(obj: Any, tensors: List[torch.Tensor]) -> Any:

@@ -480,3 +480,49 @@ def mlp_async_consistent(rank, size):
     allp = w.all_gather_object(flat)
     for f in allp[1:]:
         assert torch.equal(f, allp[1])
+
+
+def shm_stress(rank, size):
+    """Random all-to-all traffic over the native shm rings: messages far larger than a ring, many outstanding
+    operations, ANY_SOURCE receives — every byte must arrive intact and in per-pair order."""
+    os.environ["PSB200_TRANSPORT"] = "shm"
+    os.environ["PSB200_SHM_RING_BYTES"] = str(64 << 10)          # tiny rings: force chunking + flow control
+    ps, w = _world(rank, size)
+    from pytorch_ps_mpi_b200.parallel import transport as tp
+    tr = tp.get_transport()
+    rng = np.random.default_rng(1234)                            # same schedule on every rank
+    rounds = 30
+    plan = [[(int(rng.integers(0, 300_000)) if rng.random() < 0.8 else 0) for _ in range(size * size)] for _ in range(rounds)]
+
+    def payload(src, dst, rnd, n):
+        g = np.random.default_rng(src * 1000 + dst * 10 + rnd)
+        return g.integers(0, 256, n, dtype=np.uint8).tobytes()
+
+    sends, recvs = [], []
+    for rnd in range(rounds):
+        for dst in range(size):
+            if dst != rank:
+                sends.append(tr.isend(dst, payload(rank, dst, rnd, plan[rnd][rank * size + dst]), tag=7))
+        for src in range(size):
+            if src != rank:
+                recvs.append((src, rnd, tr.irecv(src=src, tag=7)))
+    for src, rnd, req in recvs:                                    # posted long before they are waited
+        msg = req.Wait()
+        assert bytes(memoryview(msg)) == payload(src, rank, rnd, plan[rnd][src * size + rank]), (src, rnd)
+        assert req.source == src
+    for s in sends:
+        s.Wait()
+    tr.barrier()
+    # ANY_SOURCE fan-in with a distinct tag
+    if rank == 0:
+        got = {}
+        for _ in range((size - 1) * 5):
+            r = tr.irecv(src=tp.ANY_SOURCE, tag=9)
+            m = bytes(memoryview(r.Wait()))
+            got.setdefault(r.source, []).append(m)
+        for src in range(1, size):
+            assert got[src] == [bytes([src, k]) * (1000 * k + 1) for k in range(5)]      # per-source FIFO order
+    else:
+        for k in range(5):
+            tr.isend(0, bytes([rank, k]) * (1000 * k + 1), tag=9).Wait()
+    tr.barrier()

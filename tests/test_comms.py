@@ -47,3 +47,8 @@ def test_single_process_world():
     (req, count), = ia.prepare([len(m)])
     req.Wait()
     assert ia.recv(*ia.send(m, count)) == [obj]
+
+
+def test_shm_transport_stress():
+    """Native ShmComm under load: 4 ranks, 64 KB rings, up to 300 KB messages, 30 rounds of all-to-all."""
+    spawn(_mp.shm_stress, 4, timeout=240)
