@@ -28,7 +28,7 @@ from typing import Any, List, Optional
 import torch
 
 __all__ = [
-    "Coding", "Identity", "Cast", "Scale", "TopK", "DeviceCodeSpec", "TILE",
+    "Coding", "Identity", "Cast", "Scale", "TopK", "QSGD", "SVD", "DeviceCodeSpec", "TILE",
     "WIRE_F32", "WIRE_BF16", "WIRE_F16", "WIRE_E4M3", "WIRE_E5M2", "WIRE_I8",
     "KIND_DENSE", "KIND_SCALED", "KIND_TOPK", "wire_dtype_of", "wire_code_of", "tile_k",
 ]
@@ -312,3 +312,68 @@ class TopK(Coding):
     def __repr__(self):
         what = f"k={self.k}" if self.k is not None else f"ratio={self.ratio}"
         return f"TopK({what}, values={_WIRE_TORCH[self.wire]}, exact={self.exact})"
+
+
+class QSGD(Coding):
+    """QSGD-style stochastic quantisation (Alistarh et al. 2017): ``sign · ‖g‖₂ · ξ/levels`` with ``ξ`` drawn so
+    the code is an unbiased estimate of the gradient.  Host (generic-object) path — the kind of user coding the
+    reference's external ``codings`` module carried; the fused device codings are
+    :class:`Cast` / :class:`Scale` / :class:`TopK`.
+    """
+
+    def __init__(self, levels: int = 255, seed: Optional[int] = None):
+        if not 1 <= levels <= 32767:
+            raise ValueError("levels must be in [1, 32767]")
+        self.levels = int(levels)
+        self._gen = torch.Generator().manual_seed(seed) if seed is not None else None
+
+    def encode(self, grad, **kwargs):
+        g = grad.detach().float().cpu()
+        norm = g.norm()
+        if float(norm) == 0.0 or not torch.isfinite(norm):
+            q = torch.zeros(g.shape, dtype=torch.int16)
+            return {"q": q, "norm": torch.zeros(1), "levels": self.levels, "shape": tuple(g.shape)}
+        x = g.abs() / norm * self.levels                      # in [0, levels]
+        low = x.floor()
+        up = torch.rand(x.shape, generator=self._gen) < (x - low)      # stochastic rounding → unbiased
+        q = (low + up.float()) * g.sign()
+        dt = torch.int8 if self.levels <= 127 else torch.int16
+        return {"q": q.to(dt), "norm": norm.reshape(1), "levels": self.levels, "shape": tuple(g.shape)}
+
+    def decode(self, code, cuda=False):
+        q = self._place(_as_tensor(code["q"]), cuda).float()
+        norm = self._place(_as_tensor(code["norm"]), cuda).float()
+        return (q * (norm / float(code["levels"]))).reshape(tuple(int(d) for d in code["shape"]))
+
+    def __repr__(self):
+        return f"QSGD(levels={self.levels})"
+
+
+class SVD(Coding):
+    """Rank-``r`` truncated SVD of every ≥2-D gradient (sent as ``U·S`` and ``Vᵀ``); 1-D gradients travel as is.
+    Host path (ATOMO / PowerSGD family of the reference author's coding experiments)."""
+
+    def __init__(self, rank: int = 4):
+        if rank < 1:
+            raise ValueError("rank must be >= 1")
+        self.rank = int(rank)
+
+    def encode(self, grad, **kwargs):
+        g = grad.detach().float().cpu()
+        if g.dim() < 2 or min(g.shape[0], g[0].numel()) <= self.rank:
+            return {"dense": g, "shape": tuple(g.shape)}
+        m = g.reshape(g.shape[0], -1)
+        u, s, vh = torch.linalg.svd(m, full_matrices=False)
+        r = self.rank
+        return {"us": (u[:, :r] * s[:r]).contiguous(), "vh": vh[:r].contiguous(), "shape": tuple(g.shape)}
+
+    def decode(self, code, cuda=False):
+        shape = tuple(int(d) for d in code["shape"])
+        if "dense" in code:
+            return self._place(_as_tensor(code["dense"]), cuda).float().reshape(shape)
+        us = self._place(_as_tensor(code["us"]), cuda).float()
+        vh = self._place(_as_tensor(code["vh"]), cuda).float()
+        return (us @ vh).reshape(shape)
+
+    def __repr__(self):
+        return f"SVD(rank={self.rank})"

@@ -127,7 +127,7 @@ def mlp_train(rank, size, mode, optim, coding, transport):
     ps, w = _world(rank, size)
     from pytorch_ps_mpi_b200.models import mnist_mlp
     factory = {"identity": ps.Identity, "cast": lambda: ps.Cast("bf16"), "scale": lambda: ps.Scale("int8"),
-               "topk": lambda: ps.TopK(ratio=0.25)}[coding]
+               "topk": lambda: ps.TopK(ratio=0.25), "svd": lambda: ps.SVD(rank=2)}[coding]
     hyper = {"lr": 0.05, "momentum": 0.9, "weight_decay": 1e-4} if optim == "sgd" else {"lr": 1e-2, "eps": 1e-12}
     torch.manual_seed(0)
     model = mnist_mlp(hidden=32)

@@ -16,6 +16,7 @@ from tests import _mp
     ("allgather", "sgd", "identity", "shm"),
     ("allgather", "adam", "scale", "gloo"),
     ("allgather", "sgd", "topk", "shm"),
+    ("ps", "sgd", "svd", "shm"),          # a host-path-only (user-style) coding through the generic wire format
 ])
 def test_mlp_sync(mode, optim, coding, transport):
     spawn(_mp.mlp_train, 2, (mode, optim, coding, transport))

@@ -146,3 +146,30 @@ def test_topk_error_feedback_accumulates():
     for _ in range(100):
         total += t.decode(t.encode(g, name="w"))
     assert torch.allclose(total + t._residual["w"], torch.full((1000,), 100.0))
+
+
+def test_qsgd_is_unbiased_and_bounded():
+    torch.manual_seed(0)
+    g = torch.randn(2000)
+    c = ps.QSGD(levels=15, seed=1)
+    dec = torch.stack([c.decode(c.encode(g)) for _ in range(400)])
+    assert dec.shape == (400, 2000)
+    assert (dec.mean(0) - g).abs().mean() < 0.12 * g.abs().mean()          # unbiased: the mean converges to g
+    step = float(g.norm()) / 15
+    assert (dec[0] - g).abs().max() <= step + 1e-5                           # one quantisation step at most
+    assert c.encode(g)["q"].dtype == torch.int8 and ps.QSGD(levels=255).encode(g)["q"].dtype == torch.int16
+    z = ps.QSGD().decode(ps.QSGD().encode(torch.zeros(5)))
+    assert torch.equal(z, torch.zeros(5)) and c.device_spec() is None       # host path only
+
+
+def test_svd_coding_low_rank_exact_and_passthrough():
+    torch.manual_seed(0)
+    a, b = torch.randn(40, 3), torch.randn(3, 7 * 5)
+    g = (a @ b).reshape(40, 7, 5)                                           # exactly rank 3
+    c = ps.SVD(rank=3)
+    code = c.encode(g)
+    assert code["us"].shape == (40, 3) and code["vh"].shape == (3, 35)
+    assert torch.allclose(c.decode(code), g, atol=1e-4)
+    assert (ps.SVD(rank=1).decode(ps.SVD(rank=1).encode(g)) - g).norm() < g.norm()     # best rank-1 approx
+    v = torch.randn(11)
+    assert torch.equal(c.decode(c.encode(v)), v)                            # 1-D gradients are sent dense
