@@ -1,5 +1,6 @@
 """Small helpers the reference keeps beside the optimizer (``/root/reference/ps.py:25-50``)."""
-from .misc import _bytes_of, bytes_of, find_param, StepTimer, CudaStepTimer
+from .misc import _bytes_of, bytes_of, find_param, StepTimer, CudaStepTimer, summarize_timings, dump_chrome_trace
 from .clocks import ClockSampler
 
-__all__ = ["_bytes_of", "bytes_of", "find_param", "StepTimer", "CudaStepTimer", "ClockSampler"]
+__all__ = ["_bytes_of", "bytes_of", "find_param", "StepTimer", "CudaStepTimer", "ClockSampler",
+           "summarize_timings", "dump_chrome_trace"]

@@ -91,3 +91,28 @@ class CudaStepTimer:
                 keep.append((key, s, e))
         self._pending = keep
         return dict(self.last)
+
+
+def summarize_timings(timings: Iterable[Dict[str, float]]) -> Dict[str, Dict[str, float]]:
+    """Aggregate the per-step ``data`` dicts an optimizer keeps in ``opt.timings`` (the list the reference
+    declared but never filled, ``/root/reference/ps.py:80``): ``{key: {mean, max, total, n}}`` for numeric keys."""
+    acc: Dict[str, List[float]] = {}
+    for d in timings:
+        for k, v in d.items():
+            if isinstance(v, (int, float)) and not isinstance(v, bool):
+                acc.setdefault(k, []).append(float(v))
+    return {k: {"mean": sum(v) / len(v), "max": max(v), "total": sum(v), "n": len(v)} for k, v in acc.items()}
+
+
+def dump_chrome_trace(timings: Iterable[Dict[str, float]], path: str, pid: int = 0) -> None:
+    """Write the host-side sections of every step as a Chrome / Perfetto trace (``chrome://tracing``)."""
+    import json
+    events, t = [], 0.0
+    for step, d in enumerate(timings):
+        for key in ("code_wait", "iallgather_prepare_time", "isend_time", "comm_wait", "decode_time", "optim_step_time"):
+            dur = float(d.get(key, 0.0) or 0.0) * 1e6
+            if dur > 0:
+                events.append({"name": key, "ph": "X", "ts": t, "dur": dur, "pid": pid, "tid": 0, "args": {"step": step}})
+                t += dur
+    with open(path, "w") as f:
+        json.dump({"traceEvents": events, "displayTimeUnit": "ms"}, f)

@@ -193,3 +193,17 @@ def test_lr_scheduler_is_honoured():
         assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
     assert abs(o.param_groups[0]["lr"] - 0.2 * 0.25) < 1e-12
     o.close()
+
+
+def test_timings_summary_and_chrome_trace(tmp_path):
+    import json
+    from pytorch_ps_mpi_b200.utils import summarize_timings, dump_chrome_trace
+    _, opt = _train(lambda m: ps.SGD(m.named_parameters(), m.parameters(), lr=0.1), steps=3)
+    assert len(opt.timings) == 3                                  # the reference declared `timings` but never filled it (ps.py:80)
+    s = summarize_timings(opt.timings)
+    assert s["optim_step_time"]["n"] == 3 and s["msg_bytes"]["mean"] > 0 and s["comm_wait"]["max"] >= 0
+    out = tmp_path / "trace.json"
+    dump_chrome_trace(opt.timings, str(out))
+    ev = json.load(open(out))["traceEvents"]
+    assert ev and all(e["ph"] == "X" and e["dur"] > 0 for e in ev)
+    opt.close()
