@@ -173,3 +173,29 @@ def test_svd_coding_low_rank_exact_and_passthrough():
     assert (ps.SVD(rank=1).decode(ps.SVD(rank=1).encode(g)) - g).norm() < g.norm()     # best rank-1 approx
     v = torch.randn(11)
     assert torch.equal(c.decode(c.encode(v)), v)                            # 1-D gradients are sent dense
+
+
+# ---- property tests ------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st   # noqa: E402
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(1, 3 * TILE), st.floats(0.001, 1.0), st.integers(0, 2 ** 31 - 1))
+def test_topk_blockwise_properties(n, ratio, seed):
+    g = torch.randn(n, generator=torch.Generator().manual_seed(seed))
+    code = ps.TopK(ratio=ratio).encode(g)
+    idx = code["idx"].long()
+    assert torch.equal(idx, torch.sort(idx).values) and idx.unique().numel() == idx.numel()      # sorted, unique
+    want = sum(tile_k(ratio, min(TILE, n - t * TILE)) for t in range(-(-n // TILE)))
+    assert idx.numel() == want and torch.equal(code["val"], g[idx])
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.lists(st.integers(0, 40), min_size=0, max_size=3), st.sampled_from(["float32", "bfloat16", "float16", "int64", "uint8"]),
+       st.integers(0, 3))
+def test_wire_roundtrip_random_tensors(shape, dtype, level):
+    dt = getattr(torch, dtype)
+    t = (torch.randn(shape) * 10).to(dt) if dt.is_floating_point else torch.randint(0, 100, shape).to(dt)
+    obj = {"t": t, "meta": {"shape": tuple(shape), "k": [1, 2.5, "s"]}}
+    back = ser.loads(ser.decompress(ser.compress(ser.dumps(obj), level=level)))
+    assert back["t"].dtype == dt and back["t"].shape == t.shape and torch.equal(back["t"], t) and back["meta"] == obj["meta"]
