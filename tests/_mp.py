@@ -122,7 +122,7 @@ def _oracle_sum_sgd(size, steps, optim, hyper, coding_factory):
     return [p.detach().clone() for p in model.parameters()]
 
 
-def mlp_train(rank, size, mode, optim, coding, transport):
+def mlp_train(rank, size, mode, optim, coding, transport, coalesce=False):
     os.environ["PSB200_TRANSPORT"] = transport
     ps, w = _world(rank, size)
     from pytorch_ps_mpi_b200.models import mnist_mlp
@@ -132,7 +132,7 @@ def mlp_train(rank, size, mode, optim, coding, transport):
     torch.manual_seed(0)
     model = mnist_mlp(hidden=32)
     cls = ps.SGD if optim == "sgd" else ps.Adam
-    opt = cls(model.named_parameters(), model.parameters(), code=factory(), mode=mode, **hyper)
+    opt = cls(model.named_parameters(), model.parameters(), code=factory(), mode=mode, coalesce=coalesce, **hyper)
     steps = 3
     for s in range(steps):
         x, y = _mlp_data(rank, s)

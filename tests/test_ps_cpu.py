@@ -22,6 +22,12 @@ def test_mlp_sync(mode, optim, coding, transport):
     spawn(_mp.mlp_train, 2, (mode, optim, coding, transport))
 
 
+@pytest.mark.parametrize("mode", ["ps", "allgather"])
+def test_mlp_sync_coalesced(mode):
+    """coalesce=True: one message per step instead of one collective per parameter — same numerics."""
+    spawn(_mp.mlp_train, 2, (mode, "sgd", "cast", "shm", True))
+
+
 def test_mlp_sync_three_ranks():
     spawn(_mp.mlp_train, 3, ("ps", "sgd", "identity", "shm"))
 
