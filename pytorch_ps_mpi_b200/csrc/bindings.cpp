@@ -65,8 +65,7 @@ struct UpdatePlan {
 
   void launch(uint64_t epoch, const std::vector<std::vector<double>>& groups, uint32_t contrib_mask, double inv_count,
               int wait_grads, int signal_mode, uint32_t ack_mask, uint64_t version, uint64_t select_out,
-              int average_dynamic, uint64_t active_ptr, double timeout_s, uint32_t wait_mask, uint64_t stream,
-              int tile_begin, int tile_end) {
+              int average_dynamic, uint64_t active_ptr, double timeout_s, uint32_t wait_mask, uint64_t stream) {
     if (groups.size() > PSB_MAX_GROUPS) throw std::runtime_error("too many param groups for one launch");
     for (size_t i = 0; i < groups.size(); ++i) {
       const auto& g = groups[i];
@@ -88,15 +87,7 @@ struct UpdatePlan {
     a.average_dynamic = average_dynamic;
     a.active = reinterpret_cast<const uint8_t*>(active_ptr);
     a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
-    // windowed launch (experimental, PSB200_UPDATE_WINDOW_MB): [tile_begin, tile_end) of the arena; tile_end <= 0 = all
-    UpdateArgs w = a;
-    const int total = a.ntiles;
-    w.tile_begin = tile_begin > 0 ? tile_begin : 0;
-    w.ntiles = (tile_end > 0 && tile_end < total) ? tile_end : total;
-    int g = grid;
-    if (w.ntiles - w.tile_begin < g) g = w.ntiles - w.tile_begin;
-    if (g < 1) g = 1;
-    psb_launch_update(pick_stream(stream), kind, wire, opt, w, g);
+    psb_launch_update(pick_stream(stream), kind, wire, opt, a, grid);
     check_launch("psb_update_kernel launch");
   }
 };
@@ -244,8 +235,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("launch", &UpdatePlan::launch, py::arg("epoch"), py::arg("groups"), py::arg("contrib_mask"),
            py::arg("inv_count"), py::arg("wait_grads"), py::arg("signal_mode"), py::arg("ack_mask") = 0,
            py::arg("version") = 0, py::arg("select_out") = 0, py::arg("average_dynamic") = 0, py::arg("active_ptr") = 0,
-           py::arg("timeout_s") = 30.0, py::arg("wait_mask") = 0xffffffffu, py::arg("stream") = 0, py::arg("tile_begin") = 0,
-           py::arg("tile_end") = 0);
+           py::arg("timeout_s") = 30.0, py::arg("wait_mask") = 0xffffffffu, py::arg("stream") = 0);
 
   m.def("update_max_grid", &psb_update_max_grid);
   m.def("launch_count", []() { return (uint64_t)psb_launch_count(); }, "kernels of ours launched by this process so far");

@@ -55,7 +55,6 @@ struct UpdateArgs {
   uint32_t* stats;                     // [0]=tiles processed (debug / tests), may be nullptr
   GroupHyper groups[PSB_MAX_GROUPS];
   int32_t world, rank, ntiles, bytes_per_tile, cap;
-  int32_t tile_begin;                  // first tile of this launch (windowed launches; 0 = whole arena, `ntiles` is the end)
   int32_t param_dt, bcast, reduce;
   uint32_t contrib_mask;               // ranks whose gradient is summed
   uint32_t wait_mask;                  // ranks whose GRAD_READY flag is awaited (the launching rank's own gradient is

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(PSB_THREADS, U == 1 ? 3 : 2) psb_update_kernel
 
   if constexpr (KIND == KIND_TOPK) {
     // ---- block-wise top-k: scatter-add every rank's (index, value) entries into a shared-memory tile ----
-    for (int tile = a.tile_begin + blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       const TileInfo ti = a.tiles[tile];
       if (a.active != nullptr && a.active[ti.param] == 0) continue;
       const size_t e0 = (size_t)tile * PSB_TILE + tid * PSB_EPT;
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(PSB_THREADS, U == 1 ? 3 : 2) psb_update_kernel
     constexpr int CH = 4;
     const bool nvls = (KIND == KIND_DENSE && (WIRE == WIRE_F32 || WIRE == WIRE_BF16 || WIRE == WIRE_F16)) &&
                       a.reduce == REDUCE_NVLS;
-    for (int tile0 = a.tile_begin + blockIdx.x; tile0 < a.ntiles; tile0 += U * gridDim.x) {
+    for (int tile0 = blockIdx.x; tile0 < a.ntiles; tile0 += U * gridDim.x) {
       TileInfo ti[U];
       bool live[U];
       float acc[U][PSB_EPT], w[1][PSB_EPT], m[1][PSB_EPT], v[1][PSB_EPT], vm[1][PSB_EPT];

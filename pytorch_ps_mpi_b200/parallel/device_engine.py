@@ -161,8 +161,6 @@ class DeviceEngine:
             self._expose_state()
         self._group_steps = [0] * len(opt.param_groups)
         self._hyper_cache = None
-        wmb = float(os.environ.get("PSB200_UPDATE_WINDOW_MB", "0") or 0)      # experimental, default off
-        self._window_tiles = int(wmb * (1 << 20) / max(self.bpt, 1)) if wmb > 0 else 0
 
         # ---- publication / reduction strategy ----
         mc = A.has_multicast
@@ -474,25 +472,11 @@ class DeviceEngine:
         if self.is_server:
             n = self.size
             inv = (1.0 / n) if o.average else 1.0
-            hy = self._hypers()
-            sigm = 0 if n == 1 else (1 if self.mode == "ps" else 2)
-            wmask = ((1 << n) - 1) & ~(1 << self.rank)
-            win = self._window_tiles
-            if win <= 0 or win >= self.layout.ntiles:
-                self.plan.launch(epoch, hy, (1 << n) - 1, inv, 1 if n > 1 else 0, sigm,
-                                 active_ptr=active_ptr, timeout_s=self.timeout_s, wait_mask=wmask, stream=csh)
-                self.launches += 1
-            else:
-                # EXPERIMENTAL (PSB200_UPDATE_WINDOW_MB): several back-to-back launches, each over a bounded window of
-                # the arena (the 1 GB x 8-rank P2P gather fell off a cliff, BENCH_NOTES §3); only the first waits for
-                # the flags and only the last raises PARAMS_READY / CONSUMED.
-                nt = self.layout.ntiles
-                for b in range(0, nt, win):
-                    e = min(nt, b + win)
-                    self.plan.launch(epoch, hy, (1 << n) - 1, inv, 1 if (n > 1 and b == 0) else 0,
-                                     sigm if e == nt else 0, active_ptr=active_ptr, timeout_s=self.timeout_s,
-                                     wait_mask=wmask, stream=csh, tile_begin=b, tile_end=e)
-                    self.launches += 1
+            self.plan.launch(epoch, self._hypers(), (1 << n) - 1, inv, 1 if n > 1 else 0,
+                             0 if n == 1 else (1 if self.mode == "ps" else 2),
+                             active_ptr=active_ptr, timeout_s=self.timeout_s,
+                             wait_mask=((1 << n) - 1) & ~(1 << self.rank), stream=csh)
+            self.launches += 1
         else:
             self._hypers()                   # keep per-group step counters aligned with the server
         data["optim_step_time"] = time.time() - t2
