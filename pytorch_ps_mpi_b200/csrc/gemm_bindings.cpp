@@ -53,7 +53,11 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   auto y = at::empty({M, N}, x.options());
   if (M == 0) return y;
   // cta_group::2 (two SMs per 256x256 tile) whenever there are at least 256 rows; `variant` forces it (tests)
-  const bool two_cta = variant == 2 || (variant == 0 && M >= 256);
+  // bits 4-7 / 8-11 of `variant` select an experimental epilogue / diagnostic mode (bcast_gemm_exp.cu; 2-CTA only)
+  const int base = variant & 15, epi = (variant >> 4) & 15, dbg = (variant >> 8) & 15;
+  TORCH_CHECK(base <= 2 && epi <= 2 && dbg <= 2, "unknown bcast_gemm variant ", variant);
+  TORCH_CHECK((epi | dbg) == 0 || base == 2, "experimental bcast_gemm variants need the 2-CTA kernel (variant & 15 == 2)");
+  const bool two_cta = base == 2 || (base == 0 && M >= 256);
   CUtensorMap ma = make_map(reinterpret_cast<uint64_t>(x.data_ptr()), M, K, K, 128);
   const int bnt2 = N <= 64 ? 64 : (N <= 128 ? 128 : 256);          // must match psb_launch_bcast_gemm's choice
   CUtensorMap mb = make_map(w_ptr, N, K, K, two_cta ? bnt2 / 2 : 256);   // B box: half tile per CTA (2-CTA) or BN rows
@@ -75,7 +79,8 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   a.two_cta = two_cta ? 1 : 0;
   a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  psb_launch_bcast_gemm(c10::cuda::getCurrentCUDAStream().stream(), a, sms);
+  if (epi | dbg) psb_launch_bcast_gemm_exp(c10::cuda::getCurrentCUDAStream().stream(), a, sms, epi, dbg);
+  else psb_launch_bcast_gemm(c10::cuda::getCurrentCUDAStream().stream(), a, sms);
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_bcast_gemm_kernel launch: ", cudaGetErrorString(e));
   return y;

@@ -1,0 +1,294 @@
+// EXPERIMENTAL variants of the cta_group::2 GEMM (psb_bcast_gemm2_kernel in bcast_gemm.cu).  Nothing here is on a
+// default path: the kernels below are only reachable through `bcast_linear(..., variant=2 | EPI<<4 | DBG<<8)` and
+// exist to find out, on hardware, why the K <= 1024 shapes run at ~47 % of the measured tensor peak while 8192^3
+// runs at 93 % (BENCH_NOTES §5).  The operand traffic per MMA does not depend on K, so the short-K loss must be a
+// per-TILE cost: the epilogue (TMEM drain + bf16 pack + global stores), or a hand-off bubble around it.
+//
+//   EPI = 0  the production epilogue: lane == row, 16-byte stores at a row stride (partial 32 B sectors)
+//   EPI = 1  staged epilogue: each warp transposes 32 rows x 64 columns through padded shared memory and writes
+//            full 128-byte lines (4 rows per store instruction)
+//   EPI = 2  eight epilogue warps instead of four (two per TMEM lane quarter, half of the columns each)
+//
+//   DBG = 0  normal
+//   DBG = 1  the epilogue drains TMEM and packs but never stores      → time without the output traffic
+//   DBG = 2  the MMA warp commits without issuing tcgen05.mma          → time of TMA + epilogue alone
+//
+// `bench/gemm_variants.py` runs the matrix of variants, checks the numerics of the DBG = 0 ones against torch and
+// prints the timing table that decides which epilogue becomes the default.
+#include "gemm_common.cuh"
+
+namespace {
+
+template <int BNT, int EPI>
+struct CfgX {
+  using C = Cfg2<BNT>;
+  static constexpr int EPI_WARPS = EPI == 2 ? 8 : 4;
+  static constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int ROW_PITCH = 144;                                  // 128 B of bf16 + 16 B pad: conflict-free both ways
+  static constexpr int STAGING = EPI == 1 ? 4 * 32 * ROW_PITCH : 0;      // one 32-row buffer per epilogue warp
+  static constexpr int SMEM_BYTES = C::SMEM_BYTES + STAGING;
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// 32 fp32 accumulator columns of one row → (+bias, ReLU) → 16 packed bf16x2 words
+__device__ __forceinline__ void finish32(const uint32_t* r, const GemmParams& p, int col0, uint32_t* out16) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float a = __uint_as_float(r[j]), b = __uint_as_float(r[j + 1]);
+    if (p.bias != nullptr) {
+      if (col0 + j < p.N) a += p.bias[col0 + j];
+      if (col0 + j + 1 < p.N) b += p.bias[col0 + j + 1];
+    }
+    if (p.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+    out16[j >> 1] = psb::pack_bf16x2(a, b);
+  }
+}
+
+template <int BNT, int EPI, int DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((CfgX<BNT, EPI>::NTHREADS), 1)
+psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using C = Cfg2<BNT>;
+  using X = CfgX<BNT, EPI>;
+  constexpr int STAGES2 = C::STAGES, STAGE2_BYTES = C::STAGE_BYTES, A2_BYTES = C::A_BYTES, TMEM_COLS2 = C::TMEM_COLS;
+  constexpr int BN2 = BNT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES2;
+  uint64_t* tmem_full = bars + 2 * STAGES2;
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+  uint8_t* staging = smem + STAGES2 * STAGE2_BYTES + 256;      // EPI == 1 only
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int ncl = gridDim.x / 2, cl = blockIdx.x / 2;
+  const int tiles_m = (p.M + 255) / 256, tiles_n = (p.N + BN2 - 1) / BN2;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * X::EPI_WARPS);       // every epilogue warp of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"((uint32_t)TMEM_COLS2)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) — identical to the production kernel =====================
+    if (elect_one()) {
+      if (p.ready_flag != nullptr) {
+        psb::spin_until_ge(p.ready_flag, p.ready_epoch, p.err_slot, p.timeout_ns);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cl; tile < num_tiles; tile += ncl) {
+        const int m0 = (tile / tiles_n) * 256 + (int)cta * BM;
+        const int n0 = (tile % tiles_n) * BN2 + (int)cta * (BN2 / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE2_BYTES;
+          const uint32_t lead_full = smem_u32(&full[stage]) & PEER_MASK;
+          if (leader) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+          tma_load_2d_2sm(&tmap_a, lead_full, sa, kb * BK, m0);
+          tma_load_2d_2sm(&tmap_b, lead_full, sa + A2_BYTES, kb * BK, n0);
+          if (++stage == STAGES2) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      const uint32_t idesc = make_idesc2<BNT>();
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = cl; tile < num_tiles; tile += ncl) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            if constexpr (DBG != 2) {
+              const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
+              const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + A2_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
+            umma_commit_2sm(&empty[stage]);      // with no MMA in flight the commit arrives at once
+            if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == STAGES2) stage = 0, phase ^= 1;
+        }
+        if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;                                     // the TMEM lane quarter this warp may read
+    const int half = EPI == 2 ? ((warp - 2) >> 2) : 0;
+    constexpr int COLS_PER_WARP = EPI == 2 ? BN2 / 2 : BN2;
+    const int cbeg = half * COLS_PER_WARP;
+    const bool vec_ok = (p.N % 8) == 0;
+    const bool store = DBG != 1 || p.M < 0;                           // DBG 1: never true, but not provably so
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = cl; tile < num_tiles; tile += ncl) {
+      const int m0 = (tile / tiles_n) * 256 + (int)cta * BM, n0 = (tile % tiles_n) * BN2;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
+      if constexpr (EPI == 1) {
+        const uint32_t stg = smem_u32(staging + (warp - 2) * 32 * X::ROW_PITCH);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN2; c0 += 64) {
+          uint32_t r[32], pk[32];
+          tmem_ld_32x32b_x32(t_row + c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          finish32(r, p, n0 + c0, pk);
+          tmem_ld_32x32b_x32(t_row + c0 + 32, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          finish32(r, p, n0 + c0 + 32, pk + 16);
+          // lane == row: 128 B of this row into the padded staging tile (quarter-warps hit 32 distinct banks)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(stg + lane * X::ROW_PITCH + j * 16, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+          __syncwarp();
+          // 8 lanes per row: every store instruction writes 4 full 128-byte lines
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3), ch = lane & 7;
+            const uint4 v = ld_shared_v4(stg + rr * X::ROW_PITCH + ch * 16);
+            const int grow = m0 + quarter * 32 + rr, gcol = n0 + c0 + ch * 8;
+            if (store && grow < p.M && gcol < p.N) {
+              __nv_bfloat16* o = p.out + (size_t)grow * p.N + gcol;
+              if (vec_ok && gcol + 8 <= p.N) {
+                *reinterpret_cast<uint4*>(o) = v;
+              } else {
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                  if (gcol + t < p.N) reinterpret_cast<uint16_t*>(o)[t] = (uint16_t)(w[t >> 1] >> ((t & 1) * 16));
+              }
+            }
+          }
+          __syncwarp();                                               // the staging tile is reused by the next chunk
+        }
+      } else {
+        const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + COLS_PER_WARP; c0 += 32) {
+          uint32_t r[32], pk[16];
+          tmem_ld_32x32b_x32(t_row + c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          finish32(r, p, n0 + c0, pk);
+          if (store && row < p.M && n0 + c0 < p.N) {
+            __nv_bfloat16* orow = p.out + (size_t)row * p.N + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = n0 + c0 + 8 * j;
+              if (vec_ok && col + 8 <= p.N) {
+                *reinterpret_cast<uint4*>(orow + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                  if (col + t < p.N)
+                    reinterpret_cast<uint16_t*>(orow + 8 * j)[t] = (uint16_t)(pk[4 * j + (t >> 1)] >> ((t & 1) * 16));
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & PEER_MASK);
+      if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS2)
+                 : "memory");
+  }
+}
+
+template <int BNT, int EPI, int DBG>
+void launch_x(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int clusters) {
+  using X = CfgX<BNT, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(psb_bcast_gemm2x_kernel<BNT, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM_BYTES);
+    configured = true;
+  }
+  psb_bcast_gemm2x_kernel<BNT, EPI, DBG><<<2 * clusters, X::NTHREADS, X::SMEM_BYTES, s>>>(ta, tb, p);
+}
+
+template <int BNT, int EPI>
+void launch_d(cudaStream_t s, int dbg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int clusters) {
+  if (dbg == 1) launch_x<BNT, EPI, 1>(s, ta, tb, p, clusters);
+  else if (dbg == 2) launch_x<BNT, EPI, 2>(s, ta, tb, p, clusters);
+  else launch_x<BNT, EPI, 0>(s, ta, tb, p, clusters);
+}
+
+template <int BNT>
+void launch_e(cudaStream_t s, int epi, int dbg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int clusters) {
+  if (epi == 1) launch_d<BNT, 1>(s, dbg, ta, tb, p, clusters);
+  else if (epi == 2) launch_d<BNT, 2>(s, dbg, ta, tb, p, clusters);
+  else launch_d<BNT, 0>(s, dbg, ta, tb, p, clusters);
+}
+
+}  // namespace
+
+// `a.two_cta` must be set (the tensor maps are built for the 2-CTA box shapes); epi / dbg as documented on top.
+void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg) {
+  GemmParams p{};
+  p.bias = a.bias;
+  p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a.tmap_c));
+  p.ready_flag = a.ready_flag;
+  p.ready_epoch = a.ready_epoch;
+  p.err_slot = a.ready_flag != nullptr ? const_cast<uint64_t*>(a.ready_flag) - SIG_PARAMS_READY + SIG_ERROR : nullptr;
+  p.M = a.M, p.N = a.N, p.K = a.K, p.relu = a.relu;
+  p.timeout_ns = a.timeout_ns;
+  psb_count_launch(1);
+  const int bnt = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
+  const int tiles = ((a.M + 255) / 256) * ((a.N + bnt - 1) / bnt);
+  int clusters = num_sms / 2;
+  if (tiles < clusters) clusters = tiles;
+  const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(a.tmap_a);
+  const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(a.tmap_b);
+  if (bnt == 64) launch_e<64>(s, epi, dbg, ta, tb, p, clusters);
+  else if (bnt == 128) launch_e<128>(s, epi, dbg, ta, tb, p, clusters);
+  else launch_e<256>(s, epi, dbg, ta, tb, p, clusters);
+}
