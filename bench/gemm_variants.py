@@ -6,6 +6,7 @@ Runs the production ``psb_bcast_gemm2_kernel`` next to the experimental variants
 * ``epi0`` production epilogue re-instantiated in the experimental kernel (must time like production),
 * ``epi1`` staged epilogue (padded smem transpose → full 128-byte lines),
 * ``epi2`` eight epilogue warps,
+* ``epi3`` TMA-store epilogue (swizzled staging, double-buffered ``cp.async.bulk.tensor`` stores; needs N % 8 == 0),
 
 each also as ``nostore`` (TMEM drained and packed, nothing written) and ``nomma`` (TMA + epilogue only).
 Numerics of every storing variant are checked against an fp32 torch matmul first.  CUDA-event timing, L2 flushed
@@ -27,7 +28,7 @@ from pytorch_ps_mpi_b200.ops.linear import bcast_linear   # noqa: E402
 
 TWO_CTA = 2
 VARIANTS = [("prod", TWO_CTA)]
-for epi in (0, 1, 2):
+for epi in (0, 1, 2, 3):
     for dbg, tag in ((0, ""), (1, ".nostore"), (2, ".nomma")):
         if epi == 0 and dbg == 0:
             continue                      # epi0/dbg0 routes to the production kernel by construction
@@ -69,6 +70,8 @@ def main():
         t_lib = bench(lambda: torch.nn.functional.linear(x, w), flush)
         fl = 2.0 * M * N * K
         for tag, v in VARIANTS:
+            if (v >> 4) & 15 == 3 and N % 8:
+                continue
             rec = {"shape": name, "M": M, "N": N, "K": K, "variant": tag, "code": v}
             if (v >> 8) == 0:             # a storing variant: numerics first (bias + ReLU exercised too)
                 y = bcast_linear(x, w, b, relu=True, variant=v).float()

@@ -55,7 +55,7 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   // cta_group::2 (two SMs per 256x256 tile) whenever there are at least 256 rows; `variant` forces it (tests)
   // bits 4-7 / 8-11 of `variant` select an experimental epilogue / diagnostic mode (bcast_gemm_exp.cu; 2-CTA only)
   const int base = variant & 15, epi = (variant >> 4) & 15, dbg = (variant >> 8) & 15;
-  TORCH_CHECK(base <= 2 && epi <= 2 && dbg <= 2, "unknown bcast_gemm variant ", variant);
+  TORCH_CHECK(base <= 2 && epi <= 3 && dbg <= 2, "unknown bcast_gemm variant ", variant);
   TORCH_CHECK((epi | dbg) == 0 || base == 2, "experimental bcast_gemm variants need the 2-CTA kernel (variant & 15 == 2)");
   const bool two_cta = base == 2 || (base == 0 && M >= 256);
   CUtensorMap ma = make_map(reinterpret_cast<uint64_t>(x.data_ptr()), M, K, K, 128);
@@ -79,7 +79,16 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   a.two_cta = two_cta ? 1 : 0;
   a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  if (epi | dbg) psb_launch_bcast_gemm_exp(c10::cuda::getCurrentCUDAStream().stream(), a, sms, epi, dbg);
+  if (epi | dbg) {
+    CUtensorMap mc;
+    const void* mcp = nullptr;
+    if (epi == 3) {
+      TORCH_CHECK(N % 8 == 0, "the TMA-store epilogue needs N % 8 == 0 (16-byte row pitch)");
+      mc = make_map(reinterpret_cast<uint64_t>(y.data_ptr()), M, N, N, 32);      // box: 64 columns x 32 rows, 128B swizzle
+      mcp = &mc;
+    }
+    psb_launch_bcast_gemm_exp(c10::cuda::getCurrentCUDAStream().stream(), a, sms, epi, dbg, mcp);
+  }
   else psb_launch_bcast_gemm(c10::cuda::getCurrentCUDAStream().stream(), a, sms);
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_bcast_gemm_kernel launch: ", cudaGetErrorString(e));

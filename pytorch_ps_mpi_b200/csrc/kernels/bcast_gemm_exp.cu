@@ -8,6 +8,9 @@
 //   EPI = 1  staged epilogue: each warp transposes 32 rows x 64 columns through padded shared memory and writes
 //            full 128-byte lines (4 rows per store instruction)
 //   EPI = 2  eight epilogue warps instead of four (two per TMEM lane quarter, half of the columns each)
+//   EPI = 3  TMA-store epilogue: each warp writes 32 rows x 64 columns into a 128B-swizzled staging tile (two per
+//            warp, so a store is in flight while the next chunk is packed) and one lane issues
+//            cp.async.bulk.tensor.2d.global.shared::cta — no LSU wavefronts at all, bounds clipped by the TMA unit
 //
 //   DBG = 0  normal
 //   DBG = 1  the epilogue drains TMEM and packs but never stores      → time without the output traffic
@@ -25,8 +28,11 @@ struct CfgX {
   static constexpr int EPI_WARPS = EPI == 2 ? 8 : 4;
   static constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
   static constexpr int ROW_PITCH = 144;                                  // 128 B of bf16 + 16 B pad: conflict-free both ways
-  static constexpr int STAGING = EPI == 1 ? 4 * 32 * ROW_PITCH : 0;      // one 32-row buffer per epilogue warp
-  static constexpr int SMEM_BYTES = C::SMEM_BYTES + STAGING;
+  static constexpr int BAR_BYTES = 1024;                                 // keeps the staging area 1024-byte aligned (swizzle)
+  static constexpr int STAGING = EPI == 1 ? 4 * 32 * ROW_PITCH           // one padded 32-row buffer per epilogue warp
+                                 : (EPI == 3 ? 4 * 2 * 4096 : 0);        // two swizzled 32 x 128 B buffers per warp
+  static constexpr int SMEM_BYTES = C::STAGES * C::STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + STAGING;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
@@ -55,7 +61,7 @@ __device__ __forceinline__ void finish32(const uint32_t* r, const GemmParams& p,
 template <int BNT, int EPI, int DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((CfgX<BNT, EPI>::NTHREADS), 1)
 psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                        const __grid_constant__ GemmParams p) {
+                        const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using C = Cfg2<BNT>;
@@ -68,7 +74,7 @@ psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   uint64_t* tmem_full = bars + 2 * STAGES2;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
-  uint8_t* staging = smem + STAGES2 * STAGE2_BYTES + 256;      // EPI == 1 only
+  uint8_t* staging = smem + STAGES2 * STAGE2_BYTES + X::BAR_BYTES;      // EPI 1 / 3 only; 1024-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();
@@ -81,6 +87,7 @@ psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    if constexpr (EPI == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
     for (int i = 0; i < STAGES2; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -163,6 +170,7 @@ psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const bool vec_ok = (p.N % 8) == 0;
     const bool store = DBG != 1 || p.M < 0;                           // DBG 1: never true, but not provably so
     uint32_t acc = 0, acc_phase = 0;
+    [[maybe_unused]] uint32_t nchunk = 0;                              // EPI 3: staging-buffer parity
     for (int tile = cl; tile < num_tiles; tile += ncl) {
       const int m0 = (tile / tiles_n) * 256 + (int)cta * BM, n0 = (tile % tiles_n) * BN2;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -204,6 +212,36 @@ psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           }
           __syncwarp();                                               // the staging tile is reused by the next chunk
         }
+      } else if constexpr (EPI == 3) {
+        const uint32_t stg0 = smem_u32(staging + (warp - 2) * 2 * 4096);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN2; c0 += 64) {
+          const uint32_t stg = stg0 + (nchunk & 1u) * 4096;
+          // the store issued two chunks ago has finished READING this buffer (bulk groups are per issuing thread)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          uint32_t r[32], pk[32];
+          tmem_ld_32x32b_x32(t_row + c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          finish32(r, p, n0 + c0, pk);
+          tmem_ld_32x32b_x32(t_row + c0 + 32, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          finish32(r, p, n0 + c0 + 32, pk + 16);
+          // lane == row; 16-byte chunk j of row r lives at chunk (j ^ (r & 7)) — the SWIZZLE_128B pattern of tmap_c
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes → visible to the TMA unit
+          __syncwarp();
+          if (lane == 0) {
+            if (store && n0 + c0 < p.N && m0 + quarter * 32 < p.M)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_c), "r"(stg),
+                           "r"(n0 + c0), "r"(m0 + quarter * 32)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");       // an empty group keeps the buffer parity uniform
+          }
+          ++nchunk;
+        }
       } else {
         const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
@@ -234,6 +272,10 @@ psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & PEER_MASK);
       if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
     }
+    if constexpr (EPI == 3) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output tiles written before exit
+      __syncwarp();
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -245,34 +287,39 @@ psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 }
 
 template <int BNT, int EPI, int DBG>
-void launch_x(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int clusters) {
+void launch_x(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+              int clusters) {
   using X = CfgX<BNT, EPI>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(psb_bcast_gemm2x_kernel<BNT, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM_BYTES);
     configured = true;
   }
-  psb_bcast_gemm2x_kernel<BNT, EPI, DBG><<<2 * clusters, X::NTHREADS, X::SMEM_BYTES, s>>>(ta, tb, p);
+  psb_bcast_gemm2x_kernel<BNT, EPI, DBG><<<2 * clusters, X::NTHREADS, X::SMEM_BYTES, s>>>(ta, tb, tc, p);
 }
 
 template <int BNT, int EPI>
-void launch_d(cudaStream_t s, int dbg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int clusters) {
-  if (dbg == 1) launch_x<BNT, EPI, 1>(s, ta, tb, p, clusters);
-  else if (dbg == 2) launch_x<BNT, EPI, 2>(s, ta, tb, p, clusters);
-  else launch_x<BNT, EPI, 0>(s, ta, tb, p, clusters);
+void launch_d(cudaStream_t s, int dbg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+              int clusters) {
+  if (dbg == 1) launch_x<BNT, EPI, 1>(s, ta, tb, tc, p, clusters);
+  else if (dbg == 2) launch_x<BNT, EPI, 2>(s, ta, tb, tc, p, clusters);
+  else launch_x<BNT, EPI, 0>(s, ta, tb, tc, p, clusters);
 }
 
 template <int BNT>
-void launch_e(cudaStream_t s, int epi, int dbg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int clusters) {
-  if (epi == 1) launch_d<BNT, 1>(s, dbg, ta, tb, p, clusters);
-  else if (epi == 2) launch_d<BNT, 2>(s, dbg, ta, tb, p, clusters);
-  else launch_d<BNT, 0>(s, dbg, ta, tb, p, clusters);
+void launch_e(cudaStream_t s, int epi, int dbg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+              const GemmParams& p, int clusters) {
+  if (epi == 1) launch_d<BNT, 1>(s, dbg, ta, tb, tc, p, clusters);
+  else if (epi == 2) launch_d<BNT, 2>(s, dbg, ta, tb, tc, p, clusters);
+  else if (epi == 3) launch_d<BNT, 3>(s, dbg, ta, tb, tc, p, clusters);
+  else launch_d<BNT, 0>(s, dbg, ta, tb, tc, p, clusters);
 }
 
 }  // namespace
 
 // `a.two_cta` must be set (the tensor maps are built for the 2-CTA box shapes); epi / dbg as documented on top.
-void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg) {
+// `tmap_out` (EPI 3): CUtensorMap of the [M, N] bf16 output, box 64 columns x 32 rows, SWIZZLE_128B; else ignored.
+void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out) {
   GemmParams p{};
   p.bias = a.bias;
   p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a.tmap_c));
@@ -288,7 +335,8 @@ void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_s
   if (tiles < clusters) clusters = tiles;
   const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(a.tmap_a);
   const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(a.tmap_b);
-  if (bnt == 64) launch_e<64>(s, epi, dbg, ta, tb, p, clusters);
-  else if (bnt == 128) launch_e<128>(s, epi, dbg, ta, tb, p, clusters);
-  else launch_e<256>(s, epi, dbg, ta, tb, p, clusters);
+  const CUtensorMap& tc = tmap_out != nullptr ? *reinterpret_cast<const CUtensorMap*>(tmap_out) : ta;   // unused unless EPI 3
+  if (bnt == 64) launch_e<64>(s, epi, dbg, ta, tb, tc, p, clusters);
+  else if (bnt == 128) launch_e<128>(s, epi, dbg, ta, tb, tc, p, clusters);
+  else launch_e<256>(s, epi, dbg, ta, tb, tc, p, clusters);
 }

@@ -98,7 +98,7 @@ struct BcastGemmArgs {
 };
 void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms);
 // bcast_gemm_exp.cu — experimental epilogue / diagnostic variants of the 2-CTA kernel (never a default path)
-void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg);
+void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out);
 
 // bn_kernels.cu — fused channels-last bf16 BatchNorm (+residual, +ReLU), forward and backward
 void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y, float* sums,
