@@ -196,6 +196,60 @@ at::Tensor normalize_pad8(const at::Tensor& x, std::vector<double> mean, std::ve
 }
 
 // bf16 NHWC [N,3,H,W] (channels_last) → patch matrix [N*OH*OW, 176] for the 7x7/s2/p3 stem
+// EXPERIMENTAL: training BatchNorm forward whose Σx / Σx² were produced by the fused stem kernel; returns (y, mean, rstd)
+std::vector<at::Tensor> bn_forward_presummed(const at::Tensor& x, c10::optional<at::Tensor> res, const at::Tensor& gamma,
+                                             const at::Tensor& beta, at::Tensor running_mean, at::Tensor running_var, double eps,
+                                             double momentum, bool relu, const at::Tensor& sums) {
+  check_nhwc(x, "x");
+  const int C = (int)x.size(1);
+  TORCH_CHECK(C % 8 == 0 && C <= 2048, "channels must be a multiple of 8 and <= 2048");
+  TORCH_CHECK(sums.is_cuda() && sums.scalar_type() == at::kFloat && sums.numel() == 2 * C && sums.is_contiguous(),
+              "sums must be a contiguous fp32 CUDA tensor of 2*C elements");
+  const long long pixels = x.numel() / C;
+  const void* rp = nullptr;
+  if (res.has_value() && res->defined()) {
+    check_nhwc(*res, "residual");
+    TORCH_CHECK(res->sizes() == x.sizes(), "residual shape mismatch");
+    rp = res->data_ptr();
+  }
+  TORCH_CHECK(running_mean.scalar_type() == at::kFloat && running_var.scalar_type() == at::kFloat, "running stats must be fp32");
+  auto y = at::empty_like(x);
+  auto scratch = at::empty({4 * C}, x.options().dtype(at::kFloat));   // mean | rstd | scale | shift
+  float* sp = scratch.data_ptr<float>();
+  psb_bn_forward_presummed(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), rp, gamma.data_ptr(), beta.data_ptr(),
+                           y.data_ptr(), sums.data_ptr<float>(), sp, sp + C, sp + 2 * C, sp + 3 * C,
+                           running_mean.data_ptr<float>(), running_var.data_ptr<float>(), pixels, C, (float)eps, (float)momentum,
+                           relu ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_bn_forward_presummed: ", cudaGetErrorString(e));
+  return {y, scratch.narrow(0, 0, C), scratch.narrow(0, C, C)};
+}
+
+// EXPERIMENTAL fused stem: x [N,3,H,W] bf16 channels-last, w2d [64,176] bf16 (ops/stem.py layout)
+// → (y [N,64,OH,OW] bf16 channels-last, sums [128] fp32 = Σy | Σy² per channel, or an empty tensor)
+std::vector<at::Tensor> stem_fwd(const at::Tensor& x, const at::Tensor& w2d, bool want_sums) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.size(1) == 3, "x must be [N,3,H,W] bf16");
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "x must be channels_last contiguous");
+  TORCH_CHECK(w2d.is_cuda() && w2d.scalar_type() == at::kBFloat16 && w2d.dim() == 2 && w2d.size(0) == 64 && w2d.size(1) == 176 &&
+                  w2d.is_contiguous(),
+              "w2d must be a contiguous [64,176] bf16 matrix");
+  const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3);
+  TORCH_CHECK(W % 8 == 0 && W <= 256 && W >= 8 && H >= 1, "fused stem: W must be a multiple of 8 and <= 256");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(w2d.data_ptr()) % 16 == 0,
+              "operands must be 16-byte aligned");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  auto y = at::empty({N, OH, OW, 64}, x.options());
+  at::Tensor sums = want_sums ? at::zeros({128}, x.options().dtype(at::kFloat)) : at::Tensor();
+  CUtensorMap mw = make_map(reinterpret_cast<uint64_t>(w2d.data_ptr()), 64, 176, 176, 64);
+  CUtensorMap my = make_map(reinterpret_cast<uint64_t>(y.data_ptr()), (int64_t)N * OH * OW, 64, 64, OW);
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  psb_stem_fwd_launch(c10::cuda::getCurrentCUDAStream().stream(), &mw, &my, x.data_ptr(), want_sums ? sums.data_ptr<float>() : nullptr,
+                      N, H, W, sms);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_stem_fwd_kernel launch: ", cudaGetErrorString(e));
+  return {y.permute({0, 3, 1, 2}), sums};
+}
+
 at::Tensor im2col_stem(const at::Tensor& x) {
   check_nhwc(x, "x");
   TORCH_CHECK(x.size(1) == 3, "stem input must have 3 channels");
@@ -232,6 +286,9 @@ void bind_gemm(py::module_& m) {
   m.def("maxpool_forward", &maxpool_forward, "channels-last bf16 3x3/s2/p1 max pool → (y, argpos)");
   m.def("maxpool_backward", &maxpool_backward, "gather-style backward of maxpool_forward");
   m.def("bn_forward", &bn_forward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) forward");
+  m.def("bn_forward_presummed", &bn_forward_presummed, "EXPERIMENTAL: BN forward with sums produced by the fused stem kernel");
+  m.def("stem_fwd", &stem_fwd, py::arg("x"), py::arg("w2d"), py::arg("want_sums") = true,
+        "EXPERIMENTAL: fused implicit-GEMM ResNet stem (+ BN statistics) on tcgen05");
   m.def("bn_backward", &bn_backward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");
   m.def("bcast_gemm", &bcast_gemm, py::arg("x"), py::arg("w_ptr"), py::arg("N"), py::arg("K"), py::arg("bias"),
         py::arg("relu"), py::arg("flag_ptr") = 0, py::arg("epoch") = 0, py::arg("timeout_s") = 30.0, py::arg("variant") = 0,

@@ -308,6 +308,30 @@ void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* 
   }
 }
 
+// Training forward whose per-channel sums were produced elsewhere (the fused stem kernel's epilogue, stem_kernels.cu):
+// finalize + apply only — the statistics pass over x is skipped.  EXPERIMENTAL (PSB200_STEM=fused).
+void psb_bn_forward_presummed(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y,
+                              const float* sums /*2C, filled by the producer*/, float* mean, float* rstd, float* scale,
+                              float* shift, float* running_mean, float* running_var, long long pixels, int C, float eps,
+                              float momentum, int relu) {
+  const BnGeom g = geom(pixels, C);
+  const int grid = grid_for(pixels, g);
+  auto X = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto R = reinterpret_cast<const __nv_bfloat16*>(res);
+  auto Y = reinterpret_cast<__nv_bfloat16*>(y);
+  psb_count_launch(2);
+  psb_bn_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma),
+                                                   reinterpret_cast<const __nv_bfloat16*>(beta), mean, rstd, scale, shift,
+                                                   running_mean, running_var, C, pixels, eps, momentum);
+  if (res != nullptr) {
+    if (relu) psb_bn_apply<true, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
+    else psb_bn_apply<true, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
+  } else {
+    if (relu) psb_bn_apply<false, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
+    else psb_bn_apply<false, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
+  }
+}
+
 void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* y, const void* gamma, const float* mean,
                      const float* rstd, float* sums /*2C*/, float* coef /*3C*/, void* dx, void* dres, void* dgamma, void* dbeta,
                      long long pixels, int C, int relu) {

@@ -104,6 +104,9 @@ void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_s
 void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y, float* sums,
                     float* mean, float* rstd, float* scale, float* shift, float* running_mean, float* running_var,
                     long long pixels, int C, float eps, float momentum, int relu, int training);
+void psb_bn_forward_presummed(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y,
+                              const float* sums, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
+                              float* running_var, long long pixels, int C, float eps, float momentum, int relu);
 void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* y, const void* gamma, const float* mean,
                      const float* rstd, float* sums, float* coef, void* dx, void* dres, void* dgamma, void* dbeta,
                      long long pixels, int C, int relu);
@@ -114,6 +117,11 @@ void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, 
 void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW);
 void psb_im2col_stem_launch(cudaStream_t s, const void* x, void* a, int N, int H, int W);
 void psb_normalize_nhwc3_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW);
+
+// stem_kernels.cu — EXPERIMENTAL fused implicit-GEMM ResNet stem (7x7/s2, 3 → 64) with BN statistics in the epilogue
+int psb_stem_fwd_smem_bytes();
+void psb_stem_fwd_launch(cudaStream_t s, const void* tmap_w, const void* tmap_y, const void* x, float* sums, int N, int H, int W,
+                         int num_sms);
 
 // process-wide count of OUR kernel launches (every psb_* launcher adds to it; bench.py reports the delta)
 void psb_count_launch(int n);

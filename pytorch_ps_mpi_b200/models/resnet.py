@@ -6,6 +6,7 @@ kernels sit on the parameter-server paths, not here.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Type, Union
 
 import torch
@@ -14,7 +15,11 @@ import torch.nn.functional as F
 
 from ..ops.batchnorm import FusedBatchNormAct2d
 from ..ops.pooling import FusedMaxPool2d
-from ..ops.stem import stem_conv, stem_supported
+from ..ops.stem import stem_conv, stem_conv_fused, stem_fused_supported, stem_supported
+
+# EXPERIMENTAL, default off: one implicit-GEMM stem kernel with the BatchNorm statistics in its epilogue
+# (csrc/kernels/stem_kernels.cu) instead of im2col + GEMM + statistics pass.  Validate with bench/stem_fused_check.py.
+_FUSED_STEM = os.environ.get("PSB200_STEM", "").lower() == "fused"
 
 
 def _conv3x3(i, o, stride=1):
@@ -115,7 +120,12 @@ class ResNet(nn.Module):
         return F.conv2d(x, w, c.bias, c.stride, c.padding, c.dilation, c.groups)
 
     def forward(self, x):
-        x = self.maxpool(self.bn1(self.stem(x)))
+        if (_FUSED_STEM and self.gemm_stem and self.training and x.shape[1] == self.conv1.in_channels
+                and stem_fused_supported(x, self.conv1)):
+            y, sums = stem_conv_fused(x, self.conv1.weight)     # EXPERIMENTAL: implicit GEMM + BN statistics in one kernel
+            x = self.maxpool(self.bn1(y, sums=sums))
+        else:
+            x = self.maxpool(self.bn1(self.stem(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 

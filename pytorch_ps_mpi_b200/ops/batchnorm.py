@@ -22,9 +22,12 @@ from . import ext
 
 class _FusedBN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, training):
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, training, sums=None):
         m = ext.cuda()
-        y, mean, rstd = m.bn_forward(x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, training)
+        if sums is not None and training:    # EXPERIMENTAL: Σx / Σx² came out of the producer's epilogue (fused stem)
+            y, mean, rstd = m.bn_forward_presummed(x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, sums)
+        else:
+            y, mean, rstd = m.bn_forward(x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, training)
         ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
         ctx.relu, ctx.has_res = relu, res is not None
         return y
@@ -36,7 +39,7 @@ class _FusedBN(torch.autograd.Function):
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx, dres, dgamma, dbeta = m.bn_backward(dy, x, y if ctx.relu else x, gamma, mean, rstd, ctx.relu, ctx.has_res)
-        return dx, (dres if ctx.has_res else None), dgamma, dbeta, None, None, None, None, None, None
+        return dx, (dres if ctx.has_res else None), dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def _kernel_ok(x: torch.Tensor, res: Optional[torch.Tensor], weight) -> bool:
@@ -63,12 +66,15 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
                 setattr(self, name, b.float())
         return self
 
-    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``sums`` (experimental): fp32 ``[2C]`` = Σx | Σx² over N·H·W already computed by the producer of ``x``."""
         if _kernel_ok(x, residual, self.weight) and (self.training or self.running_mean is not None):
             if self.training and self.num_batches_tracked is not None:
                 self.num_batches_tracked.add_(1)
             return _FusedBN.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
-                                  self.eps, self.momentum if self.momentum is not None else 0.1, self.relu, self.training)
+                                  self.eps, self.momentum if self.momentum is not None else 0.1, self.relu, self.training,
+                                  sums)
         rm, rv = self.running_mean, self.running_var
         w, b = self.weight, self.bias
         if rm is not None and rm.dtype != x.dtype and not x.is_cuda:

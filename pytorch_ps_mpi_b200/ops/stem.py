@@ -37,6 +37,46 @@ def stem_supported(x: torch.Tensor, conv: torch.nn.Conv2d) -> bool:
             and conv.stride == (2, 2) and conv.padding == (3, 3) and conv.dilation == (1, 1) and conv.groups == 1)
 
 
+def _w2d(weight: torch.Tensor) -> torch.Tensor:
+    """[cout,3,7,7] → [cout,176]: (kh | kw,c) rows padded 21→24, then 8 zero columns (the layout psb_im2col_stem writes)."""
+    cout = weight.shape[0]
+    w2d = F.pad(weight.permute(0, 2, 3, 1).reshape(cout, 7, 21), (0, 3)).reshape(cout, 168)
+    return F.pad(w2d, (0, STEM_K - 168)).contiguous()
+
+
+class _StemFused(torch.autograd.Function):
+    """EXPERIMENTAL (``PSB200_STEM=fused``): one implicit-GEMM kernel (``csrc/kernels/stem_kernels.cu``) instead of
+    im2col + GEMM; also returns the BatchNorm sums of its output.  The weight gradient still goes through the patch
+    matrix (rebuilt in backward) until the implicit wgrad kernel exists."""
+
+    @staticmethod
+    def forward(ctx, x, w2d):
+        y, sums = ext.cuda().stem_fwd(x, w2d, True)
+        ctx.save_for_backward(x)
+        ctx.mark_non_differentiable(sums)
+        return y, sums
+
+    @staticmethod
+    def backward(ctx, gy, _gsums):
+        (x,) = ctx.saved_tensors
+        gw = None
+        if ctx.needs_input_grad[1]:
+            a = ext.cuda().im2col_stem(x)
+            g2 = gy.permute(0, 2, 3, 1).reshape(-1, gy.shape[1])          # NHWC view of the channels-last gradient
+            gw = g2.t() @ a
+        return None, gw
+
+
+def stem_fused_supported(x: torch.Tensor, conv: torch.nn.Conv2d) -> bool:
+    return stem_supported(x, conv) and conv.out_channels == 64 and x.shape[3] % 8 == 0 and x.shape[3] <= 256
+
+
+def stem_conv_fused(x: torch.Tensor, weight: torch.Tensor):
+    """``(F.conv2d(x, weight, stride=2, padding=3), sums)`` where ``sums`` = per-channel Σy | Σy² (fp32, 128 values)
+    for the BatchNorm that follows (``FusedBatchNormAct2d.forward(y, sums=sums)``)."""
+    return _StemFused.apply(x, _w2d(weight))
+
+
 def stem_conv(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """``F.conv2d(x, weight, stride=2, padding=3)`` for a 3-channel channels-last bf16 ``x`` (no input grad)."""
     n, _, h, w = x.shape
