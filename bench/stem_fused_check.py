@@ -80,6 +80,25 @@ def main():
     gerr = (wa.grad.float() - wb.grad.float()).abs().max().item() / max(wa.grad.float().abs().max().item(), 1e-6)
     emit(check="wgrad", max_rel_diff=gerr, ok=bool(gerr < 1e-2))
 
+    # 2b. implicit weight-gradient kernel vs the same reference, several shapes (partial K steps, small grids)
+    from pytorch_ps_mpi_b200.ops.stem import stem_wgrad_implicit
+    for (n, h, wd) in [(8, 224, 224), (2, 64, 64), (1, 30, 40), (3, 17, 8), (2, 33, 256)]:
+        xs = torch.randn(n, 3, h, wd, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+        oh, ow = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
+        g = torch.randn(n, 64, oh, ow, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+        a = m.im2col_stem(xs).float()
+        ref = g.permute(0, 2, 3, 1).reshape(-1, 64).float().t() @ a               # [64,176]
+        got = stem_wgrad_implicit(xs, g).float()
+        e = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+        emit(check="wgrad_implicit", shape=[n, h, wd], max_rel_err=e, ok=bool(e < 1e-2))
+    flush0 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    xs = torch.randn(256, 3, 224, 224, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    g = torch.randn(256, 64, 112, 112, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    t_impl = bench(lambda: stem_wgrad_implicit(xs, g), flush0)
+    t_gemm = bench(lambda: g.permute(0, 2, 3, 1).reshape(-1, 64).t() @ m.im2col_stem(xs), flush0)
+    emit(check="wgrad_timing", batch=256, implicit_ms=t_impl, im2col_plus_gemm_ms=t_gemm, ok=True)
+    del xs, g, flush0
+
     # 3. whole model, default vs fused stem
     losses = {}
     for fused in (False, True):

@@ -250,6 +250,28 @@ std::vector<at::Tensor> stem_fwd(const at::Tensor& x, const at::Tensor& w2d, boo
   return {y.permute({0, 3, 1, 2}), sums};
 }
 
+// EXPERIMENTAL implicit weight gradient of the stem: x [N,3,H,W], gy [N,64,OH,OW] (both bf16 channels-last)
+// → per-CTA partials [grid,176,64] fp32 of dW2d^T (sum over dim 0 on the caller's side)
+at::Tensor stem_wgrad(const at::Tensor& x, const at::Tensor& gy) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.size(1) == 3, "x must be [N,3,H,W] bf16");
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "x must be channels_last contiguous");
+  const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3);
+  TORCH_CHECK(W % 8 == 0 && W <= 256 && W >= 8, "fused stem: W must be a multiple of 8 and <= 256");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  check_nhwc(gy, "gy");
+  TORCH_CHECK(gy.size(0) == N && gy.size(1) == 64 && gy.size(2) == OH && gy.size(3) == OW, "gy shape mismatch");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(gy.data_ptr()) % 16 == 0,
+              "operands must be 16-byte aligned");
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int grid = psb_stem_wgrad_grid(N, H, sms);
+  auto partial = at::empty({grid, 176, 64}, x.options().dtype(at::kFloat));
+  CUtensorMap mg = make_map(reinterpret_cast<uint64_t>(gy.data_ptr()), (int64_t)N * OH * OW, 64, 64, OW);
+  psb_stem_wgrad_launch(c10::cuda::getCurrentCUDAStream().stream(), &mg, x.data_ptr(), partial.data_ptr<float>(), N, H, W, sms);
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_stem_wgrad_kernel launch: ", cudaGetErrorString(e));
+  return partial;
+}
+
 at::Tensor im2col_stem(const at::Tensor& x) {
   check_nhwc(x, "x");
   TORCH_CHECK(x.size(1) == 3, "stem input must have 3 channels");
@@ -289,6 +311,7 @@ void bind_gemm(py::module_& m) {
   m.def("bn_forward_presummed", &bn_forward_presummed, "EXPERIMENTAL: BN forward with sums produced by the fused stem kernel");
   m.def("stem_fwd", &stem_fwd, py::arg("x"), py::arg("w2d"), py::arg("want_sums") = true,
         "EXPERIMENTAL: fused implicit-GEMM ResNet stem (+ BN statistics) on tcgen05");
+  m.def("stem_wgrad", &stem_wgrad, "EXPERIMENTAL: implicit weight gradient of the stem → per-CTA fp32 partials [grid,176,64]");
   m.def("bn_backward", &bn_backward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");
   m.def("bcast_gemm", &bcast_gemm, py::arg("x"), py::arg("w_ptr"), py::arg("N"), py::arg("K"), py::arg("bias"),
         py::arg("relu"), py::arg("flag_ptr") = 0, py::arg("epoch") = 0, py::arg("timeout_s") = 30.0, py::arg("variant") = 0,

@@ -123,6 +123,9 @@ int psb_stem_fwd_smem_bytes();
 void psb_stem_fwd_launch(cudaStream_t s, const void* tmap_w, const void* tmap_y, const void* x, float* sums, int N, int H, int W,
                          int num_sms);
 
+int psb_stem_wgrad_grid(int N, int H, int num_sms);
+void psb_stem_wgrad_launch(cudaStream_t s, const void* tmap_g, const void* x, float* partial, int N, int H, int W, int num_sms);
+
 // process-wide count of OUR kernel launches (every psb_* launcher adds to it; bench.py reports the delta)
 void psb_count_launch(int n);
 unsigned long long psb_launch_count();

@@ -89,6 +89,34 @@ __device__ __forceinline__ void load_patch(const StemParams& p, int tile, uint32
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// A-operand row `bt` (output pixel ow = bt) of one tile: for each kernel row the 42 contiguous patch bytes
+// x[ih, 2ow-3 .. 2ow+3, 0..2] → three 16-byte chunks of the 128B-swizzled [128 x 64] k-blocks.  The same tile serves
+// the forward (K-major A operand) and the weight gradient (MN-major operand: rows are then the reduction dimension).
+__device__ __forceinline__ void build_row(uint32_t patch, uint32_t a_tile, int pitch, int bt) {
+  const uint32_t prow = patch + 30 + 12 * bt;                               // MARGIN + (2*ow - 3) * 6 bytes
+  const uint32_t arow = a_tile + (bt >> 3) * 1024 + (bt & 7) * 128;
+#pragma unroll
+  for (int kh = 0; kh < 7; ++kh) {
+    const uint32_t q = prow + kh * pitch;              // 2-mod-4 aligned: one 2-byte and ten 4-byte loads
+    const uint32_t first = lds_u16(q);
+    uint32_t w4[10], v[12];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) w4[j] = lds_u32(q + 2 + 4 * j);
+    v[0] = first | (w4[0] << 16);
+#pragma unroll
+    for (int j = 1; j < 10; ++j) v[j] = (w4[j - 1] >> 16) | (w4[j] << 16);
+    v[10] = w4[9] >> 16;
+    v[11] = 0u;
+#pragma unroll
+    for (int c3 = 0; c3 < 3; ++c3) {
+      const int qc = kh * 3 + c3;                      // 16-byte chunk index within the 352-byte logical row
+      sts_v4(arow + (qc >> 3) * SA_BLK + (((qc & 7) ^ (bt & 7)) << 4), v[4 * c3], v[4 * c3 + 1], v[4 * c3 + 2],
+             v[4 * c3 + 3]);
+    }
+  }
+  // chunk 21 (columns 168..175) stays zero from the initial clear
+}
+
 __global__ void __launch_bounds__(S_THREADS, 1)
 psb_stem_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
                     const __grid_constant__ StemParams p) {
@@ -151,30 +179,7 @@ psb_stem_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       }
       named_bar(1, 128);                               // everybody's copies of patch[buf] have landed
       mbar_wait(&a_empty[buf], ((i >> 1) & 1) ^ 1);    // the MMAs that read A[buf] two tiles ago are done
-      if (bt < p.OW) {
-        const uint32_t prow = sP + buf * PATCH_BYTES + 30 + 12 * bt;        // MARGIN + (2*ow - 3) * 6 bytes
-        const uint32_t arow = sA + buf * SA_BYTES + (bt >> 3) * 1024 + (bt & 7) * 128;
-#pragma unroll
-        for (int kh = 0; kh < 7; ++kh) {
-          const uint32_t q = prow + kh * pitch;        // 2-mod-4 aligned: one 2-byte and ten 4-byte loads
-          const uint32_t first = lds_u16(q);
-          uint32_t w4[10], v[12];
-#pragma unroll
-          for (int j = 0; j < 10; ++j) w4[j] = lds_u32(q + 2 + 4 * j);
-          v[0] = first | (w4[0] << 16);
-#pragma unroll
-          for (int j = 1; j < 10; ++j) v[j] = (w4[j - 1] >> 16) | (w4[j] << 16);
-          v[10] = w4[9] >> 16;
-          v[11] = 0u;
-#pragma unroll
-          for (int c3 = 0; c3 < 3; ++c3) {
-            const int qc = kh * 3 + c3;                // 16-byte chunk index within the 352-byte logical row
-            sts_v4(arow + (qc >> 3) * SA_BLK + (((qc & 7) ^ (bt & 7)) << 4), v[4 * c3], v[4 * c3 + 1], v[4 * c3 + 2],
-                   v[4 * c3 + 3]);
-          }
-        }
-        // chunk 21 (columns 168..175) stays zero from the initial clear
-      }
+      if (bt < p.OW) build_row(sP + buf * PATCH_BYTES, sA + buf * SA_BYTES, pitch, bt);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic writes → visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[buf]);
@@ -273,6 +278,181 @@ psb_stem_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   }
 }
 
+// ==========================================================================================================
+// Weight gradient of the stem, implicit too:  dW2d[co][k] = Σ_pixels gy[p][co] · A[p][k].
+// The reduction runs over PIXELS, so both operands are "MN-major" for the tensor core — which is exactly how they
+// already sit in shared memory: the im2col tile built by build_row ([pixel rows][k], k contiguous) is the M-side
+// operand, the TMA-loaded gy tile ([pixel rows][64 channels]) the N-side one.  UMMA M = 128 covers k-blocks {0,1};
+// a second MMA over k-blocks {1,2} provides k = 128..175 (rows 64..111 of its accumulator).  Both accumulators stay
+// in TMEM for the CTA's whole life; each CTA writes one fp32 partial [176][64] and the host sums the partials
+// (deterministic, 148 x 45 KB).
+//   warps 0-3  builders (as in the forward), then the final TMEM → global epilogue
+//   warp  4    TMA producer of the gy tiles     warp 5   MMA issuer
+// ==========================================================================================================
+constexpr int WG_THREADS = 192;
+constexpr int SG_BYTES = 128 * 128;                              // gy tile: up to 128 pixel rows x 64 bf16
+constexpr int WOFF_A = 0;
+constexpr int WOFF_G = WOFF_A + 2 * SA_BYTES;                    // 98 304
+constexpr int WOFF_P = WOFF_G + 2 * SG_BYTES;                    // 131 072
+constexpr int WOFF_BAR = WOFF_P + 2 * PATCH_BYTES;
+constexpr int WGRAD_SMEM = WOFF_BAR + 256 + 1024;
+static_assert(WOFF_G % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
+static_assert(WGRAD_SMEM <= 232448, "shared memory budget");
+
+struct StemWgradParams {
+  const __nv_bfloat16* x;     // [N, H, W, 3] bf16
+  float* partial;             // [gridDim.x][176][64] fp32
+  int N, H, W, OH, OW;
+};
+
+// MN-major, SWIZZLE_128B smem descriptor: 64-element MN blocks `lbo` bytes apart, 8-row K groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t stem_idesc_mn() {   // as stem_idesc, both operands MN-major (bits 15 / 16)
+  return stem_idesc() | (1u << 15) | (1u << 16);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+psb_stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ StemWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WOFF_BAR);
+  uint64_t* a_full = bars;            // [2]  4 builder warps arrive
+  uint64_t* g_full = bars + 2;        // [2]  TMA bytes of the gy tile
+  uint64_t* empty = bars + 4;         // [2]  tcgen05.commit: A[buf] and G[buf] are free again
+  uint64_t* d_full = bars + 6;        // [1]  every MMA of this CTA has completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = p.N * p.OH;
+  const int per = (tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = min(t0 + per, tiles);
+  const int pitch = MARGIN + p.W * 6 + MARGIN;
+  const uint32_t sA = smem_u32(smem + WOFF_A), sG = smem_u32(smem + WOFF_G), sP = smem_u32(smem + WOFF_P);
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_g) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 4);
+      mbar_init(&g_full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(d_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // rows >= OW of A and of the gy tiles take part in the last K step: they must be zero, not stale bits
+  for (int i = threadIdx.x; i < (2 * SA_BYTES + 2 * SG_BYTES) / 16; i += WG_THREADS) sts_v4(sA + i * 16, 0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < (2 * PATCH_BYTES) / 16; i += WG_THREADS) sts_v4(sP + i * 16, 0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+  StemParams lp{};                                     // load_patch only reads x / H / W / OH
+  lp.x = p.x, lp.N = p.N, lp.H = p.H, lp.W = p.W, lp.OH = p.OH, lp.OW = p.OW;
+
+  if (warp < 4) {
+    // ============================== builders ==============================
+    const int bt = threadIdx.x;
+    if (t0 < t1) load_patch(lp, t0, sP, pitch, bt);
+    for (int t = t0, i = 0; t < t1; ++t, ++i) {
+      const int buf = i & 1;
+      if (t + 1 < t1) {
+        load_patch(lp, t + 1, sP + (buf ^ 1) * PATCH_BYTES, pitch, bt);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      named_bar(1, 128);
+      mbar_wait(&empty[buf], ((i >> 1) & 1) ^ 1);
+      if (bt < p.OW) build_row(sP + buf * PATCH_BYTES, sA + buf * SA_BYTES, pitch, bt);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[buf]);
+      named_bar(1, 128);
+    }
+    // ---- final epilogue: this CTA's partial dW2d^T [176][64] ----
+    float* out = p.partial + (size_t)blockIdx.x * SK * 64;
+    const int r = warp * 32 + lane;                    // TMEM lane == accumulator row
+    if (t0 < t1) {
+      mbar_wait(d_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {           // accumulator 0: k = r;  accumulator 1: k = 64 + r (r >= 64 only)
+        const int k = part == 0 ? r : 64 + r;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + part * 64 + c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if ((part == 0 || r >= 64) && k < SK) {
+            float4* o = reinterpret_cast<float4*>(out + (size_t)k * 64 + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+          }
+        }
+      }
+    } else {
+      for (int k = r; k < SK; k += 128)
+        for (int c = 0; c < 64; ++c) out[(size_t)k * 64 + c] = 0.f;
+    }
+  } else if (warp == 4) {
+    // ============================== gy TMA producer ==============================
+    if (elect_one()) {
+      for (int t = t0, i = 0; t < t1; ++t, ++i) {
+        const int buf = i & 1;
+        mbar_wait(&empty[buf], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&g_full[buf], (uint32_t)p.OW * 128u);
+        tma_load_2d(&tmap_g, &g_full[buf], smem + WOFF_G + buf * SG_BYTES, 0, t * p.OW);
+      }
+    }
+  } else {
+    // ============================== MMA issuer ==============================
+    const uint32_t idesc = stem_idesc_mn();
+    const int ksteps = (p.OW + 15) >> 4;               // 16 pixel rows per UMMA K step (rows >= OW are zero)
+    for (int t = t0, i = 0; t < t1; ++t, ++i) {
+      const int buf = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      mbar_wait(&a_full[buf], par);
+      mbar_wait(&g_full[buf], par);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t a0 = sA + buf * SA_BYTES + ks * 2048;
+          const uint64_t dg = make_desc_mn(sG + buf * SG_BYTES + ks * 2048, 16);
+          umma(tmem_base, make_desc_mn(a0, SA_BLK), dg, idesc, (i | ks) != 0);                 // k-blocks 0,1 → k 0..127
+          umma(tmem_base + 64, make_desc_mn(a0 + SA_BLK, SA_BLK), dg, idesc, (i | ks) != 0);   // k-blocks 1,2 → k 64..191
+        }
+        umma_commit(&empty[buf]);
+        if (t + 1 == t1) umma_commit(d_full);
+      }
+      __syncwarp();
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
 }  // namespace
 
 int psb_stem_fwd_smem_bytes() { return STEM_SMEM; }
@@ -296,4 +476,26 @@ void psb_stem_fwd_launch(cudaStream_t s, const void* tmap_w, const void* tmap_y,
   psb_count_launch(1);
   psb_stem_fwd_kernel<<<grid, S_THREADS, STEM_SMEM, s>>>(*reinterpret_cast<const CUtensorMap*>(tmap_w),
                                                         *reinterpret_cast<const CUtensorMap*>(tmap_y), p);
+}
+
+// tmap_g: [N*OH*OW, 64] bf16 output gradient (channels-last), box 64 columns x OW rows, SWIZZLE_128B.
+// `partial`: [grid][176][64] fp32, fully written (no zeroing needed); returns the grid size through *grid_out.
+int psb_stem_wgrad_grid(int N, int H, int num_sms) {
+  const int tiles = N * ((H - 1) / 2 + 1);
+  return tiles < num_sms ? tiles : num_sms;
+}
+void psb_stem_wgrad_launch(cudaStream_t s, const void* tmap_g, const void* x, float* partial, int N, int H, int W, int num_sms) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(psb_stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM);
+    configured = true;
+  }
+  StemWgradParams p{};
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.partial = partial;
+  p.N = N, p.H = H, p.W = W;
+  p.OH = (H - 1) / 2 + 1, p.OW = (W - 1) / 2 + 1;
+  psb_count_launch(1);
+  psb_stem_wgrad_kernel<<<psb_stem_wgrad_grid(N, H, num_sms), WG_THREADS, WGRAD_SMEM, s>>>(
+      *reinterpret_cast<const CUtensorMap*>(tmap_g), p);
 }

@@ -7,6 +7,8 @@ cuDNN needs 2.5 ms per step for this layer on B200 (C=3 defeats its tensor-core 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -14,6 +16,8 @@ from . import ext
 from .linear import bcast_linear
 
 STEM_K = 176          # 7 kernel rows x 24 (21 real + 3 zero) + 8 zero columns (csrc/kernels/pool_kernels.cu)
+# EXPERIMENTAL, default off: weight gradient of the fused stem through psb_stem_wgrad_kernel instead of im2col + GEMM
+_IMPLICIT_WGRAD = os.environ.get("PSB200_STEM_WGRAD", "").lower() == "implicit"
 
 
 class _StemGemm(torch.autograd.Function):
@@ -61,10 +65,21 @@ class _StemFused(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         gw = None
         if ctx.needs_input_grad[1]:
-            a = ext.cuda().im2col_stem(x)
-            g2 = gy.permute(0, 2, 3, 1).reshape(-1, gy.shape[1])          # NHWC view of the channels-last gradient
-            gw = g2.t() @ a
+            if not gy.is_contiguous(memory_format=torch.channels_last):
+                gy = gy.contiguous(memory_format=torch.channels_last)
+            if _IMPLICIT_WGRAD:
+                gw = stem_wgrad_implicit(x, gy)
+            else:
+                a = ext.cuda().im2col_stem(x)
+                g2 = gy.permute(0, 2, 3, 1).reshape(-1, gy.shape[1])      # NHWC view of the channels-last gradient
+                gw = g2.t() @ a
         return None, gw
+
+
+def stem_wgrad_implicit(x: torch.Tensor, gy: torch.Tensor) -> torch.Tensor:
+    """EXPERIMENTAL: ``dW2d [64,176]`` (bf16) of the stem from ``psb_stem_wgrad_kernel`` — no patch matrix."""
+    partial = ext.cuda().stem_wgrad(x, gy)                                # [grid,176,64] fp32
+    return partial.sum(0).t().to(gy.dtype)
 
 
 def stem_fused_supported(x: torch.Tensor, conv: torch.nn.Conv2d) -> bool:
