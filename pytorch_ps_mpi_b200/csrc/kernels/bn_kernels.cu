@@ -261,6 +261,179 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bn_bwd_apply(const __nv_bfloat
   }
 }
 
+// ==========================================================================================================
+// EXPERIMENTAL (opt-in, PSB200_BNPOOL=fused): BatchNorm-apply + ReLU + 3x3/s2/p1 max-pool in ONE pass, forward and
+// backward — the ResNet stem tail.  Unfused, the 411 MB BN output (batch 256) is written, read back by the pool, and
+// in backward the pool gradient is materialised (411 MB) and read twice together with the BN output (ReLU mask):
+//   forward : psb_bnrelu_pool_fwd   reads x once, writes the pooled tensor + 1-byte window positions
+//   backward: psb_bnpool_bwd_reduce / psb_bnpool_bwd_apply GATHER dy from (dy_pooled, arg) on the fly and recompute
+//             the ReLU mask from x·scale+shift, so neither the BN output nor the un-pooled gradient ever exists.
+// Values are rounded to bf16 before the max exactly as the unfused pair does, so the forward is bit-identical.
+// ==========================================================================================================
+struct BnPoolGeom {
+  int N, H, W, C, OH, OW, groups;
+};
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void __launch_bounds__(256) psb_bnrelu_pool_fwd(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+                                                           uint8_t* __restrict__ arg, BnPoolGeom g) {
+  const long long total = (long long)g.N * g.OH * g.OW * g.groups;
+  int cur = -1;
+  float sc[8], sh[8];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % g.groups);
+    if (cg != cur) {
+      cur = cg;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sc[j] = scale[cg * 8 + j], sh[j] = shift[cg * 8 + j];
+    }
+    long long p = i / g.groups;
+    const int ow = (int)(p % g.OW);
+    p /= g.OW;
+    const int oh = (int)(p % g.OH);
+    const int n = (int)(p / g.OH);
+    float best[8];
+    uint32_t pos[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY, pos[j] = 255;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = oh * 2 - 1 + kh;
+      if (h < 0 || h >= g.H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = ow * 2 - 1 + kw;
+        if (w < 0 || w >= g.W) continue;
+        float v[8];
+        ld8(x + (((long long)n * g.H + h) * g.W + w) * g.C + cg * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = bf16_round(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f));
+          if (z > best[j]) {             // strictly greater: the first maximum wins ties (ATen's rule)
+            best[j] = z;
+            pos[j] = kh * 3 + kw;
+          }
+        }
+      }
+    }
+    const long long o = (((long long)n * g.OH + oh) * g.OW + ow) * g.C + cg * 8;
+    st8(y + o, best);
+    *reinterpret_cast<uint2*>(arg + o) =
+        make_uint2(pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24), pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24));
+  }
+}
+
+// gradient reaching the (never materialised) BN+ReLU output at input pixel (n, h, w), channels cg*8..+7
+__device__ __forceinline__ void gather_pool_grad(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ arg,
+                                                 const BnPoolGeom& g, int n, int h, int w, int cg, float* acc) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int oh0 = h >> 1, ow0 = w >> 1;          // windows covering (h, w): oh*2-1 <= h <= oh*2+1
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int oh = oh0 + a;
+    const int kh = h - (oh * 2 - 1);
+    if (oh >= g.OH || kh < 0 || kh > 2) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ow = ow0 + b;
+      const int kw = w - (ow * 2 - 1);
+      if (ow >= g.OW || kw < 0 || kw > 2) continue;
+      const long long o = (((long long)n * g.OH + oh) * g.OW + ow) * g.C + cg * 8;
+      const uint2 pr = *reinterpret_cast<const uint2*>(arg + o);
+      float d[8];
+      ld8(dy + o, d);
+      const uint32_t want = (uint32_t)(kh * 3 + kw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t pj = ((j < 4 ? pr.x : pr.y) >> (8 * (j & 3))) & 0xffu;
+        if (pj == want) acc[j] += d[j];
+      }
+    }
+  }
+}
+
+// Σ dy' and Σ dy'·x̂ over all input pixels (dy' = pooled gradient gathered back, masked by the recomputed ReLU)
+__global__ void __launch_bounds__(BN_THREADS) psb_bnpool_bwd_reduce(const __nv_bfloat16* __restrict__ dy,
+                                                                     const uint8_t* __restrict__ arg,
+                                                                     const __nv_bfloat16* __restrict__ x,
+                                                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                     float* __restrict__ sums, BnGeom g, BnPoolGeom pg) {
+  extern __shared__ float smem[];
+  const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
+  float s[8], q[8], mu[8], rs[8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j] = q[j] = 0.f;
+    mu[j] = mean[tx * 8 + j];
+    rs[j] = rstd[tx * 8 + j];
+    sc[j] = scale[tx * 8 + j];
+    sh[j] = shift[tx * 8 + j];
+  }
+  const long long per_cta = (g.pixels + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per_cta;
+  const long long p1 = p0 + per_cta < g.pixels ? p0 + per_cta : g.pixels;
+  if (ty < g.lanes) {
+    for (long long p = p0 + ty; p < p1; p += g.lanes) {
+      const int w = (int)(p % pg.W);
+      const long long t = p / pg.W;
+      const int h = (int)(t % pg.H), n = (int)(t / pg.H);
+      float d[8], a[8];
+      gather_pool_grad(dy, arg, pg, n, h, w, tx, d);
+      ld8_stream(x + p * g.C + tx * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o = bf16_round(fmaxf(fmaf(a[j], sc[j], sh[j]), 0.f));
+        const float dd = o > 0.f ? d[j] : 0.f;
+        s[j] += dd;
+        q[j] = fmaf(dd, (a[j] - mu[j]) * rs[j], q[j]);
+      }
+    }
+  }
+  reduce_lanes_atomic(smem, s, tx, ty, g, sums);
+  reduce_lanes_atomic(smem, q, tx, ty, g, sums + g.C);
+}
+
+__global__ void __launch_bounds__(BN_THREADS) psb_bnpool_bwd_apply(const __nv_bfloat16* __restrict__ dy,
+                                                                    const uint8_t* __restrict__ arg,
+                                                                    const __nv_bfloat16* __restrict__ x,
+                                                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                    const float* __restrict__ ca, const float* __restrict__ cb,
+                                                                    const float* __restrict__ cc, __nv_bfloat16* __restrict__ dx,
+                                                                    BnGeom g, BnPoolGeom pg) {
+  const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
+  if (ty >= g.lanes) return;
+  float a[8], b[8], c[8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = ca[tx * 8 + j];
+    b[j] = cb[tx * 8 + j];
+    c[j] = cc[tx * 8 + j];
+    sc[j] = scale[tx * 8 + j];
+    sh[j] = shift[tx * 8 + j];
+  }
+  const long long stride = (long long)gridDim.x * g.lanes;
+  for (long long p = (long long)blockIdx.x * g.lanes + ty; p < g.pixels; p += stride) {
+    const int w = (int)(p % pg.W);
+    const long long t = p / pg.W;
+    const int h = (int)(t % pg.H), n = (int)(t / pg.H);
+    float d[8], xv[8];
+    gather_pool_grad(dy, arg, pg, n, h, w, tx, d);
+    const long long off = p * g.C + tx * 8;
+    ld8_stream(x + off, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float o = bf16_round(fmaxf(fmaf(xv[j], sc[j], sh[j]), 0.f));
+      const float dd = o > 0.f ? d[j] : 0.f;
+      xv[j] = fmaf(dd, a[j], fmaf(xv[j], b[j], c[j]));
+    }
+    st8(dx + off, xv);
+  }
+}
+
 BnGeom geom(long long pixels, int C) {
   BnGeom g;
   g.pixels = pixels;
@@ -357,4 +530,48 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
     if (relu) psb_bn_bwd_apply<false, true><<<grid, BN_THREADS, 0, s>>>(DY, X, Y, coef, coef + C, coef + 2 * C, DX, DR, g);
     else psb_bn_bwd_apply<false, false><<<grid, BN_THREADS, 0, s>>>(DY, X, Y, coef, coef + C, coef + 2 * C, DX, DR, g);
   }
+}
+
+// ---- EXPERIMENTAL fused BN + ReLU + 3x3/s2/p1 max-pool (training) -------------------------------------------------
+// `sums_in` != nullptr: Σx / Σx² were produced elsewhere (fused stem epilogue) and the statistics pass is skipped.
+void psb_bnpool_forward(cudaStream_t s, const void* x, const void* gamma, const void* beta, void* y, void* arg, float* sums,
+                        const float* sums_in, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
+                        float* running_var, int N, int H, int W, int C, float eps, float momentum) {
+  const long long pixels = (long long)N * H * W;
+  const BnGeom g = geom(pixels, C);
+  const int grid = grid_for(pixels, g);
+  auto X = reinterpret_cast<const __nv_bfloat16*>(x);
+  psb_count_launch(sums_in ? 2 : 3);
+  if (sums_in == nullptr) {
+    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
+    psb_bn_stats<<<grid, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
+  }
+  psb_bn_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums_in ? sums_in : sums, reinterpret_cast<const __nv_bfloat16*>(gamma),
+                                                   reinterpret_cast<const __nv_bfloat16*>(beta), mean, rstd, scale, shift,
+                                                   running_mean, running_var, C, pixels, eps, momentum);
+  BnPoolGeom pg{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
+  const long long total = (long long)N * pg.OH * pg.OW * pg.groups;
+  long long want = (total + 255) / 256, cap = (long long)grid_for(pixels, g) * 2;
+  psb_bnrelu_pool_fwd<<<(int)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, s>>>(
+      X, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<uint8_t*>(arg), pg);
+}
+
+void psb_bnpool_backward(cudaStream_t s, const void* dy, const void* arg, const void* x, const void* gamma, const float* mean,
+                         const float* rstd, const float* scale, const float* shift, float* sums /*2C*/, float* coef /*3C*/,
+                         void* dx, void* dgamma, void* dbeta, int N, int H, int W, int C) {
+  const long long pixels = (long long)N * H * W;
+  const BnGeom g = geom(pixels, C);
+  const int grid = grid_for(pixels, g);
+  BnPoolGeom pg{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
+  auto DY = reinterpret_cast<const __nv_bfloat16*>(dy);
+  auto A = reinterpret_cast<const uint8_t*>(arg);
+  auto X = reinterpret_cast<const __nv_bfloat16*>(x);
+  psb_count_launch(3);
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
+  psb_bnpool_bwd_reduce<<<grid, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(DY, A, X, scale, shift, mean, rstd, sums, g, pg);
+  psb_bn_bwd_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd, coef,
+                                                       coef + C, coef + 2 * C, reinterpret_cast<__nv_bfloat16*>(dgamma),
+                                                       reinterpret_cast<__nv_bfloat16*>(dbeta), C, pixels);
+  psb_bnpool_bwd_apply<<<grid, BN_THREADS, 0, s>>>(DY, A, X, scale, shift, coef, coef + C, coef + 2 * C,
+                                                   reinterpret_cast<__nv_bfloat16*>(dx), g, pg);
 }

@@ -13,13 +13,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..ops.batchnorm import FusedBatchNormAct2d
+from ..ops.batchnorm import FusedBatchNormAct2d, _kernel_ok, fused_bn_relu_maxpool
 from ..ops.pooling import FusedMaxPool2d
 from ..ops.stem import stem_conv, stem_conv_fused, stem_fused_supported, stem_supported
 
 # EXPERIMENTAL, default off: one implicit-GEMM stem kernel with the BatchNorm statistics in its epilogue
 # (csrc/kernels/stem_kernels.cu) instead of im2col + GEMM + statistics pass.  Validate with bench/stem_fused_check.py.
 _FUSED_STEM = os.environ.get("PSB200_STEM", "").lower() == "fused"
+# EXPERIMENTAL, default off: BN1 + ReLU + max-pool in one pass each way (bn_kernels.cu).  Validate with bench/bnpool_check.py.
+_FUSED_BNPOOL = os.environ.get("PSB200_BNPOOL", "").lower() == "fused"
 
 
 def _conv3x3(i, o, stride=1):
@@ -119,13 +121,21 @@ class ResNet(nn.Module):
             w = w.contiguous(memory_format=torch.channels_last)
         return F.conv2d(x, w, c.bias, c.stride, c.padding, c.dilation, c.groups)
 
+    def _tail(self, y, sums=None):
+        """BN1 + ReLU + max-pool after the stem convolution."""
+        mp = self.maxpool
+        if (_FUSED_BNPOOL and self.training and self.bn1.relu and self.bn1.running_mean is not None
+                and (mp.kernel_size, mp.stride, mp.padding) == (3, 2, 1) and _kernel_ok(y, None, self.bn1.weight)):
+            return fused_bn_relu_maxpool(y, self.bn1, sums)
+        return mp(self.bn1(y, sums=sums) if sums is not None else self.bn1(y))
+
     def forward(self, x):
         if (_FUSED_STEM and self.gemm_stem and self.training and x.shape[1] == self.conv1.in_channels
                 and stem_fused_supported(x, self.conv1)):
             y, sums = stem_conv_fused(x, self.conv1.weight)     # EXPERIMENTAL: implicit GEMM + BN statistics in one kernel
-            x = self.maxpool(self.bn1(y, sums=sums))
+            x = self._tail(y, sums)
         else:
-            x = self.maxpool(self.bn1(self.stem(x)))
+            x = self._tail(self.stem(x))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 
