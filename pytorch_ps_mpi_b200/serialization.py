@@ -6,18 +6,20 @@ straight out of tensor memory via ``blosc.compress_ptr(data_ptr, numel, element_
 (``/root/reference/serialization.py:8-36``; its ``compress`` returns an undefined name and the
 ``__main__`` demo calls undefined ``dumps``/``loads``).  This module finishes that idea:
 
-``dumps(obj)`` walks the object, swaps every tensor / ndarray for a tiny placeholder, pickles
-only that *skeleton*, and appends the raw tensor bytes taken from ``data_ptr()`` (one memcpy,
-done by the native ``host_codec`` when the extension is built; no numpy round trip, so bf16 /
-fp8 tensors survive — the reference's ``to_torch`` silently turned everything into float32,
-``mpi_comms.py:48``).  ``loads`` rebuilds tensors as zero-copy views of the received buffer.
+``dumps(obj)`` lets the C pickler walk the object; every torch tensor is lifted out of the stream
+(``reducer_override``) and every large ndarray leaves it as a protocol-5 out-of-band buffer, so the
+pickle holds only a *skeleton*; the raw bytes are appended behind it, taken from ``data_ptr()``
+(one memcpy, done by the native ``host_codec`` when the extension is built; no numpy round trip, so
+bf16 / fp8 tensors survive — the reference's ``to_torch`` silently turned everything into float32,
+``mpi_comms.py:48``).  ``loads`` rebuilds tensors and arrays as zero-copy views of the received buffer.
 
 Frame (little endian)::
 
     magic 'PSB2' | u8 version | u8 codec | u8 typesize | u8 reserved | u64 raw_len      (16 B)
     [codec 0: raw bytes | codec 1: zlib(shuffle(raw)) | codec 2: zlib(raw)]
-    raw := u32 skel_len | u32 ntensors | ntensors x (u8 dtype, u8 ndim, u16 0, u32 0, u64 nbytes,
-           ndim x i64 dims) | skeleton pickle | pad16 | tensor bytes, each padded to 16
+    raw := u32 skel_len | u32 nentries | nentries x (u8 dtype, u8 ndim, u16 0, u32 0, u64 nbytes,
+           ndim x i64 dims) | skeleton pickle | pad16 | entry bytes, each padded to 16
+           (dtype 255 = an out-of-band ndarray buffer of the pickle itself)
 
 The explicit ``raw_len`` header replaces the reference's 32-byte ``0x29`` sentinel + 10x
 over-allocated slots (``mpi_comms.py:80-85,96-104``) which could collide with payload bytes.
@@ -27,6 +29,7 @@ from __future__ import annotations
 import io
 import pickle
 import struct
+import threading
 import zlib
 from typing import Any, List, Tuple
 
@@ -51,18 +54,6 @@ _NP_OK = {torch.float32, torch.float64, torch.float16, torch.int8, torch.uint8, 
           torch.int32, torch.int64, torch.bool, torch.complex64}
 
 
-class _TensorRef:
-    """Placeholder left in the pickled skeleton where a tensor (or ndarray) was."""
-
-    __slots__ = ("i", "as_numpy")
-
-    def __init__(self, i: int, as_numpy: bool):
-        self.i, self.as_numpy = i, as_numpy
-
-    def __reduce__(self):
-        return (_TensorRef, (self.i, self.as_numpy))
-
-
 def tensor_info(t: torch.Tensor) -> dict:
     """``numel / data_ptr / element_size`` of a tensor (``/root/reference/serialization.py:8-11``)."""
     return {"numel": t.numel(), "data_ptr": t.data_ptr(), "element_size": t.element_size()}
@@ -83,108 +74,165 @@ def _native():
     return _NATIVE
 
 
-def _split(obj: Any, tensors: List[torch.Tensor]) -> Any:
-    """Replace tensors/ndarrays by placeholders, collecting them (``_predump``, ``serialization.py:14-19``)."""
-    if isinstance(obj, torch.Tensor):
-        t = obj.detach()
-        if t.is_cuda:
-            t = t.cpu()                       # device→host staging (slow path only)
-        if not t.is_contiguous():
-            t = t.contiguous()
-        tensors.append(t)
-        return _TensorRef(len(tensors) - 1, False)
-    if isinstance(obj, np.ndarray) and obj.dtype != object and obj.dtype.kind in "fiubc":
-        t = torch.from_numpy(np.ascontiguousarray(obj))
-        tensors.append(t)
-        return _TensorRef(len(tensors) - 1, True)
-    if isinstance(obj, dict):
-        return {k: _split(v, tensors) for k, v in obj.items()}
-    if isinstance(obj, list):
-        return [_split(v, tensors) for v in obj]
-    if isinstance(obj, tuple):
-        return tuple(_split(v, tensors) for v in obj)
-    if isinstance(obj, map):
-        return [_split(v, tensors) for v in obj]
-    return obj
+# Objects are walked by the C pickler itself (no Python-level recursion): ``reducer_override`` lifts torch tensors out
+# of the stream (``_predump``, ``/root/reference/serialization.py:14-19``), protocol-5 out-of-band buffers lift large
+# ndarrays out, small ndarrays stay in-band where a memcpy is cheaper than a header entry.
+_INBAND_BYTES = 4096          # ndarrays up to this size are pickled in-band (a memcpy beats a table entry)
+_RAW_BUFFER = 255             # dtype code of a protocol-5 out-of-band buffer in the tensor table
+_TLS = threading.local()
 
 
-def _join(obj: Any, tensors: List[torch.Tensor]) -> Any:
-    if isinstance(obj, _TensorRef):
-        t = tensors[obj.i]
-        return t.numpy() if obj.as_numpy else t
-    if isinstance(obj, dict):
-        return {k: _join(v, tensors) for k, v in obj.items()}
-    if isinstance(obj, list):
-        return [_join(v, tensors) for v in obj]
-    if isinstance(obj, tuple):
-        return tuple(_join(v, tensors) for v in obj)
-    return obj
+def _restore_tensor(i: int) -> torch.Tensor:
+    return _TLS.tensors[i]
+
+
+def _from_map(items: list) -> list:
+    return items
+
+
+class _Pickler(pickle.Pickler):
+    """One instance per thread, reused across :func:`dumps` calls (constructing a pickler costs more than a small dump)."""
+
+    def __init__(self):
+        self.file = io.BytesIO()
+        self.tensors: List[torch.Tensor] = []
+        self.bufs: list = []
+        super().__init__(self.file, protocol=5, buffer_callback=self._buffer)
+
+    def _buffer(self, pb) -> bool:
+        if pb.raw().nbytes <= _INBAND_BYTES:
+            return True                   # small array: stays in the pickle stream
+        self.bufs.append(pb)
+        return False
+
+    def reducer_override(self, obj):      # called by the C pickler for non-builtin objects only
+        if isinstance(obj, torch.Tensor):
+            t = obj.detach()
+            if t.is_cuda:
+                t = t.cpu()               # device→host staging (slow path only)
+            if not t.is_contiguous():
+                t = t.contiguous()
+            self.tensors.append(t)
+            return (_restore_tensor, (len(self.tensors) - 1,))
+        if isinstance(obj, map):          # the reference's to_np accepts map objects (mpi_comms.py:33-43)
+            return (_from_map, (list(obj),))
+        return NotImplemented
+
+
+def _pickler() -> "_Pickler":
+    pk = getattr(_TLS, "pickler", None)
+    if pk is None or getattr(_TLS, "busy", False):     # first use in this thread, or a nested dumps()
+        pk = _Pickler()
+        if not getattr(_TLS, "busy", False):
+            _TLS.pickler = pk
+    return pk
 
 
 def _pad16(n: int) -> int:
     return (n + 15) & ~15
 
 
+_HDR = struct.Struct("<II")
+_ENT = struct.Struct("<BBHIQ")
+
+
 def dumps(obj: Any) -> bytearray:
-    """Serialise ``obj`` to the raw (unframed) byte layout; tensors are copied exactly once."""
-    tensors: List[torch.Tensor] = []
-    skel = pickle.dumps(_split(obj, tensors), protocol=pickle.HIGHEST_PROTOCOL)
-    head = io.BytesIO()
-    head.write(struct.pack("<II", len(skel), len(tensors)))
-    for t in tensors:
-        head.write(struct.pack("<BBHIQ", _DT2CODE[t.dtype], t.dim(), 0, 0, t.numel() * t.element_size()))
-        head.write(struct.pack(f"<{t.dim()}q", *t.shape))
-    hb = head.getvalue()
-    off = _pad16(len(hb) + len(skel))
-    offs = []
-    for t in tensors:
-        offs.append(off)
-        off = _pad16(off + t.numel() * t.element_size())
-    out = bytearray(off)
-    out[: len(hb)] = hb
-    out[len(hb): len(hb) + len(skel)] = skel
-    nat = _native()
-    if nat is not None and tensors:
-        nat.pack_ptrs(out, offs, [t.data_ptr() for t in tensors],
-                      [t.numel() * t.element_size() for t in tensors])
-        # `tensors` keeps the sources alive until here
-    else:
-        mv = memoryview(out)
-        for t, o in zip(tensors, offs):
+    """Serialise ``obj`` to the raw (unframed) byte layout; tensor / large-array bytes are copied exactly once."""
+    pk = _pickler()
+    outer_busy = getattr(_TLS, "busy", False)
+    _TLS.busy = True
+    try:
+        f = pk.file
+        f.seek(0)
+        f.truncate()
+        pk.clear_memo()
+        pk.dump(obj)
+        tensors, bufs = pk.tensors, pk.bufs
+        skel = f.getvalue()
+        if not tensors and not bufs:           # plain Python payload (and small arrays): header + pickle
+            out = bytearray(_pad16(8 + len(skel)))
+            _HDR.pack_into(out, 0, len(skel), 0)
+            out[8: 8 + len(skel)] = skel
+            return out
+        parts = [_HDR.pack(len(skel), len(tensors) + len(bufs))]
+        sizes = []
+        for t in tensors:
             nb = t.numel() * t.element_size()
-            if nb:
-                src = t.reshape(-1).view(torch.uint8).numpy()
-                mv[o: o + nb] = src.data
-    return out
+            sizes.append(nb)
+            parts.append(_ENT.pack(_DT2CODE[t.dtype], t.dim(), 0, 0, nb))
+            parts.append(struct.pack(f"<{t.dim()}q", *t.shape))
+        raws = [pb.raw() for pb in bufs]
+        for r in raws:
+            sizes.append(r.nbytes)
+            parts.append(_ENT.pack(_RAW_BUFFER, 0, 0, 0, r.nbytes))
+        hb = b"".join(parts)
+        off = _pad16(len(hb) + len(skel))
+        offs = []
+        for nb in sizes:
+            offs.append(off)
+            off = _pad16(off + nb)
+        out = bytearray(off)
+        out[: len(hb)] = hb
+        out[len(hb): len(hb) + len(skel)] = skel
+        nt = len(tensors)
+        nat = _native() if nt else None
+        if nat is not None:
+            nat.pack_ptrs(out, offs[:nt], [t.data_ptr() for t in tensors], sizes[:nt])
+        elif nt:
+            mv = memoryview(out)
+            for t, o, nb in zip(tensors, offs, sizes):
+                if nb:
+                    mv[o: o + nb] = t.reshape(-1).view(torch.uint8).numpy().data
+        if raws:
+            mv = memoryview(out)
+            for r, o in zip(raws, offs[nt:]):
+                mv[o: o + r.nbytes] = r
+        return out
+    finally:
+        pk.tensors.clear()                     # the sources were kept alive until the copies above
+        pk.bufs.clear()
+        _TLS.busy = outer_busy
 
 
 def loads(buf) -> Any:
-    """Inverse of :func:`dumps`; tensors are zero-copy views into ``buf`` (keep it alive)."""
+    """Inverse of :func:`dumps`; tensors and large arrays are zero-copy views into ``buf`` (keep it alive)."""
     mv = memoryview(buf)
-    skel_len, nt = struct.unpack_from("<II", mv, 0)
+    skel_len, nent = _HDR.unpack_from(mv, 0)
     p = 8
     metas: List[Tuple[int, Tuple[int, ...], int]] = []
-    for _ in range(nt):
-        code, ndim, _, _, nbytes = struct.unpack_from("<BBHIQ", mv, p)
+    for _ in range(nent):
+        code, ndim, _, _, nbytes = _ENT.unpack_from(mv, p)
         p += 16
-        dims = struct.unpack_from(f"<{ndim}q", mv, p)
+        dims = struct.unpack_from(f"<{ndim}q", mv, p) if ndim else ()
         p += 8 * ndim
         metas.append((code, dims, nbytes))
-    skel = pickle.loads(mv[p: p + skel_len])
+    skel = mv[p: p + skel_len]
     off = _pad16(p + skel_len)
-    tensors = []
-    base = np.frombuffer(mv, dtype=np.uint8) if nt else None
+    tensors, buffers = [], []
+    base = None
     for code, dims, nbytes in metas:
-        dt = _DTYPES[code]
-        if nbytes:
-            raw = torch.from_numpy(base[off: off + nbytes]) if not mv.readonly else \
-                torch.frombuffer(bytearray(mv[off: off + nbytes]), dtype=torch.uint8)
-            t = raw.view(dt).view(dims)
+        if code == _RAW_BUFFER:
+            buffers.append(mv[off: off + nbytes])
         else:
-            t = torch.empty(dims, dtype=dt)
-        tensors.append(t)
+            dt = _DTYPES[code]
+            if nbytes:
+                if mv.readonly:
+                    raw = torch.frombuffer(bytearray(mv[off: off + nbytes]), dtype=torch.uint8)
+                else:
+                    if base is None:
+                        base = np.frombuffer(mv, dtype=np.uint8)
+                    raw = torch.from_numpy(base[off: off + nbytes])
+                t = raw.view(dt).view(dims)
+            else:
+                t = torch.empty(dims, dtype=dt)
+            tensors.append(t)
         off = _pad16(off + nbytes)
-    return _join(skel, tensors)
+    prev = getattr(_TLS, "tensors", None)
+    _TLS.tensors = tensors
+    try:
+        return pickle.loads(skel, buffers=buffers)
+    finally:
+        _TLS.tensors = prev
 
 
 # ---------------------------------------------------------------------------------------
