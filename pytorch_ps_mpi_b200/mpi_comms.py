@@ -128,13 +128,12 @@ def print_summary(flat_dict):
 
 def format_for_send(obj, level: int = 0):
     """Serialise + frame an object → ``(packaged, {'msg_bytes', 'packaged_bytes'})`` (``mpi_comms.py:186-193``)."""
-    send = serialization.dumps(obj)
-    packaged = compress(send, level=level)
-    return packaged, {"msg_bytes": len(send), "packaged_bytes": len(packaged)}
+    packaged, raw_len = serialization.dumps_framed(obj, level=level)
+    return packaged, {"msg_bytes": raw_len, "packaged_bytes": len(packaged)}
 
 
 def _unpack(msg, cuda: bool = False, numpy: bool = False):
-    obj = serialization.loads(decompress(msg))
+    obj = serialization.loads(serialization.unframe_view(msg))      # tensors are views into `msg` (kept alive by them)
     return to_np(obj) if numpy else to_torch(obj, cuda=cuda)
 
 
@@ -200,9 +199,8 @@ def igather(obj, name="", root: int = 0, level: int = 0):
     """
     tr = _tp.get_transport()
     t = [time.time()]
-    raw = serialization.dumps(obj)
+    send, _ = serialization.dumps_framed(obj, level=level)     # level 0: serialise + frame in one buffer
     t += [time.time()]
-    send = compress(raw, level=level)
     t += [time.time()]
     max_bytes[name] = max(max_bytes.get(name, 0), len(send))
     tag = _next_tag()
@@ -242,7 +240,7 @@ def ibroadcast(obj, root: int = 0, level: int = 0):
     tr = _tp.get_transport()
     tag = _next_tag()
     if tr.rank == root:
-        send = compress(serialization.dumps(obj), level=level)
+        send, _ = serialization.dumps_framed(obj, level=level)
         req = _Multi([tr.isend(r, send, tag=tag) for r in range(tr.size) if r != root])
         return send, req
     req = tr.irecv(src=root, tag=tag)
@@ -344,7 +342,7 @@ class Iallgather:
 # ---------------------------------------------------------------------------------------
 def isend_obj(obj, dst: int, tag: int = 0, level: int = 0):
     tr = _tp.get_transport()
-    send = compress(serialization.dumps(obj), level=level)
+    send, _ = serialization.dumps_framed(obj, level=level)
     req = tr.isend(dst, send, tag=_TAG_P2P + tag)
     req._keep = send
     return req

@@ -244,6 +244,7 @@ def get_transport(kind: Optional[str] = None) -> Transport:
         return _TRANSPORT
     w = runtime.world()
     kind = (kind or os.environ.get("PSB200_TRANSPORT") or "").lower()
+    runtime.tune_host_allocator()          # message-sized host buffers recycle instead of page-faulting every step
     if w.size == 1:
         _TRANSPORT = LocalTransport()
         return _TRANSPORT

@@ -36,7 +36,7 @@ from typing import Any, List, Tuple
 import numpy as np
 import torch
 
-__all__ = ["dumps", "loads", "compress", "decompress", "frame", "unframe", "tensor_info",
+__all__ = ["dumps", "loads", "dumps_framed", "unframe_view", "compress", "decompress", "frame", "unframe", "tensor_info",
            "MAGIC", "HEADER_BYTES"]
 
 MAGIC = b"PSB2"
@@ -136,8 +136,11 @@ _HDR = struct.Struct("<II")
 _ENT = struct.Struct("<BBHIQ")
 
 
-def dumps(obj: Any) -> bytearray:
-    """Serialise ``obj`` to the raw (unframed) byte layout; tensor / large-array bytes are copied exactly once."""
+def dumps(obj: Any, headroom: int = 0) -> bytearray:
+    """Serialise ``obj`` to the raw (unframed) byte layout; tensor / large-array bytes are copied exactly once.
+
+    ``headroom`` (a multiple of 16) leaves that many bytes free in front of the layout, so a frame header can be
+    written in place (:func:`dumps_framed`) instead of copying the whole message once more."""
     pk = _pickler()
     outer_busy = getattr(_TLS, "busy", False)
     _TLS.busy = True
@@ -149,10 +152,11 @@ def dumps(obj: Any) -> bytearray:
         pk.dump(obj)
         tensors, bufs = pk.tensors, pk.bufs
         skel = f.getvalue()
+        H = headroom
         if not tensors and not bufs:           # plain Python payload (and small arrays): header + pickle
-            out = bytearray(_pad16(8 + len(skel)))
-            _HDR.pack_into(out, 0, len(skel), 0)
-            out[8: 8 + len(skel)] = skel
+            out = bytearray(H + _pad16(8 + len(skel)))
+            _HDR.pack_into(out, H, len(skel), 0)
+            out[H + 8: H + 8 + len(skel)] = skel
             return out
         parts = [_HDR.pack(len(skel), len(tensors) + len(bufs))]
         sizes = []
@@ -166,14 +170,14 @@ def dumps(obj: Any) -> bytearray:
             sizes.append(r.nbytes)
             parts.append(_ENT.pack(_RAW_BUFFER, 0, 0, 0, r.nbytes))
         hb = b"".join(parts)
-        off = _pad16(len(hb) + len(skel))
+        off = H + _pad16(len(hb) + len(skel))
         offs = []
         for nb in sizes:
             offs.append(off)
-            off = _pad16(off + nb)
+            off = H + _pad16(off - H + nb)
         out = bytearray(off)
-        out[: len(hb)] = hb
-        out[len(hb): len(hb) + len(skel)] = skel
+        out[H: H + len(hb)] = hb
+        out[H + len(hb): H + len(hb) + len(skel)] = skel
         nt = len(tensors)
         nat = _native() if nt else None
         if nat is not None:
@@ -294,6 +298,29 @@ def unframe(msg) -> bytearray:
     if len(raw) != raw_len:
         raise ValueError("unframe: length mismatch after decompression")
     return bytearray(raw)
+
+
+def dumps_framed(obj: Any, level: int = 0) -> Tuple[bytearray, int]:
+    """``compress(dumps(obj), level)`` → ``(message, raw_len)``.  At level 0 the 16-byte header is written into the
+    head room of the serialised buffer: one allocation and one copy of the tensor bytes per message instead of two."""
+    if level <= 0:
+        out = dumps(obj, headroom=HEADER_BYTES)
+        raw_len = len(out) - HEADER_BYTES
+        out[:HEADER_BYTES] = MAGIC + struct.pack("<BBBBQ", _VERSION, _CODEC_STORE, 4, 0, raw_len)
+        return out, raw_len
+    raw = dumps(obj)
+    return frame(raw, level=level), len(raw)
+
+
+def unframe_view(msg):
+    """:func:`unframe` without the copy for stored (level-0) frames: a memoryview into ``msg`` (keep ``msg`` alive)."""
+    mv = memoryview(msg)
+    if len(mv) >= HEADER_BYTES and bytes(mv[:4]) == MAGIC and mv[5] == _CODEC_STORE and mv[4] == _VERSION:
+        raw_len = struct.unpack_from("<Q", mv, 8)[0]
+        if len(mv) - HEADER_BYTES < raw_len:
+            raise ValueError(f"unframe: message truncated ({len(mv) - HEADER_BYTES} < {raw_len} bytes)")
+        return mv[HEADER_BYTES: HEADER_BYTES + raw_len]
+    return unframe(msg)
 
 
 _BANNED = {"lz4", "snappy"}

@@ -199,3 +199,34 @@ def test_wire_roundtrip_random_tensors(shape, dtype, level):
     obj = {"t": t, "meta": {"shape": tuple(shape), "k": [1, 2.5, "s"]}}
     back = ser.loads(ser.decompress(ser.compress(ser.dumps(obj), level=level)))
     assert back["t"].dtype == dt and back["t"].shape == t.shape and torch.equal(back["t"], t) and back["meta"] == obj["meta"]
+
+
+def test_dumps_framed_matches_compress_of_dumps_and_views_roundtrip():
+    """One-buffer serialise+frame (level 0) is byte-identical to compress(dumps()), and unframe_view is zero-copy."""
+    import numpy as np
+    import torch
+    from pytorch_ps_mpi_b200 import serialization as ser
+    obj = {"w": torch.arange(10, dtype=torch.float32).bfloat16(), "big": np.arange(5000.0), "small": np.arange(3), "s": "x",
+           "t": (1, 2.5)}
+    for level in (0, 1):
+        msg, raw_len = ser.dumps_framed(obj, level=level)
+        ref = ser.compress(ser.dumps(obj), level=level)
+        assert bytes(msg) == bytes(ref) and raw_len == len(ser.dumps(obj))
+        view = ser.unframe_view(msg)
+        back = ser.loads(view)
+        assert torch.equal(back["w"], obj["w"]) and np.array_equal(back["big"], obj["big"]) and back["t"] == obj["t"]
+        if level == 0:
+            assert isinstance(view, memoryview) and view.obj is msg          # no copy of the payload
+    import pytest
+    with pytest.raises(ValueError):
+        ser.unframe_view(bytes(ser.dumps_framed(obj)[0])[:40])
+
+
+def test_allocator_tuning_is_idempotent_and_optional(monkeypatch):
+    from pytorch_ps_mpi_b200 import runtime
+    monkeypatch.setattr(runtime, "_ALLOC_TUNED", False)
+    monkeypatch.setenv("PSB200_MALLOC_TUNE", "0")
+    assert runtime.tune_host_allocator() is False
+    monkeypatch.setenv("PSB200_MALLOC_TUNE", "1")
+    assert runtime.tune_host_allocator() in (True, False)       # True on glibc
+    assert runtime.tune_host_allocator() == runtime._ALLOC_TUNED
