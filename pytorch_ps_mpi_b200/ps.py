@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import math
 import os
+import pickle
 import time
 import weakref
 from collections import OrderedDict
@@ -287,14 +288,21 @@ class MPI_PS(torch.optim.Optimizer):
         if not all(g.shape == grads[0].shape for g in grads):
             print("  !!", self.rank, name, [tuple(g.shape) for g in grads])
             raise ValueError("shapes not the same")
-        d_p = grads[0].clone() if len(grads) == 1 else sum(grads[1:], grads[0].clone())
         if p.grad is None:
             return
+        # rank-ordered sum (ps.py:180) with one allocation and no dead passes: the first pair is added out of place
+        # (the decoded gradients may be views of received messages), the rest accumulate in place
+        if len(grads) == 1:
+            d_p = grads[0].clone()
+        else:
+            d_p = torch.add(grads[0], grads[1])
+            for g in grads[2:]:
+                d_p.add_(g)
         d_p = d_p.to(device=p.device).reshape(p.shape)
         if d_p.dtype != p.dtype:
             d_p = d_p.to(p.dtype)
         if self.average and scale_by > 1:
-            d_p = d_p / scale_by
+            d_p.div_(scale_by)
         with torch.no_grad():
             self.optim_step(p, d_p, **self._hyper(groups[id(p)]))
         data["optim_step_time"] += time.time() - start
@@ -338,7 +346,7 @@ class MPI_PS(torch.optim.Optimizer):
     def _step_allgather_coalesced(self, data, names, msgs, groups):
         """One all-gather for the whole step: ``{"names": [...], "msgs": [framed bytes per parameter]}``."""
         start = time.time()
-        bundle, _ = comms.format_for_send({"names": names, "msgs": [bytes(m) for m in msgs]})
+        bundle, _ = comms.format_for_send({"names": names, "msgs": [pickle.PickleBuffer(m) for m in msgs]})
         data["iallgather_prepare_time"] = 0.0
         resp = self.iallgather.send(bundle, None)
         data["isend_time"] = time.time() - start
@@ -364,7 +372,9 @@ class MPI_PS(torch.optim.Optimizer):
 
         start = time.time()
         if self.coalesce:
-            recv, req, _t = comms.igather({"names": names, "msgs": [bytes(m) for m in msgs]}, name="__step__", level=-1)
+            # the encoded messages travel out of band (protocol-5 buffers): no second copy into the bundle's pickle
+            recv, req, _t = comms.igather({"names": names, "msgs": [pickle.PickleBuffer(m) for m in msgs]},
+                                          name="__step__", level=-1)
             data["isend_time"] = time.time() - start
             start = time.time()
             bundles = comms.irecv(recv, req, name="__step__")
@@ -380,7 +390,8 @@ class MPI_PS(torch.optim.Optimizer):
             posted = []
         else:
             # one gather per parameter, all posted before any is waited (the reference's pipelining)
-            posted = [comms.igather({"name": n, "msg": m}, name=n, level=-1) for n, m in zip(names, msgs)]
+            posted = [comms.igather({"name": n, "msg": pickle.PickleBuffer(m)}, name=n, level=-1)
+                      for n, m in zip(names, msgs)]
             data["isend_time"] = time.time() - start
 
         for n, (recv, req, _t) in zip(names, posted):
@@ -446,7 +457,7 @@ class MPI_PS(torch.optim.Optimizer):
             if self._async_send_req is not None:
                 self._async_send_req.Wait()
             self._async_send_req = comms.isend_obj(
-                {"kind": "grad", "names": names, "msgs": [bytes(m) for m in msgs],
+                {"kind": "grad", "names": names, "msgs": [pickle.PickleBuffer(m) for m in msgs],
                  "version": self._param_version, "rank": self.rank}, dst=0, tag=_TAG_GRAD)
             data["isend_time"] = time.time() - start
             start = time.time()

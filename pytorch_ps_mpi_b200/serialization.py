@@ -27,6 +27,7 @@ over-allocated slots (``mpi_comms.py:80-85,96-104``) which could collide with pa
 from __future__ import annotations
 
 import io
+import os
 import pickle
 import struct
 import threading
@@ -77,7 +78,7 @@ def _native():
 # Objects are walked by the C pickler itself (no Python-level recursion): ``reducer_override`` lifts torch tensors out
 # of the stream (``_predump``, ``/root/reference/serialization.py:14-19``), protocol-5 out-of-band buffers lift large
 # ndarrays out, small ndarrays stay in-band where a memcpy is cheaper than a header entry.
-_INBAND_BYTES = 4096          # ndarrays up to this size are pickled in-band (a memcpy beats a table entry)
+_INBAND_BYTES = int(os.environ.get("PSB200_INBAND_BYTES", 4096))   # buffers up to this size are pickled in-band (a memcpy beats a table entry)
 _RAW_BUFFER = 255             # dtype code of a protocol-5 out-of-band buffer in the tensor table
 _TLS = threading.local()
 
