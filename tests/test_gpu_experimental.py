@@ -1,0 +1,116 @@
+"""GPU tests of the EXPERIMENTAL kernels (fused stem, fused BN+ReLU+max-pool, GEMM epilogue variants).
+
+They are written but have never run on hardware, so they are skipped unless ``PSB200_TEST_EXPERIMENTAL=1`` — the
+default ``pytest -m gpu`` run must only exercise verified code.  Once ``bench/stem_fused_check.py``,
+``bench/bnpool_check.py`` and ``bench/gemm_variants.py`` are green on a B200, drop the skip and flip the defaults.
+Each compares the kernel with a plain PyTorch fp32 reference of the same op.
+"""
+import copy
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PSB200_TEST_EXPERIMENTAL") != "1",
+                                 reason="experimental kernels: set PSB200_TEST_EXPERIMENTAL=1 (never run on hardware yet)")]
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _rel(a, b):
+    return (a.float() - b.float()).abs().max().item() / max(b.float().abs().max().item(), 1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 224, 224), (3, 64, 64), (1, 30, 40), (5, 17, 8), (2, 225, 256)])
+def test_fused_stem_forward_and_bn_sums(shape):
+    from pytorch_ps_mpi_b200.ops import ext
+    from pytorch_ps_mpi_b200.ops.stem import _w2d
+    n, h, w = shape
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    wt = (torch.randn(64, 3, 7, 7, device=dev) * 0.05).bfloat16()
+    x = _cl(torch.randn(n, 3, h, w, device=dev).bfloat16())
+    y, sums = ext.cuda().stem_fwd(x, _w2d(wt), True)
+    ref = F.conv2d(x.float(), wt.float(), stride=2, padding=3)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert _rel(y, ref) < 2e-2
+    yf = y.float()
+    want = torch.cat([yf.sum((0, 2, 3)), (yf * yf).sum((0, 2, 3))])
+    assert ((sums - want).abs() / (want.abs() + 1.0)).max().item() < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(8, 224, 224), (2, 64, 64), (1, 30, 40), (3, 17, 8), (2, 33, 256)])
+def test_implicit_stem_wgrad(shape):
+    from pytorch_ps_mpi_b200.ops import ext
+    from pytorch_ps_mpi_b200.ops.stem import stem_wgrad_implicit
+    n, h, w = shape
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    x = _cl(torch.randn(n, 3, h, w, device=dev).bfloat16())
+    g = _cl(torch.randn(n, 64, (h - 1) // 2 + 1, (w - 1) // 2 + 1, device=dev).bfloat16())
+    ref = g.permute(0, 2, 3, 1).reshape(-1, 64).float().t() @ ext.cuda().im2col_stem(x).float()
+    assert _rel(stem_wgrad_implicit(x, g), ref) < 1e-2
+
+
+def test_fused_stem_autograd_matches_default_path():
+    from pytorch_ps_mpi_b200.ops import stem as stem_mod
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    wt = (torch.randn(64, 3, 7, 7, device=dev) * 0.05).bfloat16()
+    x = _cl(torch.randn(4, 3, 224, 224, device=dev).bfloat16())
+    gy = _cl(torch.randn(4, 64, 112, 112, device=dev).bfloat16())
+    grads = []
+    for fused, implicit in ((False, False), (True, False), (True, True)):
+        stem_mod._IMPLICIT_WGRAD = implicit
+        wv = wt.clone().requires_grad_(True)
+        y = stem_mod.stem_conv_fused(x, wv)[0] if fused else stem_mod.stem_conv(x, wv)
+        y.backward(gy)
+        grads.append(wv.grad.float())
+    stem_mod._IMPLICIT_WGRAD = False
+    assert _rel(grads[1], grads[0]) < 1e-2 and _rel(grads[2], grads[0]) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 112, 112), (2, 64, 17, 23), (3, 128, 8, 8), (1, 8, 5, 4)])
+def test_fused_bn_relu_maxpool(shape):
+    from pytorch_ps_mpi_b200.ops.batchnorm import FusedBatchNormAct2d, fused_bn_relu_maxpool
+    from pytorch_ps_mpi_b200.ops.pooling import FusedMaxPool2d
+    n, c, h, w = shape
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    pool = FusedMaxPool2d(3, 2, 1)
+    bn_a = FusedBatchNormAct2d(c, relu=True).to(dev).bfloat16().train()
+    with torch.no_grad():
+        bn_a.weight.copy_(torch.randn(c).abs() + 0.5)
+        bn_a.bias.copy_(torch.randn(c) * 0.3)
+    bn_b = copy.deepcopy(bn_a)
+    x = _cl((torch.randn(n, c, h, w, device=dev) * 2 + 0.3).bfloat16())
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = pool(bn_a(xa)), fused_bn_relu_maxpool(xb, bn_b)
+    assert torch.equal(ya, yb), "same bf16 rounding point: the forward must be bit-identical"
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+    assert _rel(xb.grad, xa.grad) < 2e-2
+    assert _rel(bn_b.weight.grad, bn_a.weight.grad) < 2e-2 and _rel(bn_b.bias.grad, bn_a.bias.grad) < 2e-2
+    assert _rel(bn_b.running_var, bn_a.running_var) < 1e-5
+
+
+@pytest.mark.parametrize("epi", [1, 2, 3])
+@pytest.mark.parametrize("mnk", [(512, 256, 128), (1000, 328, 264), (4096, 3072, 768), (300, 64, 176), (515, 330, 72)])
+def test_gemm_epilogue_variants(epi, mnk):
+    from pytorch_ps_mpi_b200.ops.linear import bcast_linear
+    M, N, K = mnk
+    if epi == 3 and N % 8:
+        pytest.skip("TMA-store epilogue needs N % 8 == 0")
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    x = (torch.randn(M, K, device=dev) / K ** 0.5).bfloat16()
+    w = torch.randn(N, K, device=dev).bfloat16()
+    b = torch.randn(N, device=dev)
+    ref = torch.relu(x.float() @ w.float().t() + b)
+    y = bcast_linear(x, w, b, relu=True, variant=2 | epi << 4)
+    assert _rel(y, ref) < 2e-2
