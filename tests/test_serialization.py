@@ -230,3 +230,49 @@ def test_allocator_tuning_is_idempotent_and_optional(monkeypatch):
     monkeypatch.setenv("PSB200_MALLOC_TUNE", "1")
     assert runtime.tune_host_allocator() in (True, False)       # True on glibc
     assert runtime.tune_host_allocator() == runtime._ALLOC_TUNED
+
+
+def test_dumps_is_thread_safe_and_reentrant():
+    """The encode pool calls dumps() from several threads at once (ps.py::async_code); each thread has its own pickler."""
+    import pickle
+    import threading
+    import numpy as np
+    import torch
+    from pytorch_ps_mpi_b200 import serialization as ser
+    errs = []
+
+    def work(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for i in range(40):
+                n = int(rng.integers(1, 5000))
+                obj = {"t": torch.full((n,), float(seed)), "a": np.full(n, seed, dtype=np.float64), "i": i, "s": "x" * (i % 7),
+                       "raw": pickle.PickleBuffer(bytes([seed % 251]) * n)}
+                back = ser.loads(ser.dumps(obj))
+                assert back["i"] == i and torch.equal(back["t"], obj["t"]) and np.array_equal(back["a"], obj["a"])
+                assert bytes(back["raw"]) == bytes([seed % 251]) * n
+        except Exception as e:      # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+
+    class Weird:                     # dumps() called while another dumps() is on the stack of the same thread
+        def __reduce__(self):
+            return (bytes, (bytes(ser.dumps({"inner": torch.arange(3)})),))
+
+    inner = ser.loads(ser.loads(ser.dumps({"w": Weird(), "after": torch.arange(4)}))["w"])
+    assert torch.equal(inner["inner"], torch.arange(3))
+
+
+def test_loads_from_readonly_bytes_and_memoryview():
+    import numpy as np
+    import torch
+    from pytorch_ps_mpi_b200 import serialization as ser
+    obj = {"t": torch.arange(6, dtype=torch.int32).view(2, 3), "big": np.arange(2000, dtype=np.float32), "e": torch.empty(0, 3)}
+    raw = ser.dumps(obj)
+    for buf in (raw, bytes(raw), memoryview(raw), memoryview(bytes(raw))):
+        back = ser.loads(buf)
+        assert torch.equal(back["t"], obj["t"]) and np.array_equal(back["big"], obj["big"]) and back["e"].shape == (0, 3)
