@@ -42,3 +42,22 @@ def test_sass_shows_blackwell_paths():
     assert "STRONG.SYS" in p            # system-scope peer loads/stores of the gather / broadcast
     ptx_like = subprocess.run(["strings", str(psk)], stdout=subprocess.PIPE, text=True).stdout
     assert "HMMA" not in s.replace("UTCHMMA", "")      # no legacy mma.sync tensor path in the GEMM
+
+
+def test_sass_of_the_experimental_kernels():
+    """The opt-in kernels (fused stem, GEMM epilogue variants) are real tcgen05 / TMA code too, and spill nothing."""
+    stem, gexp = ext.OBJ / "stem_kernels.o", ext.OBJ / "bcast_gemm_exp.o"
+    if not stem.exists() or not gexp.exists():
+        pytest.skip("object files not present (built elsewhere)")
+    s = _sass(stem)
+    for mnemonic in ("UTCHMMA", "UTMALDG.2D", "UTMASTG.2D", "LDTM", "LDGSTS"):
+        assert mnemonic in s, f"{mnemonic} missing from stem_kernels SASS"
+    g = _sass(gexp)
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTMASTG.2D", "LDTM"):
+        assert mnemonic in g, f"{mnemonic} missing from bcast_gemm_exp SASS"
+    for log in ("stem_kernels.nvcc.log", "bcast_gemm_exp.nvcc.log", "bn_kernels.nvcc.log"):
+        p = ext.OBJ / log
+        if p.exists():
+            for line in p.read_text().splitlines():
+                if "spill" in line:
+                    assert "0 bytes spill stores, 0 bytes spill loads" in line, f"{log}: {line.strip()}"
