@@ -36,7 +36,8 @@ import sys
 from dataclasses import dataclass, field
 from typing import Dict, FrozenSet, Iterable, List, Optional, Sequence, Tuple
 
-__all__ = ["Violation", "Result", "Model", "build_ps", "build_allgather", "build_async", "check", "MODES"]
+__all__ = ["Violation", "Result", "Model", "build_ps", "build_allgather", "build_async", "build_stem_pipeline", "build_stem_wgrad_pipeline",
+           "check", "MODES"]
 
 DONE = 1 << 62          # device_engine._DONE_EPOCH / PSB_DONE_EPOCH
 
@@ -619,7 +620,108 @@ def build_async(n: int, epochs: int, quota: int = 1, consistent: bool = False, d
     return m
 
 
-MODES = {"ps": build_ps, "allgather": build_allgather, "async": build_async}
+def build_stem_pipeline(n: int = 1, epochs: int = 4, drop: Optional[str] = None) -> Model:
+    """Intra-CTA pipeline of the experimental fused stem kernel (``csrc/kernels/stem_kernels.cu::psb_stem_fwd_kernel``):
+    builder warps, the MMA warp, the epilogue warps, the cp.async patch loads and the bulk stores, over ``epochs``
+    tiles.  mbarrier phase waits are modelled as counts (``wait(parity)`` at tile ``i`` of a double-buffered resource
+    == "at least ``i // 2`` completions", exact because nothing can run two phases ahead — which the search confirms by
+    never finding a version mismatch).  ``n`` is unused (one CTA).
+
+    ``drop``: ``'a_empty'`` (builders do not wait for the MMAs that read the A buffer), ``'t_empty'`` (the MMA warp does
+    not wait for the epilogue to drain the accumulator), ``'store_wait'`` (the staging tile is rewritten while the bulk
+    store still reads it).  (The named barriers between the four builder warps are below this model's resolution:
+    they are one process here.)"""
+    m = Model()
+    T = epochs
+    builder, mma, epi, store = [], [], [], []
+    for i in range(T):
+        b = i & 1
+        k = i // 2
+        # ---- builders (4 warps in lock step through named barriers) ----
+        if i == 0:
+            builder.append(("acq", [(("patch", 0), "w", None)]))                    # load_patch(t0)
+        if i + 1 < T:
+            builder.append(("acq", [(("patch", b ^ 1), "w", None)]))                  # cp.async of tile i+1
+        builder.append(("rel", [(("patch", b), "w", i)]))                            # cp.async.wait_group + barrier
+        if drop != "a_empty":
+            builder.append(("wait", ("a_empty", b), k))
+        builder.append(("acq", [(("patch", b), "r", i), (("A", b), "w", None)]))     # build_row
+        builder.append(("rel", [(("patch", b), "r", None), (("A", b), "w", i)]))
+        builder.append(("sig", ("a_full", b), k + 1))
+        # ---- MMA warp ----
+        if drop != "t_empty":
+            mma.append(("wait", ("t_empty", b), k))
+        mma.append(("wait", ("a_full", b), k + 1))
+        mma.append(("acq", [(("A", b), "r", i), (("T", b), "w", None)]))
+        mma.append(("rel", [(("A", b), "r", None), (("T", b), "w", i)]))             # tcgen05.commit fires when they finish
+        mma.append(("sig", ("a_empty", b), k + 1))
+        mma.append(("sig", ("t_full", b), k + 1))
+        # ---- epilogue warps ----
+        epi.append(("wait", ("t_full", b), k + 1))
+        epi.append(("acq", [(("T", b), "r", i)]))
+        epi.append(("rel", [(("T", b), "r", None)]))
+        epi.append(("sig", ("t_empty", b), k + 1))
+        if drop != "store_wait" and i >= 2:
+            epi.append(("wait", ("st_done",), i - 1))                                 # cp.async.bulk.wait_group.read 1
+        epi.append(("acq", [(("O", b), "w", None)]))
+        epi.append(("rel", [(("O", b), "w", i)]))
+        epi.append(("sig", ("st_issued",), i + 1))
+        epi.append(("acq", [(("O", b), "r", i)]))                                     # BatchNorm column sums
+        epi.append(("rel", [(("O", b), "r", None)]))
+        # ---- the TMA unit executing the bulk stores, in order ----
+        store.append(("wait", ("st_issued",), i + 1))
+        store.append(("acq", [(("O", b), "r", i)]))
+        store.append(("rel", [(("O", b), "r", None)]))
+        store.append(("sig", ("st_done",), i + 1))
+    m.add("builders", builder)
+    m.add("mma", mma)
+    m.add("epilogue", epi)
+    m.add("tma_store", store)
+    return m
+
+
+def build_stem_wgrad_pipeline(n: int = 1, epochs: int = 4, drop: Optional[str] = None) -> Model:
+    """Intra-CTA pipeline of ``psb_stem_wgrad_kernel``: builders + the gy TMA producer fill (A, G)[buf]; the MMA warp
+    accumulates every tile into one TMEM-resident accumulator and frees the pair with one commit; the builders read the
+    accumulator after the last commit.  ``drop``: ``'empty'`` (producers do not wait for the MMAs), ``'d_full'``
+    (the final epilogue does not wait for the last MMA)."""
+    m = Model()
+    T = epochs
+    builder, prod, mma = [], [], []
+    for i in range(T):
+        b, k = i & 1, i // 2
+        if i == 0:
+            builder.append(("acq", [(("patch", 0), "w", None)]))
+        if i + 1 < T:
+            builder.append(("acq", [(("patch", b ^ 1), "w", None)]))
+        builder.append(("rel", [(("patch", b), "w", i)]))
+        if drop != "empty":
+            builder.append(("wait", ("empty", b), k))
+            prod.append(("wait", ("empty", b), k))
+        builder.append(("acq", [(("patch", b), "r", i), (("A", b), "w", None)]))
+        builder.append(("rel", [(("patch", b), "r", None), (("A", b), "w", i)]))
+        builder.append(("sig", ("a_full", b), k + 1))
+        prod.append(("acq", [(("G", b), "w", None)]))                                 # cp.async.bulk.tensor load of gy
+        prod.append(("rel", [(("G", b), "w", i)]))
+        prod.append(("sig", ("g_full", b), k + 1))
+        mma.append(("wait", ("a_full", b), k + 1))
+        mma.append(("wait", ("g_full", b), k + 1))
+        mma.append(("acq", [(("A", b), "r", i), (("G", b), "r", i), (("D",), "w", None)]))
+        mma.append(("rel", [(("A", b), "r", None), (("G", b), "r", None), (("D",), "w", i + 1)]))
+        mma.append(("sig", ("empty", b), k + 1))
+    mma.append(("sig", ("d_full",), 1))
+    if drop != "d_full":
+        builder.append(("wait", ("d_full",), 1))
+    builder.append(("acq", [(("D",), "r", T)]))                                       # the CTA's partial dW
+    builder.append(("rel", [(("D",), "r", None)]))
+    m.add("builders", builder)
+    m.add("gy_tma", prod)
+    m.add("mma", mma)
+    return m
+
+
+MODES = {"ps": build_ps, "allgather": build_allgather, "async": build_async, "stem_pipeline": build_stem_pipeline,
+         "stem_wgrad_pipeline": build_stem_wgrad_pipeline}
 
 
 def check(mode: str, n: int, epochs: int, max_states: int = 2_000_000, **kw) -> Result:
@@ -629,7 +731,8 @@ def check(mode: str, n: int, epochs: int, max_states: int = 2_000_000, **kw) -> 
 
 def main(argv: Optional[Sequence[str]] = None) -> int:
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
-    ap.add_argument("--mode", choices=sorted(MODES), default="ps")
+    ap.add_argument("--mode", choices=sorted(MODES), default="ps",
+                    help="engine protocols (ps / allgather / async) or the kernel pipelines (stem_*; --epochs = tiles)")
     ap.add_argument("--ranks", type=int, default=3)
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--quota", type=int, default=1)

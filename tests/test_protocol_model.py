@@ -57,3 +57,18 @@ def test_cli(capsys):
     assert "ok:" in capsys.readouterr().out
     assert pm.main(["--mode", "ps", "--ranks", "2", "--epochs", "2", "--drop", "params_ready"]) == 1
     assert "VIOLATION" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("mode,tiles", [("stem_pipeline", 6), ("stem_wgrad_pipeline", 6)])
+def test_kernel_pipelines_hold(mode, tiles):
+    """The mbarrier hand-offs inside the experimental fused-stem kernels (double-buffered A / patch / staging / TMEM)."""
+    res = pm.check(mode, 1, tiles)
+    assert res.finals == 1
+
+
+@pytest.mark.parametrize("mode,drop", [("stem_pipeline", "a_empty"), ("stem_pipeline", "t_empty"), ("stem_pipeline", "store_wait"),
+                                       ("stem_wgrad_pipeline", "empty"), ("stem_wgrad_pipeline", "d_full")])
+def test_kernel_pipeline_mutants_are_caught(mode, drop):
+    with pytest.raises(pm.Violation) as ei:
+        pm.check(mode, 1, 5, drop=drop)
+    assert ei.value.kind in {"race", "version"}, str(ei.value)
