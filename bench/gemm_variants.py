@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Where does the 2-CTA tcgen05 GEMM lose time on short-K shapes?  (round-2 diagnosis, needs a GPU)
 
-Runs the production ``psb_bcast_gemm2_kernel`` next to the experimental variants of ``bcast_gemm_exp.cu``:
+Runs the production choice of ``psb_bcast_gemm2_kernel`` (``bcast_gemm2.cu``) next to every epilogue it can be built with
+(the round-2 run of this script is ``profiles/gemm_variants_r2.jsonl``; it made ``epi3`` / ``epi1`` the defaults):
 
-* ``epi0`` production epilogue re-instantiated in the experimental kernel (must time like production),
+* ``epi0`` the round-1 epilogue (lane == row, row-strided 16-byte stores),
 * ``epi1`` staged epilogue (padded smem transpose → full 128-byte lines),
 * ``epi2`` eight epilogue warps,
 * ``epi3`` TMA-store epilogue (swizzled staging, double-buffered ``cp.async.bulk.tensor`` stores; needs N % 8 == 0),
@@ -27,12 +28,10 @@ sys.path.insert(0, ROOT)
 from pytorch_ps_mpi_b200.ops.linear import bcast_linear   # noqa: E402
 
 TWO_CTA = 2
-VARIANTS = [("prod", TWO_CTA)]
-for epi in (0, 1, 2, 3):
+VARIANTS = [("prod", TWO_CTA)]            # epilogue selector 0 = the production choice (TMA store if N % 8 == 0, else staged)
+for epi, sel in ((0, 4), (1, 1), (2, 2), (3, 3)):   # kernel template EPI → selector bits of `variant`
     for dbg, tag in ((0, ""), (1, ".nostore"), (2, ".nomma")):
-        if epi == 0 and dbg == 0:
-            continue                      # epi0/dbg0 routes to the production kernel by construction
-        VARIANTS.append((f"epi{epi}{tag}", TWO_CTA | epi << 4 | dbg << 8))
+        VARIANTS.append((f"epi{epi}{tag}", TWO_CTA | sel << 4 | dbg << 8))
 
 SHAPES = [("bert.ffn_in", 16384, 3072, 768), ("bert.qkv", 16384, 2304, 768), ("bert.ffn_out", 16384, 768, 3072),
           ("mlp.fc1", 8192, 4096, 784), ("stem", 256 * 112 * 112 // 8, 64, 176), ("square4096", 4096, 4096, 4096),

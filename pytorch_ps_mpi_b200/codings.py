@@ -277,7 +277,10 @@ class TopK(Coding):
         g = grad.detach()
         flat = g.reshape(-1)
         if self.error_feedback:
-            key = name if name is not None else id(grad)
+            if name is None:
+                # id(grad) of a temporary is recycled across parameters and steps: it would mix residuals
+                raise ValueError("TopK(error_feedback=True).encode needs name= (the parameter the residual belongs to)")
+            key = name
             res = self._residual.get(key)
             work = flat.float() if res is None else flat.float() + res
         else:

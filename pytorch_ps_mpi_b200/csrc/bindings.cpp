@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 
@@ -65,7 +66,8 @@ struct UpdatePlan {
 
   void launch(uint64_t epoch, const std::vector<std::vector<double>>& groups, uint32_t contrib_mask, double inv_count,
               int wait_grads, int signal_mode, uint32_t ack_mask, uint64_t version, uint64_t select_out,
-              int average_dynamic, uint64_t active_ptr, double timeout_s, uint32_t wait_mask, uint64_t stream) {
+              int average_dynamic, uint64_t active_ptr, double timeout_s, uint32_t wait_mask, uint64_t stream,
+              int tile_begin, int tile_end, uint64_t wait_value) {
     if (groups.size() > PSB_MAX_GROUPS) throw std::runtime_error("too many param groups for one launch");
     for (size_t i = 0; i < groups.size(); ++i) {
       const auto& g = groups[i];
@@ -76,6 +78,11 @@ struct UpdatePlan {
       h.nesterov = (int)g[8], h.amsgrad = (int)g[9], h.first_step = (int)g[10], h.pad = 0;
     }
     a.epoch = epoch;
+    // one chunk of the pipeline (tile_end < 0: the whole arena, waiting for the plain epoch value)
+    a.tile_begin = tile_end < 0 ? 0 : tile_begin;
+    a.tile_end = tile_end < 0 ? a.ntiles : tile_end;
+    if (a.tile_begin < 0 || a.tile_end > a.ntiles || a.tile_begin >= a.tile_end) throw std::runtime_error("bad tile range");
+    a.wait_value = tile_end < 0 ? epoch : wait_value;
     a.contrib_mask = contrib_mask;
     a.wait_mask = wait_mask;
     a.inv_count = (float)inv_count;
@@ -87,7 +94,7 @@ struct UpdatePlan {
     a.average_dynamic = average_dynamic;
     a.active = reinterpret_cast<const uint8_t*>(active_ptr);
     a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
-    psb_launch_update(pick_stream(stream), kind, wire, opt, a, grid);
+    psb_launch_update(pick_stream(stream), kind, wire, opt, a, std::min(grid, a.tile_end - a.tile_begin));
     check_launch("psb_update_kernel launch");
   }
 };
@@ -235,7 +242,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("launch", &UpdatePlan::launch, py::arg("epoch"), py::arg("groups"), py::arg("contrib_mask"),
            py::arg("inv_count"), py::arg("wait_grads"), py::arg("signal_mode"), py::arg("ack_mask") = 0,
            py::arg("version") = 0, py::arg("select_out") = 0, py::arg("average_dynamic") = 0, py::arg("active_ptr") = 0,
-           py::arg("timeout_s") = 30.0, py::arg("wait_mask") = 0xffffffffu, py::arg("stream") = 0);
+           py::arg("timeout_s") = 30.0, py::arg("wait_mask") = 0xffffffffu, py::arg("stream") = 0,
+           py::arg("tile_begin") = 0, py::arg("tile_end") = -1, py::arg("wait_value") = 0);
 
   m.def("update_max_grid", &psb_update_max_grid);
   m.def("launch_count", []() { return (uint64_t)psb_launch_count(); }, "kernels of ours launched by this process so far");

@@ -52,11 +52,13 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   const int64_t M = x.size(0);
   auto y = at::empty({M, N}, x.options());
   if (M == 0) return y;
-  // cta_group::2 (two SMs per 256x256 tile) whenever there are at least 256 rows; `variant` forces it (tests)
-  // bits 4-7 / 8-11 of `variant` select an experimental epilogue / diagnostic mode (bcast_gemm_exp.cu; 2-CTA only)
-  const int base = variant & 15, epi = (variant >> 4) & 15, dbg = (variant >> 8) & 15;
-  TORCH_CHECK(base <= 2 && epi <= 3 && dbg <= 2, "unknown bcast_gemm variant ", variant);
-  TORCH_CHECK((epi | dbg) == 0 || base == 2, "experimental bcast_gemm variants need the 2-CTA kernel (variant & 15 == 2)");
+  // cta_group::2 (two SMs per 256x256 tile) whenever there are at least 256 rows; `variant & 15` forces 1-CTA (1) / 2-CTA (2).
+  // bits 4-7: epilogue of the 2-CTA kernel — 0 auto (TMA store when N % 8 == 0, else staged), 1 staged, 2 eight warps,
+  // 3 TMA store, 4 the round-1 row-strided stores;  bits 8-11: diagnostic mode (bench/gemm_variants.py)
+  const int base = variant & 15, epi_sel = (variant >> 4) & 15, dbg = (variant >> 8) & 15;
+  TORCH_CHECK(base <= 2 && epi_sel <= 4 && dbg <= 2, "unknown bcast_gemm variant ", variant);
+  TORCH_CHECK((epi_sel | dbg) == 0 || base == 2, "epilogue / diagnostic variants need the 2-CTA kernel (variant & 15 == 2)");
+  const int epi = epi_sel == 0 ? -1 : (epi_sel == 4 ? 0 : epi_sel);
   const bool two_cta = base == 2 || (base == 0 && M >= 256);
   CUtensorMap ma = make_map(reinterpret_cast<uint64_t>(x.data_ptr()), M, K, K, 128);
   const int bnt2 = N <= 64 ? 64 : (N <= 128 ? 128 : 256);          // must match psb_launch_bcast_gemm's choice
@@ -79,17 +81,19 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   a.two_cta = two_cta ? 1 : 0;
   a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  if (epi | dbg) {
+  const cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+  if (two_cta) {
     CUtensorMap mc;
     const void* mcp = nullptr;
-    if (epi == 3) {
-      TORCH_CHECK(N % 8 == 0, "the TMA-store epilogue needs N % 8 == 0 (16-byte row pitch)");
+    TORCH_CHECK(epi != 3 || N % 8 == 0, "the TMA-store epilogue needs N % 8 == 0 (16-byte row pitch)");
+    if (N % 8 == 0 && (epi == 3 || epi < 0)) {
       mc = make_map(reinterpret_cast<uint64_t>(y.data_ptr()), M, N, N, 32);      // box: 64 columns x 32 rows, 128B swizzle
       mcp = &mc;
     }
-    psb_launch_bcast_gemm_exp(c10::cuda::getCurrentCUDAStream().stream(), a, sms, epi, dbg, mcp);
+    psb_launch_bcast_gemm2(stream, a, sms, epi, dbg, mcp);
+  } else {
+    psb_launch_bcast_gemm(stream, a, sms);
   }
-  else psb_launch_bcast_gemm(c10::cuda::getCurrentCUDAStream().stream(), a, sms);
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_bcast_gemm_kernel launch: ", cudaGetErrorString(e));
   return y;
@@ -274,9 +278,10 @@ std::vector<at::Tensor> bn_forward_presummed(const at::Tensor& x, c10::optional<
   return {y, scratch.narrow(0, 0, C), scratch.narrow(0, C, C)};
 }
 
-// EXPERIMENTAL fused stem: x [N,3,H,W] bf16 channels-last, w2d [64,176] bf16 (ops/stem.py layout)
+// fused stem: x [N,3,H,W] bf16 channels-last, w2d [64,176] bf16 (ops/stem.py layout)
 // → (y [N,64,OH,OW] bf16 channels-last, sums [128] fp32 = Σy | Σy² per channel, or an empty tensor)
-std::vector<at::Tensor> stem_fwd(const at::Tensor& x, const at::Tensor& w2d, bool want_sums) {
+std::vector<at::Tensor> stem_fwd(const at::Tensor& x, const at::Tensor& w2d, bool want_sums, uint64_t flag_ptr, uint64_t epoch,
+                                 double timeout_s) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.size(1) == 3, "x must be [N,3,H,W] bf16");
   TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "x must be channels_last contiguous");
   TORCH_CHECK(w2d.is_cuda() && w2d.scalar_type() == at::kBFloat16 && w2d.dim() == 2 && w2d.size(0) == 64 && w2d.size(1) == 176 &&
@@ -293,13 +298,13 @@ std::vector<at::Tensor> stem_fwd(const at::Tensor& x, const at::Tensor& w2d, boo
   CUtensorMap my = make_map(reinterpret_cast<uint64_t>(y.data_ptr()), (int64_t)N * OH * OW, 64, 64, OW);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   psb_stem_fwd_launch(c10::cuda::getCurrentCUDAStream().stream(), &mw, &my, x.data_ptr(), want_sums ? sums.data_ptr<float>() : nullptr,
-                      N, H, W, sms);
+                      N, H, W, sms, reinterpret_cast<const uint64_t*>(flag_ptr), epoch, (unsigned long long)(timeout_s * 1e9));
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_stem_fwd_kernel launch: ", cudaGetErrorString(e));
   return {y.permute({0, 3, 1, 2}), sums};
 }
 
-// EXPERIMENTAL implicit weight gradient of the stem: x [N,3,H,W], gy [N,64,OH,OW] (both bf16 channels-last)
+// implicit weight gradient of the stem: x [N,3,H,W], gy [N,64,OH,OW] (both bf16 channels-last)
 // → per-CTA partials [grid,176,64] fp32 of dW2d^T (sum over dim 0 on the caller's side)
 at::Tensor stem_wgrad(const at::Tensor& x, const at::Tensor& gy) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.size(1) == 3, "x must be [N,3,H,W] bf16");
@@ -357,10 +362,11 @@ void bind_gemm(py::module_& m) {
   m.def("maxpool_forward", &maxpool_forward, "channels-last bf16 3x3/s2/p1 max pool → (y, argpos)");
   m.def("maxpool_backward", &maxpool_backward, "gather-style backward of maxpool_forward");
   m.def("bn_forward", &bn_forward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) forward");
-  m.def("bn_forward_presummed", &bn_forward_presummed, "EXPERIMENTAL: BN forward with sums produced by the fused stem kernel");
-  m.def("stem_fwd", &stem_fwd, py::arg("x"), py::arg("w2d"), py::arg("want_sums") = true,
-        "EXPERIMENTAL: fused implicit-GEMM ResNet stem (+ BN statistics) on tcgen05");
-  m.def("stem_wgrad", &stem_wgrad, "EXPERIMENTAL: implicit weight gradient of the stem → per-CTA fp32 partials [grid,176,64]");
+  m.def("bn_forward_presummed", &bn_forward_presummed, "BN forward with sums produced by the fused stem kernel");
+  m.def("stem_fwd", &stem_fwd, py::arg("x"), py::arg("w2d"), py::arg("want_sums") = true, py::arg("flag_ptr") = 0,
+        py::arg("epoch") = 0, py::arg("timeout_s") = 30.0,
+        "fused implicit-GEMM ResNet stem (+ BN statistics) on tcgen05; flag_ptr/epoch: PARAMS_READY gate of the weight load");
+  m.def("stem_wgrad", &stem_wgrad, "implicit weight gradient of the stem → per-CTA fp32 partials [grid,176,64]");
   m.def("bnpool_forward", &bnpool_forward, "EXPERIMENTAL: BatchNorm + ReLU + 3x3/s2 max-pool forward in one pass");
   m.def("bnpool_backward", &bnpool_backward, "EXPERIMENTAL: backward of bnpool_forward (no materialised pool gradient)");
   m.def("bn_backward", &bn_backward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");

@@ -12,6 +12,7 @@
 // and this GEMM *is* the req.Wait() for the whole forward pass that follows it on the stream.
 //
 // Structure (one CTA per SM, persistent over output tiles):
+// (M >= 256 runs on the cta_group::2 kernel in bcast_gemm2.cu; this 1-CTA kernel serves small M.)
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d → smem ring (4 stages x {A 128x64, B 256x64} = 192 KB)
 //   warp 1      MMA issuer     one elected lane: tcgen05.mma.cta_group::1.kind::f16, UMMA 128x256x16,
 //                              tcgen05.commit → frees smem slots / publishes the accumulator
@@ -165,180 +166,18 @@ psb_bcast_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 }
 
 
-// ==========================================================================================
-// 2-CTA variant: a thread-block cluster of two CTAs (one TPC) works on ONE 256x256 output tile.
-//   * each CTA TMA-loads its own 128 rows of A and its own 128-row HALF of the B tile, and signals the
-//     LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2, peer-masked mbarrier address);
-//   * only the leader issues tcgen05.mma.cta_group::2 (UMMA 256x256x16): the tensor cores of both SMs
-//     read A from their own smem and the two B halves from both — each B byte is fetched from L2 once
-//     per PAIR, halving operand traffic (128x128 tiles were L2-bound, see BENCH_NOTES §4);
-//   * tcgen05.commit ... .multicast::cluster releases the smem slot / publishes the accumulator in BOTH
-//     CTAs; each CTA's epilogue drains its own 128 TMEM lanes and arrives on the leader's tmem_empty.
-// ==========================================================================================
-// BNT (the N extent of the pair tile) is a template parameter: 256 for big layers, 128 / 64 for narrow
-// outputs (the ResNet stem GEMM has N = 64: a 256-wide tile would waste 3/4 of the MMA work).
-template <int BNT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-psb_bcast_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       const __grid_constant__ GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using C = Cfg2<BNT>;
-  constexpr int STAGES2 = C::STAGES, STAGE2_BYTES = C::STAGE_BYTES, A2_BYTES = C::A_BYTES, TMEM_COLS2 = C::TMEM_COLS;
-  constexpr int BN2 = BNT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
-  uint64_t* full = bars;                        // [STAGES2]  (only the leader's are waited on)
-  uint64_t* empty = bars + STAGES2;             // [STAGES2]  (each CTA's own; the commit multicasts to both)
-  uint64_t* tmem_full = bars + 2 * STAGES2;     // [ACC_STAGES] each CTA's own
-  uint64_t* tmem_empty = tmem_full + ACC_STAGES;   // [ACC_STAGES] the leader's collects 8 arrivals (4 warps x 2 CTAs)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta = cluster_ctarank();
-  const bool leader = cta == 0;
-  const int ncl = gridDim.x / 2, cl = blockIdx.x / 2;
-  const int tiles_m = (p.M + 255) / 256, tiles_n = (p.N + BN2 - 1) / BN2;
-  const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (p.K + BK - 1) / BK;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
-    for (int i = 0; i < STAGES2; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    for (int i = 0; i < ACC_STAGES; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  cluster_sync_all();   // both CTAs' barriers exist before anybody signals across the pair
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "r"((uint32_t)TMEM_COLS2)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  cluster_sync_all();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (elect_one()) {
-      if (p.ready_flag != nullptr) {
-        psb::spin_until_ge(p.ready_flag, p.ready_epoch, p.err_slot, p.timeout_ns);
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
-      uint32_t stage = 0, phase = 0;
-      for (int tile = cl; tile < num_tiles; tile += ncl) {
-        const int m0 = (tile / tiles_n) * 256 + (int)cta * BM;
-        const int n0 = (tile % tiles_n) * BN2 + (int)cta * (BN2 / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE2_BYTES;
-          const uint32_t lead_full = smem_u32(&full[stage]) & PEER_MASK;
-          if (leader) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);   // both CTAs' bytes land on the leader's barrier
-          tma_load_2d_2sm(&tmap_a, lead_full, sa, kb * BK, m0);
-          tma_load_2d_2sm(&tmap_b, lead_full, sa + A2_BYTES, kb * BK, n0);
-          if (++stage == STAGES2) stage = 0, phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (leader) {
-      const uint32_t idesc = make_idesc2<BNT>();
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = cl; tile < num_tiles; tile += ncl) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + acc * BN2;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (elect_one()) {
-            const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
-            const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + A2_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            umma_commit_2sm(&empty[stage]);
-            if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc]);
-          }
-          __syncwarp();
-          if (++stage == STAGES2) stage = 0, phase ^= 1;
-        }
-        if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2..5 of BOTH CTAs) =====================
-    const int quarter = warp & 3;
-    uint32_t acc = 0, acc_phase = 0;
-    for (int tile = cl; tile < num_tiles; tile += ncl) {
-      const int m0 = (tile / tiles_n) * 256 + (int)cta * BM, n0 = (tile % tiles_n) * BN2;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = m0 + quarter * 32 + lane;
-      const bool vec_ok = (p.N % 8) == 0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN2; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2 + c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < p.M && n0 + c0 < p.N) {
-          __nv_bfloat16* orow = p.out + (size_t)row * p.N + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int col = n0 + c0 + j;
-            float v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              v[t] = __uint_as_float(r[j + t]);
-              if (p.bias != nullptr && col + t < p.N) v[t] += p.bias[col + t];
-              if (p.relu) v[t] = fmaxf(v[t], 0.f);
-            }
-            if (vec_ok && col + 8 <= p.N) {
-              *reinterpret_cast<uint4*>(orow + j) = make_uint4(psb::pack_bf16x2(v[0], v[1]), psb::pack_bf16x2(v[2], v[3]),
-                                                               psb::pack_bf16x2(v[4], v[5]), psb::pack_bf16x2(v[6], v[7]));
-            } else {
-#pragma unroll
-              for (int t = 0; t < 8; ++t)
-                if (col + t < p.N) orow[j + t] = __float2bfloat16_rn(v[t]);
-            }
-          }
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & PEER_MASK);   // the leader's barrier
-      if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
-    }
-  }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  cluster_sync_all();   // the peer may still be reading our smem / TMEM through the pair MMA
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS2)
-                 : "memory");
-  }
-}
-
 }  // namespace
 
 int psb_bcast_gemm_smem_bytes() { return SMEM_BYTES; }
 
 void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms) {
+  if (a.two_cta) {   // M >= 256: the cta_group::2 kernel with the TMA-store (or staged) epilogue, bcast_gemm2.cu
+    psb_launch_bcast_gemm2(s, a, num_sms, -1, 0, a.tmap_out);
+    return;
+  }
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(psb_bcast_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64>::SMEM_BYTES);
-    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128>::SMEM_BYTES);
-    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256>::SMEM_BYTES);
     configured = true;
   }
   GemmParams p{};
@@ -350,18 +189,6 @@ void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms) 
   p.M = a.M, p.N = a.N, p.K = a.K, p.relu = a.relu;
   p.timeout_ns = a.timeout_ns;
   psb_count_launch(1);
-  if (a.two_cta) {
-    const int bnt = a.N <= 64 ? 64 : (a.N <= 128 ? 128 : 256);
-    const int tiles = ((a.M + 255) / 256) * ((a.N + bnt - 1) / bnt);
-    int clusters = num_sms / 2;
-    if (tiles < clusters) clusters = tiles;
-    const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(a.tmap_a);
-    const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(a.tmap_b);
-    if (bnt == 64) psb_bcast_gemm2_kernel<64><<<2 * clusters, THREADS, Cfg2<64>::SMEM_BYTES, s>>>(ta, tb, p);
-    else if (bnt == 128) psb_bcast_gemm2_kernel<128><<<2 * clusters, THREADS, Cfg2<128>::SMEM_BYTES, s>>>(ta, tb, p);
-    else psb_bcast_gemm2_kernel<256><<<2 * clusters, THREADS, Cfg2<256>::SMEM_BYTES, s>>>(ta, tb, p);
-    return;
-  }
   const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   psb_bcast_gemm_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(*reinterpret_cast<const CUtensorMap*>(a.tmap_a),

@@ -1,23 +1,28 @@
-// EXPERIMENTAL variants of the cta_group::2 GEMM (psb_bcast_gemm2_kernel in bcast_gemm.cu).  Nothing here is on a
-// default path: the kernels below are only reachable through `bcast_linear(..., variant=2 | EPI<<4 | DBG<<8)` and
-// exist to find out, on hardware, why the K <= 1024 shapes run at ~47 % of the measured tensor peak while 8192^3
-// runs at 93 % (BENCH_NOTES §5).  The operand traffic per MMA does not depend on K, so the short-K loss must be a
-// per-TILE cost: the epilogue (TMEM drain + bf16 pack + global stores), or a hand-off bubble around it.
+// psb_bcast_gemm2_kernel — the cta_group::2 tcgen05 GEMM (the production kernel behind bcast_linear / BcastLinear for
+// M >= 256): Y[M,N] = act(X[M,K] · W[N,K]^T + bias), bf16 in, fp32 accumulate in TMEM, bf16 out.
 //
-//   EPI = 0  the production epilogue: lane == row, 16-byte stores at a row stride (partial 32 B sectors)
-//   EPI = 1  staged epilogue: each warp transposes 32 rows x 64 columns through padded shared memory and writes
-//            full 128-byte lines (4 rows per store instruction)
-//   EPI = 2  eight epilogue warps instead of four (two per TMEM lane quarter, half of the columns each)
-//   EPI = 3  TMA-store epilogue: each warp writes 32 rows x 64 columns into a 128B-swizzled staging tile (two per
-//            warp, so a store is in flight while the next chunk is packed) and one lane issues
-//            cp.async.bulk.tensor.2d.global.shared::cta — no LSU wavefronts at all, bounds clipped by the TMA unit
+// A thread-block cluster of two CTAs (one TPC) works on ONE 256 x BNT output tile:
+//   * each CTA TMA-loads its own 128 rows of A and its own HALF of the B tile and signals the LEADER's full barrier
+//     (cp.async.bulk.tensor ... .cta_group::2, peer-masked mbarrier address);
+//   * only the leader issues tcgen05.mma.cta_group::2 (UMMA 256 x BNT x 16): each B byte is fetched from L2 once per PAIR;
+//   * tcgen05.commit ... .multicast::cluster releases the smem slot / publishes the accumulator in BOTH CTAs; each CTA's
+//     epilogue warps drain their own 128 TMEM lanes and arrive on the leader's tmem_empty.
+// The weight tensor map points INTO the symmetric parameter arena and the TMA producer acquires the PARAMS_READY epoch
+// (ld.acquire.sys + fence.proxy.async) before its first weight load: the GEMM is the req.Wait() of the PS broadcast
+// (/root/reference/mpi_comms.py:120-133).
 //
-//   DBG = 0  normal
-//   DBG = 1  the epilogue drains TMEM and packs but never stores      → time without the output traffic
-//   DBG = 2  the MMA warp commits without issuing tcgen05.mma          → time of TMA + epilogue alone
-//
-// `bench/gemm_variants.py` runs the matrix of variants, checks the numerics of the DBG = 0 ones against torch and
-// prints the timing table that decides which epilogue becomes the default.
+// Epilogues (template EPI).  Round-1's epilogue (EPI 0: lane == row, 16-byte stores at a row stride → 32 LSU wavefronts
+// per store instruction) cost a constant ~3.4 us per 256x256 tile and held the K <= 1024 shapes at 0.65x cuBLAS.  The
+// round-2 hardware sweep (bench/gemm_variants.py → profiles/gemm_variants_r2.jsonl) decided the defaults:
+//   EPI = 3  (default when N % 8 == 0)  TMA-store epilogue: each warp packs 32 rows x 64 columns into a 128B-swizzled staging
+//            tile (two per warp, so a store is in flight while the next chunk is packed) and one lane issues
+//            cp.async.bulk.tensor.2d.global.shared::cta — no LSU wavefronts at all, bounds clipped by the TMA unit.
+//            16384x3072x768: 98.2 → 57.2 us (cuBLAS 62.4);  16384x2304x768: 74.5 → 45.9 us (cuBLAS 51.2).
+//   EPI = 1  (default otherwise)  staged epilogue: each warp transposes 32 rows x 64 columns through padded shared memory
+//            and writes full 128-byte lines (4 rows per store instruction); handles any N.
+//   EPI = 2  eight epilogue warps (two per TMEM lane quarter) — measured no better than EPI 0; kept for the sweep only.
+//   EPI = 0  the round-1 epilogue — kept for the sweep only.
+// Diagnostic modes (template DBG, bench only): 1 = drain + pack but never store, 2 = commit without issuing tcgen05.mma.
 #include "gemm_common.cuh"
 
 namespace {
@@ -60,7 +65,7 @@ __device__ __forceinline__ void finish32(const uint32_t* r, const GemmParams& p,
 
 template <int BNT, int EPI, int DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((CfgX<BNT, EPI>::NTHREADS), 1)
-psb_bcast_gemm2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+psb_bcast_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -292,10 +297,10 @@ void launch_x(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, cons
   using X = CfgX<BNT, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(psb_bcast_gemm2x_kernel<BNT, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM_BYTES);
+    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<BNT, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM_BYTES);
     configured = true;
   }
-  psb_bcast_gemm2x_kernel<BNT, EPI, DBG><<<2 * clusters, X::NTHREADS, X::SMEM_BYTES, s>>>(ta, tb, tc, p);
+  psb_bcast_gemm2_kernel<BNT, EPI, DBG><<<2 * clusters, X::NTHREADS, X::SMEM_BYTES, s>>>(ta, tb, tc, p);
 }
 
 template <int BNT, int EPI>
@@ -317,9 +322,11 @@ void launch_e(cudaStream_t s, int epi, int dbg, const CUtensorMap& ta, const CUt
 
 }  // namespace
 
-// `a.two_cta` must be set (the tensor maps are built for the 2-CTA box shapes); epi / dbg as documented on top.
-// `tmap_out` (EPI 3): CUtensorMap of the [M, N] bf16 output, box 64 columns x 32 rows, SWIZZLE_128B; else ignored.
-void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out) {
+// `a.two_cta` must be set (the tensor maps are built for the 2-CTA box shapes).
+// epi: -1 = auto (TMA store when N % 8 == 0 and `tmap_out` is given, else staged), 0..3 = force (see top);  dbg: 0..2.
+// `tmap_out` (EPI 3): CUtensorMap of the [M, N] bf16 output, box 64 columns x 32 rows, SWIZZLE_128B.
+void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out) {
+  if (epi < 0) epi = (tmap_out != nullptr && a.N % 8 == 0) ? 3 : 1;
   GemmParams p{};
   p.bias = a.bias;
   p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a.tmap_c));

@@ -1,4 +1,4 @@
-// Shared building blocks of the tcgen05 / TMEM / TMA GEMM kernels (bcast_gemm.cu, bcast_gemm_exp.cu):
+// Shared building blocks of the tcgen05 / TMEM / TMA GEMM kernels (bcast_gemm.cu, bcast_gemm2.cu):
 // mbarrier / TMA / UMMA / TMEM PTX wrappers, descriptors, tile constants.  Everything lives in an unnamed
 // namespace so each translation unit gets its own internal-linkage copy.
 #pragma once

@@ -60,7 +60,11 @@ struct UpdateArgs {
   uint32_t wait_mask;                  // ranks whose GRAD_READY flag is awaited (the launching rank's own gradient is
                                        // ordered by the stream, so it is normally excluded)
   float inv_count;                     // 1 or 1/#contributors (average=True)
-  uint64_t epoch;
+  uint64_t epoch;                      // value published to SIG_PARAMS_READY / SIG_CONSUMED when the LAST chunk is done
+  uint64_t wait_value;                 // SIG_GRAD_READY progress value awaited: (epoch-1)*nchunks + chunk + 1 (the
+                                       // reference's per-parameter req.Wait(), ps.py:159-162, at chunk granularity)
+  int32_t tile_begin, tile_end;        // this launch covers arena tiles [tile_begin, tile_end) — one chunk of the
+                                       // pipeline (or the whole arena)
   int32_t wait_grads;                  // spin on SIG_GRAD_READY of every contributor first
   int32_t signal_mode;                 // 0 none | 1 SIG_PARAMS_READY → all | 2 SIG_CONSUMED[rank] → all
   uint32_t ack_mask;                   // async: ranks to acknowledge (SIG_ACK) when done
@@ -94,11 +98,14 @@ struct BcastGemmArgs {
   int32_t M, N, K;
   int32_t relu;
   int32_t two_cta;      // 1 → cta_group::2 kernel (256x256 tiles per CTA pair; B box = 128 rows)
+  const void* tmap_out; // 2-CTA only: CUtensorMap* of the [M,N] output (box 64 x 32, 128B swizzle) for the TMA-store
+                        // epilogue; nullptr (or N % 8 != 0) → staged full-line stores
   unsigned long long timeout_ns;
 };
 void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms);
-// bcast_gemm_exp.cu — experimental epilogue / diagnostic variants of the 2-CTA kernel (never a default path)
-void psb_launch_bcast_gemm_exp(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out);
+// bcast_gemm2.cu — the cta_group::2 kernel; epi -1 = auto (TMA-store / staged epilogue), 0..3 and dbg 1..2 = the
+// epilogue sweep / diagnostic builds of bench/gemm_variants.py
+void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out);
 
 // bn_kernels.cu — fused channels-last bf16 BatchNorm (+residual, +ReLU), forward and backward
 void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y, float* sums,
@@ -126,10 +133,10 @@ void psb_normalize_pad8_launch(cudaStream_t s, const void* x, void* y, const flo
 void psb_im2col_stem_launch(cudaStream_t s, const void* x, void* a, int N, int H, int W);
 void psb_normalize_nhwc3_launch(cudaStream_t s, const void* x, void* y, const float* mean, const float* inv_std, int N, long long HW);
 
-// stem_kernels.cu — EXPERIMENTAL fused implicit-GEMM ResNet stem (7x7/s2, 3 → 64) with BN statistics in the epilogue
+// stem_kernels.cu — fused implicit-GEMM ResNet stem (7x7/s2, 3 → 64) with BN statistics in the epilogue
 int psb_stem_fwd_smem_bytes();
 void psb_stem_fwd_launch(cudaStream_t s, const void* tmap_w, const void* tmap_y, const void* x, float* sums, int N, int H, int W,
-                         int num_sms);
+                         int num_sms, const uint64_t* ready_flag, uint64_t ready_epoch, unsigned long long timeout_ns);
 
 int psb_stem_wgrad_grid(int N, int H, int num_sms);
 void psb_stem_wgrad_launch(cudaStream_t s, const void* tmap_g, const void* x, float* partial, int N, int H, int W, int num_sms);

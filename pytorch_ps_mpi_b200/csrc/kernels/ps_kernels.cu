@@ -392,10 +392,18 @@ __device__ __forceinline__ void load_state(const UpdateArgs& a, const TileInfo& 
   }
 }
 
-// U = tiles a thread keeps in flight.  Few ranks → few peer loads per tile → take more tiles at once so
-// enough bytes are outstanding to cover the ~2 µs NVLink round trip (B300_MICROARCH: peer LDG ≈ 1.8-2k cycles).
-template <int KIND, int WIRE, int OPT, int U>
-__global__ void __launch_bounds__(PSB_THREADS, U == 1 ? 3 : 2) psb_update_kernel(const __grid_constant__ UpdateArgs a) {
+// One launch covers arena tiles [tile_begin, tile_end): the whole model, or ONE CHUNK of the per-bucket pipeline — the
+// device analogue of the reference posting one non-blocking collective per parameter and consuming each as it completes
+// (/root/reference/ps.py:140-148,159-162).  The engine launches chunk k's update while backward is still producing
+// chunk k+1; GRAD_READY carries a monotone progress value ((epoch-1)*nchunks + chunk + 1), so one flag per rank serves
+// every chunk.
+//
+// NVLS_U = tiles a thread keeps in flight on the multimem.ld_reduce path: one 16-byte switch reduction per tile is far too
+// little to cover the NVLS round trip, so four are issued back to back before the first is consumed.
+constexpr int NVLS_U = 4;
+
+template <int KIND, int WIRE, int OPT>
+__global__ void __launch_bounds__(PSB_THREADS, 3) psb_update_kernel(const __grid_constant__ UpdateArgs a) {
   __shared__ float s_acc[KIND == KIND_TOPK ? PSB_TILE : 1];
   __shared__ int s_flag;
   const int tid = threadIdx.x;
@@ -410,44 +418,71 @@ __global__ void __launch_bounds__(PSB_THREADS, U == 1 ? 3 : 2) psb_update_kernel
     if (a.average_dynamic) inv_count = 1.f / (float)cnt;
   }
 
-  // ---- 1. the req.Wait() of the reference: every contributor's epoch flag ----
+  // ---- 1. the req.Wait() of the reference: every contributor's progress flag ----
   if (a.wait_grads) {
     bool ok = true;
     if (tid < a.world && (contrib & a.wait_mask) >> tid & 1u)
-      ok = spin_until_ge(a.signal_local + SIG_GRAD_READY + tid, a.epoch, err_slot, a.timeout_ns);
+      ok = spin_until_ge(a.signal_local + SIG_GRAD_READY + tid, a.wait_value, err_slot, a.timeout_ns);
     if (!__syncthreads_and(ok)) return;
   }
 
   if constexpr (KIND == KIND_TOPK) {
-    // ---- block-wise top-k: scatter-add every rank's (index, value) entries into a shared-memory tile ----
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    // ---- block-wise top-k: every rank's (index, value) entries are fetched with 16-byte peer loads, ALL ranks in
+    // flight at once (2 vectors per thread per round), then scatter-added into a shared-memory tile rank by rank
+    // (rank order = summation order, so the sum stays bit-reproducible) ----
+    constexpr int ENT = (WIRE == WIRE_BF16) ? 4 : 2;     // entries per 16-byte vector
+    constexpr int VPT = 2;                               // vectors per thread per round
+    const int nv = a.bytes_per_tile >> 4;                // vectors per rank per tile
+    const int total = a.world * nv;
+    for (int tile = a.tile_begin + blockIdx.x; tile < a.tile_end; tile += gridDim.x) {
       const TileInfo ti = a.tiles[tile];
       if (a.active != nullptr && a.active[ti.param] == 0) continue;
       const size_t e0 = (size_t)tile * PSB_TILE + tid * PSB_EPT;
       const size_t tile_off = (size_t)tile * a.bytes_per_tile;
       float w[PSB_EPT], m[PSB_EPT], v[PSB_EPT], vm[PSB_EPT];
-      load_state<OPT>(a, ti, e0, w, m, v, vm);
+      load_state<OPT>(a, ti, e0, w, m, v, vm);           // local; flies while the peer loads do
       for (int j = tid; j < PSB_TILE; j += PSB_THREADS) s_acc[j] = 0.f;
       __syncthreads();
-      for (int r = 0; r < a.world; ++r) {
-        if (!(contrib >> r & 1u)) continue;
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(a.wire[r]) + tile_off;
-        for (int p = tid; p < a.cap; p += PSB_THREADS) {
-          uint32_t idx;
-          float val;
-          if constexpr (WIRE == WIRE_BF16) {
-            uint32_t wd;
-            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(wd) : "l"(base + 4 * (size_t)p) : "memory");
-            idx = wd >> 16;
-            val = __uint_as_float(wd << 16);
-          } else {
-            uint2 wd = ld_sys_v2(base + 8 * (size_t)p);
-            idx = wd.x;
-            val = __uint_as_float(wd.y);
+      for (int base = 0; base < total; base += VPT * PSB_THREADS) {
+        uint4 q[VPT];
+        int qr[VPT], qj[VPT];
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+          const int vid = base + k * PSB_THREADS + tid;
+          qr[k] = -1;
+          qj[k] = 0;
+          if (vid < total) {
+            const int r = vid / nv;
+            if (contrib >> r & 1u) {
+              qr[k] = r;
+              qj[k] = vid - r * nv;
+              q[k] = ld_sys_v4(reinterpret_cast<const uint8_t*>(a.wire[r]) + tile_off + 16 * (size_t)qj[k]);
+            }
           }
-          if (idx < PSB_TILE) s_acc[idx] += val;   // indices are unique within one rank's tile
         }
-        __syncthreads();                            // rank order is the summation order
+        const int r_lo = base / nv, r_hi = (min(total, base + VPT * PSB_THREADS) - 1) / nv;
+        for (int r = r_lo; r <= r_hi; ++r) {
+#pragma unroll
+          for (int k = 0; k < VPT; ++k) {
+            if (qr[k] != r) continue;
+            const uint32_t wd[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+            for (int e = 0; e < ENT; ++e) {
+              if (qj[k] * ENT + e >= a.cap) break;       // alignment padding behind the last entry
+              uint32_t idx;
+              float val;
+              if constexpr (WIRE == WIRE_BF16) {
+                idx = wd[e] >> 16;
+                val = __uint_as_float(wd[e] << 16);
+              } else {
+                idx = wd[2 * e];
+                val = __uint_as_float(wd[2 * e + 1]);
+              }
+              if (idx < PSB_TILE) s_acc[idx] += val;     // indices are unique within one rank's tile
+            }
+          }
+          __syncthreads();
+        }
       }
       float acc[PSB_EPT];
 #pragma unroll
@@ -456,94 +491,86 @@ __global__ void __launch_bounds__(PSB_THREADS, U == 1 ? 3 : 2) psb_update_kernel
       apply_and_publish<OPT>(a, ti, e0, inv_count, acc, w, m, v, vm);
     }
   } else {
-    // ---- dense / scaled wires: U tiles x up-to-CH ranks of 16-byte peer loads in flight per thread ----
-    constexpr int CH = 4;
-    const bool nvls = (KIND == KIND_DENSE && (WIRE == WIRE_F32 || WIRE == WIRE_BF16 || WIRE == WIRE_F16)) &&
-                      a.reduce == REDUCE_NVLS;
-    for (int tile0 = blockIdx.x; tile0 < a.ntiles; tile0 += U * gridDim.x) {
-      TileInfo ti[U];
-      bool live[U];
-      float acc[U][PSB_EPT], w[1][PSB_EPT], m[1][PSB_EPT], v[1][PSB_EPT], vm[1][PSB_EPT];
+    constexpr bool NVLS_OK = KIND == KIND_DENSE && (WIRE == WIRE_F32 || WIRE == WIRE_BF16 || WIRE == WIRE_F16);
+    if (NVLS_OK && a.reduce == REDUCE_NVLS) {
+      if constexpr (NVLS_OK) {
+        // ---- the switch adds all ranks (multimem.ld_reduce): server ingress is 1x the vector, not (N-1)x ----
+        for (int tile0 = a.tile_begin + blockIdx.x; tile0 < a.tile_end; tile0 += NVLS_U * gridDim.x) {
+          uint4 v0[NVLS_U], v1[NVLS_U];
+          TileInfo ti[NVLS_U];
+          bool live[NVLS_U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int tile = tile0 + u * gridDim.x;
-        live[u] = tile < a.ntiles;
-        if (live[u]) {
-          ti[u] = a.tiles[tile];
-          if (a.active != nullptr && a.active[ti[u].param] == 0) live[u] = false;
-        }
+          for (int u = 0; u < NVLS_U; ++u) {
+            const int tile = tile0 + u * gridDim.x;
+            live[u] = tile < a.tile_end;
+            if (live[u]) {
+              ti[u] = a.tiles[tile];
+              if (a.active != nullptr && a.active[ti[u].param] == 0) live[u] = false;
+            }
+            if (live[u]) {
+              const uint8_t* p = reinterpret_cast<const uint8_t*>(a.wire_mc) + (size_t)tile * a.bytes_per_tile +
+                                 (size_t)tid * PSB_EPT * wire_elem_bytes(WIRE);
+              if constexpr (WIRE == WIRE_F32) {
+                v0[u] = multimem_ld_reduce_f32x4(p);
+                v1[u] = multimem_ld_reduce_f32x4(p + 16);
+              } else if constexpr (WIRE == WIRE_BF16) {
+                v0[u] = multimem_ld_reduce_bf16x8(p);
+              } else {
+                v0[u] = multimem_ld_reduce_f16x8(p);
+              }
+            }
+          }
 #pragma unroll
-        for (int j = 0; j < PSB_EPT; ++j) acc[u][j] = 0.f;
-      }
-      // U == 1: local optimizer state first — independent of the gather, so it overlaps the NVLink latency.
-      // U > 1: the register budget goes to peer loads in flight instead; state is loaded after the sum.
-      if constexpr (U == 1) {
-        if (live[0]) load_state<OPT>(a, ti[0], (size_t)tile0 * PSB_TILE + tid * PSB_EPT, w[0], m[0], v[0], vm[0]);
-      }
-
-      if (nvls) {
-        if constexpr (KIND == KIND_DENSE && (WIRE == WIRE_F32 || WIRE == WIRE_BF16 || WIRE == WIRE_F16)) {
-          // the switch adds all ranks: server ingress is 1x the vector, not (N-1)x
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
+          for (int u = 0; u < NVLS_U; ++u) {
             if (!live[u]) continue;
-            const uint8_t* p = reinterpret_cast<const uint8_t*>(a.wire_mc) + (size_t)(tile0 + u * gridDim.x) * a.bytes_per_tile +
-                               (size_t)tid * PSB_EPT * wire_elem_bytes(WIRE);
-            if constexpr (WIRE == WIRE_F32) {
-              uint4 v0 = multimem_ld_reduce_f32x4(p), v1 = multimem_ld_reduce_f32x4(p + 16);
-              decode_dense<WIRE_F32>(v0, v1, acc[u]);
-            } else if constexpr (WIRE == WIRE_BF16) {
-              uint4 v0 = multimem_ld_reduce_bf16x8(p);
-              unpack_bf16x8(v0, acc[u]);
-            } else {
-              uint4 v0 = multimem_ld_reduce_f16x8(p);
-              unpack_f16x8(v0, acc[u]);
-            }
+            const size_t e0 = (size_t)(tile0 + u * gridDim.x) * PSB_TILE + tid * PSB_EPT;
+            float acc[PSB_EPT], w[PSB_EPT], m[PSB_EPT], v[PSB_EPT], vm[PSB_EPT];
+            load_state<OPT>(a, ti[u], e0, w, m, v, vm);
+            decode_dense<WIRE>(v0[u], v1[u], acc);
+            apply_and_publish<OPT>(a, ti[u], e0, inv_count, acc, w, m, v, vm);
           }
-        }
-      } else {
-        for (int r0 = 0; r0 < a.world; r0 += CH) {
-          uint4 v0[U][CH], v1[U][CH];
-          float sc[U][CH];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              const int r = r0 + c;
-              sc[u][c] = 1.f;
-              if (live[u] && r < a.world && (contrib >> r & 1u)) {
-                issue_dense<WIRE>(a.wire[r], (size_t)(tile0 + u * gridDim.x) * a.bytes_per_tile, v0[u][c], v1[u][c]);
-                if constexpr (KIND == KIND_SCALED) sc[u][c] = ld_sys_f32(a.scales[r] + ti[u].param);
-              }
-            }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {       // fixed rank order → deterministic fp32 sum
-              const int r = r0 + c;
-              if (live[u] && r < a.world && (contrib >> r & 1u)) {
-                float f[PSB_EPT];
-                decode_dense<WIRE>(v0[u][c], v1[u][c], f);
-#pragma unroll
-                for (int j = 0; j < PSB_EPT; ++j) {
-                  if constexpr (KIND == KIND_SCALED) acc[u][j] += f[j] * sc[u][c];
-                  else acc[u][j] += f[j];
-                }
-              }
-            }
         }
       }
+    } else {
+      // ---- dense / scaled wires over P2P: up to CH ranks of 16-byte peer loads in flight per thread, local optimizer
+      // state issued first (independent of the gather, so it overlaps the NVLink latency) ----
+      constexpr int CH = 4;
+      for (int tile = a.tile_begin + blockIdx.x; tile < a.tile_end; tile += gridDim.x) {
+        const TileInfo ti = a.tiles[tile];
+        if (a.active != nullptr && a.active[ti.param] == 0) continue;
+        const size_t e0 = (size_t)tile * PSB_TILE + tid * PSB_EPT;
+        float acc[PSB_EPT], w[PSB_EPT], m[PSB_EPT], v[PSB_EPT], vm[PSB_EPT];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (live[u]) {
-          const size_t e0 = (size_t)(tile0 + u * gridDim.x) * PSB_TILE + tid * PSB_EPT;
-          if constexpr (U == 1) {
-            apply_and_publish<OPT>(a, ti[u], e0, inv_count, acc[u], w[0], m[0], v[0], vm[0]);
-          } else {
-            load_state<OPT>(a, ti[u], e0, w[0], m[0], v[0], vm[0]);
-            apply_and_publish<OPT>(a, ti[u], e0, inv_count, acc[u], w[0], m[0], v[0], vm[0]);
+        for (int j = 0; j < PSB_EPT; ++j) acc[j] = 0.f;
+        load_state<OPT>(a, ti, e0, w, m, v, vm);
+        for (int r0 = 0; r0 < a.world; r0 += CH) {
+          uint4 v0[CH], v1[CH];
+          float sc[CH];
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int r = r0 + c;
+            sc[c] = 1.f;
+            if (r < a.world && (contrib >> r & 1u)) {
+              issue_dense<WIRE>(a.wire[r], (size_t)tile * a.bytes_per_tile, v0[c], v1[c]);
+              if constexpr (KIND == KIND_SCALED) sc[c] = ld_sys_f32(a.scales[r] + ti.param);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {       // fixed rank order → deterministic fp32 sum
+            const int r = r0 + c;
+            if (r < a.world && (contrib >> r & 1u)) {
+              float f[PSB_EPT];
+              decode_dense<WIRE>(v0[c], v1[c], f);
+#pragma unroll
+              for (int j = 0; j < PSB_EPT; ++j) {
+                if constexpr (KIND == KIND_SCALED) acc[j] += f[j] * sc[c];
+                else acc[j] += f[j];
+              }
+            }
           }
         }
+        apply_and_publish<OPT>(a, ti, e0, inv_count, acc, w, m, v, vm);
+      }
     }
   }
 
@@ -665,22 +692,9 @@ __global__ void psb_select_kernel(const uint64_t* signal_local, uint64_t* consum
 
 template <int KIND, int WIRE, int OPT>
 void launch_update_t(cudaStream_t s, const UpdateArgs& a, int grid) {
-  if constexpr (KIND == KIND_TOPK) {
-    psb_update_kernel<KIND, WIRE, OPT, 1><<<grid, PSB_THREADS, 0, s>>>(a);
-  } else {
-    // U = 2 (two tiles in flight per thread, no state prefetch, 2 CTAs/SM) measured SLOWER than U = 1 (state
-    // prefetch, 3 CTAs/SM) on the ResNet-18 arena at N = 1: 72.6 us vs 52.5 us (profiles/psb_update_kernel_*.ncu.txt).
-    // It stays available for experiments (PSB200_UPDATE_U=2) but is not the default.
-    static const int force_u = [] {
-      const char* e = getenv("PSB200_UPDATE_U");
-      return e ? atoi(e) : 1;
-    }();
-    const int tiles_per_cta = (a.ntiles + grid - 1) / grid;
-    if (force_u == 2 && a.world >= 2 && a.world <= 4 && tiles_per_cta >= 2)
-      psb_update_kernel<KIND, WIRE, OPT, 2><<<grid, PSB_THREADS, 0, s>>>(a);
-    else
-      psb_update_kernel<KIND, WIRE, OPT, 1><<<grid, PSB_THREADS, 0, s>>>(a);
-  }
+  // (a variant with two P2P tiles in flight per thread and no state prefetch measured slower, 72.6 us vs 52.5 us on the
+  //  ResNet-18 arena at N = 1, and was removed: profiles/psb_update_kernel_resnet18_n1_v2.ncu.txt)
+  psb_update_kernel<KIND, WIRE, OPT><<<grid, PSB_THREADS, 0, s>>>(a);
 }
 template <int KIND, int WIRE>
 void launch_update_o(cudaStream_t s, int opt, const UpdateArgs& a, int grid) {

@@ -1,4 +1,4 @@
-// EXPERIMENTAL (opt-in, PSB200_STEM=fused): the ResNet stem — 7x7 / stride 2 / pad 3 convolution, 3 → 64 channels —
+// The ResNet stem (default path since round 2; PSB200_STEM=im2col falls back) — 7x7 / stride 2 / pad 3 convolution, 3 → 64 channels —
 // as ONE implicit-GEMM kernel on tcgen05, replacing psb_im2col_stem (writes a 1.13 GB patch matrix at batch 256) +
 // psb_bcast_gemm2_kernel (reads it back) + the BatchNorm statistics pass over the 411 MB output
 // (profiles/resnet18_step_launches_final.txt: 355 + 505 + ~95 us of a 7.9 ms step).
@@ -46,6 +46,14 @@ struct StemParams {
   const __nv_bfloat16* x;     // [N, H, W, 3] bf16 (channels-last, already normalised)
   float* sums;                // [128]: Σy[64] | Σy²[64], accumulated with atomics (caller zeroes); nullable
   int N, H, W, OH, OW;
+  // The broadcast gate (as in bcast_gemm*.cu): the weight matrix lives IN the symmetric parameter arena in the [64,176]
+  // GEMM layout (layout.py custom placement) and the lane that TMA-loads it first acquires the PS's PARAMS_READY epoch, so
+  // this kernel — the first consumer of parameters in a ResNet forward — is the req.Wait() of the broadcast
+  // (/root/reference/mpi_comms.py:120-124) and workers queue no separate wait kernel.
+  const uint64_t* ready_flag; // nullable
+  uint64_t ready_epoch;
+  uint64_t* err_slot;
+  unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
@@ -188,6 +196,10 @@ psb_stem_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   } else if (warp == 8) {
     // ============================== MMA issuer ==============================
     if (elect_one()) {
+      if (p.ready_flag != nullptr) {       // patch loads / A-tile builds of the first tiles already run in the other warps
+        psb::spin_until_ge(p.ready_flag, p.ready_epoch, p.err_slot, p.timeout_ns);
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire → async-proxy (TMA) reads
+      }
       mbar_expect_tx(b_full, SB_BYTES);
       for (int b = 0; b < 3; ++b) tma_load_2d(&tmap_w, b_full, smem + OFF_B + b * SB_BLK, b * 64, 0);
     }
@@ -460,7 +472,7 @@ int psb_stem_fwd_smem_bytes() { return STEM_SMEM; }
 // tmap_w: [64,176] bf16 weights, box 64 x 64, SWIZZLE_128B.  tmap_y: [N*OH*OW, 64] bf16 output, box 64 columns x OW rows,
 // SWIZZLE_128B.  `sums` (nullable) must hold 128 zeroed floats.
 void psb_stem_fwd_launch(cudaStream_t s, const void* tmap_w, const void* tmap_y, const void* x, float* sums, int N, int H, int W,
-                         int num_sms) {
+                         int num_sms, const uint64_t* ready_flag, uint64_t ready_epoch, unsigned long long timeout_ns) {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(psb_stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
@@ -471,6 +483,10 @@ void psb_stem_fwd_launch(cudaStream_t s, const void* tmap_w, const void* tmap_y,
   p.sums = sums;
   p.N = N, p.H = H, p.W = W;
   p.OH = (H - 1) / 2 + 1, p.OW = (W - 1) / 2 + 1;
+  p.ready_flag = ready_flag;
+  p.ready_epoch = ready_epoch;
+  p.err_slot = ready_flag != nullptr ? const_cast<uint64_t*>(ready_flag) - SIG_PARAMS_READY + SIG_ERROR : nullptr;
+  p.timeout_ns = timeout_ns;
   const int tiles = N * p.OH;
   const int grid = tiles < num_sms ? tiles : num_sms;
   psb_count_launch(1);

@@ -15,12 +15,14 @@ import torch.nn.functional as F
 
 from ..ops.batchnorm import FusedBatchNormAct2d, _kernel_ok, fused_bn_relu_maxpool
 from ..ops.pooling import FusedMaxPool2d
-from ..ops.stem import stem_conv, stem_conv_fused, stem_fused_supported, stem_supported
+from ..ops.stem import STEM_K, STEM_STRIDES, stem_conv, stem_conv_fused, stem_fused_supported, stem_supported
 
-# EXPERIMENTAL, default off: one implicit-GEMM stem kernel with the BatchNorm statistics in its epilogue
-# (csrc/kernels/stem_kernels.cu) instead of im2col + GEMM + statistics pass.  Validate with bench/stem_fused_check.py.
-_FUSED_STEM = os.environ.get("PSB200_STEM", "").lower() == "fused"
-# EXPERIMENTAL, default off: BN1 + ReLU + max-pool in one pass each way (bn_kernels.cu).  Validate with bench/bnpool_check.py.
+# Default since round 2 (validated on B200, bench/stem_fused_check.py): one implicit-GEMM stem kernel with the BatchNorm
+# statistics in its epilogue (csrc/kernels/stem_kernels.cu) instead of im2col + GEMM + statistics pass: 0.97 → 0.47 ms.
+# PSB200_STEM=im2col restores the round-1 path.
+_FUSED_STEM = os.environ.get("PSB200_STEM", "fused").lower() != "im2col"
+# Opt-in: BN1 + ReLU + max-pool in one pass each way (bn_kernels.cu).  Measured on B200 (bench/bnpool_check.py): forward
+# 0.47 → 0.37 ms but forward+backward 1.27 → 1.52 ms, so it stays off.
 _FUSED_BNPOOL = os.environ.get("PSB200_BNPOOL", "").lower() == "fused"
 
 
@@ -76,6 +78,8 @@ class ResNet(nn.Module):
         self.gemm_stem = gemm_stem
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self._engine = None
+        self._tag_stem()
         self.bn1 = FusedBatchNormAct2d(64, relu=True)
         self.maxpool = FusedMaxPool2d(3, 2, 1)
         self.layer1 = self._make_layer(block, 64, layers[0])
@@ -96,6 +100,17 @@ class ResNet(nn.Module):
                     nn.init.zeros_(m.bn3.weight)
                 elif isinstance(m, BasicBlock):
                     nn.init.zeros_(m.bn2.weight)
+
+    def _tag_stem(self):
+        """Ask the PS device engine to keep the stem weight in the zero-padded [64,176] GEMM layout the stem kernel TMA-loads
+        (``parallel/layout.py``): the broadcast then delivers it ready for the first forward GEMM."""
+        if self.gemm_stem and self.conv1.out_channels == 64:
+            self.conv1.weight.ps_arena_layout = (STEM_STRIDES, 64 * STEM_K)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._tag_stem()                     # conversions may re-create the Parameter object
+        return out
 
     def _make_layer(self, block, planes, blocks, stride=1):
         downsample = None
@@ -129,12 +144,27 @@ class ResNet(nn.Module):
             return fused_bn_relu_maxpool(y, self.bn1, sums)
         return mp(self.bn1(y, sums=sums) if sums is not None else self.bn1(y))
 
+    def attach(self, optimizer) -> "ResNet":
+        """Gate the stem kernel on the parameter server's broadcast: its weight load acquires ``PARAMS_READY`` itself and
+        workers stop queueing the separate wait kernel (the stem convolution is the first consumer of parameters in the
+        forward pass).  A forward that does not take the fused-stem path falls back to the engine's wait kernel."""
+        eng = getattr(optimizer, "_engine", None)
+        if eng is None:
+            raise ValueError("attach() needs an optimizer running the device engine")
+        self._engine = eng
+        eng.register_gate(self)
+        return self
+
     def forward(self, x):
+        eng = self._engine
         if (_FUSED_STEM and self.gemm_stem and self.training and x.shape[1] == self.conv1.in_channels
                 and stem_fused_supported(x, self.conv1)):
-            y, sums = stem_conv_fused(x, self.conv1.weight)     # EXPERIMENTAL: implicit GEMM + BN statistics in one kernel
+            flag_ptr, epoch = eng.gate() if eng is not None else (0, 0)
+            y, sums = stem_conv_fused(x, self.conv1.weight, flag_ptr, epoch)   # implicit GEMM + BN statistics in one kernel
             x = self._tail(y, sums)
         else:
+            if eng is not None:
+                eng.ensure_params()                  # nobody acquired the broadcast in-kernel: the plain wait kernel
             x = self._tail(self.stem(x))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))

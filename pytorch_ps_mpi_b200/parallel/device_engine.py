@@ -83,8 +83,13 @@ class DeviceEngine:
         self.wire = self.spec.resolved_wire(self.dtype)
         self.bpt = self.spec.bytes_per_tile(self.dtype)
         self.cap = self.spec.tile_capacity()
-        self.timeout_s = float(os.environ.get("PSB200_DEVICE_TIMEOUT", "60"))
-        self.bucket_bytes = int(os.environ.get("PSB200_BUCKET_BYTES", 16 << 20))
+        # bounded device spins: a dead peer must never hang the GPU, but an honest stall (rank-0 validation, a
+        # checkpoint, a slow data loader) must not poison the flags either — hence a long default, surfaced by
+        # _poll_error() every few steps instead of silently disabling synchronisation
+        self.timeout_s = float(os.environ.get("PSB200_DEVICE_TIMEOUT", "900"))
+        self.chunk_bytes = int(os.environ.get("PSB200_CHUNK_BYTES", os.environ.get("PSB200_BUCKET_BYTES", 4 << 20)))
+        self.pipeline = bool(getattr(opt, "pipeline", True)) and os.environ.get("PSB200_PIPELINE", "1") != "0" \
+            and self.mode in ("ps", "allgather")
         L = self.layout
         nt, n_pad = L.ntiles, L.numel_padded
 
@@ -114,7 +119,9 @@ class DeviceEngine:
             for s in L.slots:
                 flat = self.param_arena[s.offset: s.offset + s.numel]
                 pd = s.param.data
-                if pd.is_contiguous() or not _dense(pd):
+                if s.strides is not None:   # custom placement requested by the module (layout.py): padding stays zero
+                    view = torch.as_strided(flat, pd.shape, s.strides)
+                elif pd.is_contiguous() or not _dense(pd):
                     view = flat.view(pd.shape)
                 else:   # e.g. channels_last conv weights: keep the physical layout cuDNN wants
                     view = torch.as_strided(flat, pd.shape, pd.stride())
@@ -171,11 +178,17 @@ class DeviceEngine:
         nvls_ok = mc and self.kind == KIND_DENSE and self.wire in (WIRE_F32, WIRE_BF16, WIRE_F16) and self.size > 1
         if reduce == "nvls" and not nvls_ok:
             raise ValueError("reduce='nvls' needs multicast memory and a dense fp32/bf16/fp16 wire")
+        if reduce == "nvls" and self.mode == "async":
+            # multimem.ld_reduce sums EVERY bound rank's wire tile; async sums only the device-selected contributors
+            # (quota < N-1), so the switch reduction would re-apply stale / torn gradients of the others
+            raise ValueError("reduce='nvls' cannot be combined with mode='async' (the contributor set is a subset)")
         # 'auto': the switch reduces (multimem.ld_reduce: server ingress 1x instead of (N-1)x, 1.9-2x faster than
-        # the P2P pull at 16-64 MB on 8 GPUs) when that is exact — fp32 wires, one reducer (ps / async), N >= 4;
-        # everything else keeps the rank-ordered P2P sum (bf16 wires would get a bf16-rounded switch sum, and in
-        # allgather mode every rank must produce bit-identical sums).  'nvls' / 'p2p' force either.
-        auto_nvls = (nvls_ok and self.wire == WIRE_F32 and self.mode in ("ps", "async") and self.size >= 4
+        # the P2P pull at 16-64 MB on 8 GPUs) for dense fp32 / bf16 / fp16 wires when there is ONE reducer whose
+        # contributor set is always every rank (mode='ps') and N >= 4.  bf16/fp16 wires: the switch accumulates in
+        # fp32 and returns the sum rounded once to the wire type (|rel err| <= 2^-9 for bf16) before the fp32 master
+        # update.  allgather keeps the rank-ordered P2P sum (every rank must produce bit-identical sums), async keeps
+        # it because only the selected contributors may be summed.  'nvls' / 'p2p' force either.
+        auto_nvls = (nvls_ok and self.mode == "ps" and self.size >= 4
                      and os.environ.get("PSB200_REDUCE", "") != "p2p")
         if reduce == "p2p":
             self.reduce = 0
@@ -216,8 +229,8 @@ class DeviceEngine:
         self._sigctr_ptr = self.counters.data_ptr() + 8
         self._ratio = float(self.spec.ratio)
         self._sig_base = [p + self.off_signal for p in self.arena.ptrs]
-        self._pending: List[tuple] = []
-        self._pending_bytes = 0
+        # ---- the pipeline chunks: contiguous runs of whole parameters in arena (= backward) order ----
+        self._make_chunks()
         self._fired: set = set()
         self._keep: List[torch.Tensor] = []
         self._keep_prev: List[torch.Tensor] = []   # last step's gradients: freed one step late (see _flush)
@@ -236,12 +249,57 @@ class DeviceEngine:
         self._select_host = torch.zeros(64, dtype=torch.int64).pin_memory()
         self._async_done_workers: set = set()
         self._snap_version = 0
+        self._step_hyp = None
+        self._update_spans: list = []
+        # device-timeout surfacing: an async copy of SIG_ERROR into pinned memory every few steps, read one poll late
+        self._err_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._err_event = None
+        self._err_every = max(1, int(os.environ.get("PSB200_ERROR_POLL", "16")))
         self.world.barrier()
+
+    def _make_chunks(self):
+        """Static chunks of the update pipeline (identical on every rank: they depend on the layout only).
+
+        Chunk ``k`` = arena tiles ``[lo, hi)`` holding whole parameters, at least ``chunk_bytes`` of parameter bytes
+        each (the last one takes the remainder).  A chunk is encoded — and, on the server, gathered / updated /
+        broadcast — as soon as every parameter in it AND in all earlier chunks has produced its gradient, while
+        backward keeps running on the later chunks (``/root/reference/ps.py:140-148,159-162``: one collective per
+        parameter, consumed as each completes)."""
+        L = self.layout
+        total = L.numel_padded * self.psz
+        target = max(self.chunk_bytes, TILE * self.psz, -(-total // 48))      # at most ~48 chunks
+        if not self.pipeline and self.mode != "async":
+            target = max(target, total)                                       # one chunk = the round-1 behaviour
+        chunks, cur, nbytes = [], [], 0
+        for sl in L.slots:
+            cur.append(sl)
+            nbytes += sl.ntiles * TILE * self.psz
+            if nbytes >= target:
+                chunks.append(cur)
+                cur, nbytes = [], 0
+        if cur:
+            chunks.append(cur)
+        self.chunks = chunks
+        self.nchunks = len(chunks)
+        self.chunk_tiles = [(c[0].first_tile, c[-1].first_tile + c[-1].ntiles) for c in chunks]
+        self._chunk_of = [0] * L.nparams
+        for k, c in enumerate(chunks):
+            for sl in c:
+                self._chunk_of[sl.index] = k
+        self._chunk_items: List[list] = [[] for _ in chunks]
+        self._chunk_left = [len(c) for c in chunks]
+        self._next_chunk = 0
+
+    def _progress(self, epoch: int, chunk: int) -> int:
+        """Monotone GRAD_READY value meaning "chunks 0..chunk of step ``epoch`` are in my wire arena"."""
+        return (epoch - 1) * self.nchunks + chunk + 1
 
     # ---------------------------------------------------------------------------------- state
     @staticmethod
     def _like(flat: torch.Tensor, param: torch.Tensor) -> torch.Tensor:
         """View a flat arena slice with the parameter's shape AND physical layout."""
+        if flat.numel() != param.numel():          # custom placement (layout.py): same strides over the same span
+            return torch.as_strided(flat, param.shape, param.stride())
         if param.is_contiguous() or not _dense(param):
             return flat.view(param.shape)
         return torch.as_strided(flat, param.shape, param.stride())
@@ -303,23 +361,34 @@ class DeviceEngine:
 
     # ------------------------------------------------------------------------------- backward
     def on_grad(self, grad: torch.Tensor, name: str, param: torch.nn.Parameter):
-        """Backward hook (``ps.py:98-101``): bucket the gradient; encode when the bucket fills."""
+        """Backward hook (``ps.py:98-101``): file the gradient under its chunk; every chunk that is now complete (in
+        arena order) is encoded — and on the server gathered / updated / broadcast — right away, under backward."""
         s = self.layout.by_id[id(param)]
         g = grad.detach()
         if g.dtype != self.dtype:
             g = g.to(self.dtype)
-        if g.stride() != param.stride() or g.data_ptr() % 16:
+        if s.strides is not None:
+            # custom placement: the encode kernel reads the whole span, padding included (it must be zero)
+            if not (g.stride() == param.stride() and g.data_ptr() % 16 == 0 and g.storage_offset() * g.element_size() +
+                    s.numel * g.element_size() <= g.untyped_storage().nbytes()):
+                span = torch.zeros(s.numel, dtype=g.dtype, device=g.device)
+                torch.as_strided(span, param.shape, s.strides).copy_(g)
+                g = span
+            else:
+                g = torch.as_strided(g, (s.numel,), (1,))
+        elif g.stride() != param.stride() or g.data_ptr() % 16:
             # the arena is in the parameter's physical order: bring the gradient into it
             g = torch.empty_strided(param.shape, param.stride(), dtype=g.dtype, device=g.device).copy_(g)
         if s.index in self._fired:           # gradient accumulation: later micro-batches add up
             raise RuntimeError(f"parameter {name!r} produced two gradients before step(); "
                                "call step() after every backward (the reference encodes per backward)")
         self._fired.add(s.index)
-        self._pending.append((s, g))
-        self._pending_bytes += s.numel * self.psz
+        k = self._chunk_of[s.index]
+        self._chunk_items[k].append((s, g))
+        self._chunk_left[k] -= 1
         self._raw_bytes += s.numel * self.psz
-        if self._pending_bytes >= self.bucket_bytes:
-            self._flush()
+        while self._next_chunk < self.nchunks and self._chunk_left[self._next_chunk] == 0:
+            self._flush_chunk(self._next_chunk)
 
     def _event(self, timing: bool = False):
         """A pooled CUDA event (creating one costs more than recording one)."""
@@ -328,20 +397,20 @@ class DeviceEngine:
         self._ev_i = (self._ev_i + 1) % len(self._ev_pool)
         return self._ev_pool[self._ev_i]
 
-    def _flush(self, signal=None, joined: bool = False):
-        """Encode the pending bucket on the comm stream (launched with an explicit stream handle: no Python-side
-        stream switching).  ``signal=(targets, slot, value)``: this is the step's last encode launch, so its last
-        CTA raises the GRAD_READY flag itself.  ``joined``: the caller already made the comm stream wait for the
-        compute stream."""
-        if not self._pending:
-            return
+    def _flush_chunk(self, k: int, joined: bool = False, active_ptr: int = 0):
+        """Everything chunk ``k`` needs, queued on the comm stream (explicit stream handle: no Python-side stream
+        switching): encode its gradients into the wire arena, raise this rank's GRAD_READY progress flag from the
+        last encode CTA, and — on the server — launch the fused gather/update/broadcast kernel for exactly these tiles.
+
+        Must be called in chunk order.  ``joined``: the caller already made the comm stream wait for the compute stream."""
+        assert k == self._next_chunk
+        self._next_chunk = k + 1
+        m, cs, csh = self.m, self.comm_stream, self._cs
         cur = torch.cuda.current_stream(self.device)
-        cs = self.comm_stream
         if not joined:
             ev = self._event()
             ev.record(cur)
             cs.wait_event(ev)
-        batch, self._pending, self._pending_bytes = self._pending, [], 0
         if not self._first_flush_done:
             if self._prev_done is not None:
                 # Bound the comm stream's lag to one step: gradients are kept alive (not record_stream'ed, which
@@ -350,16 +419,45 @@ class DeviceEngine:
                 cur.wait_event(self._prev_done)
             self._first_flush_done = True
             self._before_first_encode()
-        grads = [g for _, g in batch]
-        self.m.encode(self.kind, self.wire, grads, [s.first_tile for s, _ in batch],
-                      [s.ntiles for s, _ in batch], [s.index for s, _ in batch],
-                      self._tiles_ptr, self._wire_ptr, self._scales_ptr, self._amax_ptr, self._residual_ptr,
-                      self.bpt, self.cap, self._ratio,
-                      *((signal[0], signal[1], signal[2], self._sigctr_ptr) if signal else ([], 0, 0, 0)),
-                      self._cs)
-        nb = (len(batch) + 63) // 64
-        self.launches += nb * (2 if self.kind == KIND_SCALED else 1)
-        self._keep.extend(grads)
+        epoch = self._epoch + 1
+        last = k == self.nchunks - 1
+        n = self.size
+        sync = self.mode != "async"                   # async posts its flag from _step_async
+        # the launching rank's own gradient is ordered by the stream, so the server neither signals nor waits itself
+        must_signal = sync and n > 1 and not (self.mode == "ps" and self.rank == 0) and (self.pipeline or last)
+        sig = None
+        if must_signal:
+            sb = self._sig_base
+            targets = [sb[0]] if self.mode == "ps" else [b for r, b in enumerate(sb) if r != self.rank]
+            sig = (targets, m.SIG_GRAD_READY + self.rank, self._progress(epoch, k))
+        items, self._chunk_items[k] = self._chunk_items[k], []
+        if items:
+            grads = [g for _, g in items]
+            m.encode(self.kind, self.wire, grads, [s.first_tile for s, _ in items],
+                     [s.ntiles for s, _ in items], [s.index for s, _ in items],
+                     self._tiles_ptr, self._wire_ptr, self._scales_ptr, self._amax_ptr, self._residual_ptr,
+                     self.bpt, self.cap, self._ratio,
+                     *((sig[0], sig[1], sig[2], self._sigctr_ptr) if sig else ([], 0, 0, 0)),
+                     csh)
+            nb = (len(items) + 63) // 64
+            self.launches += nb * (2 if self.kind == KIND_SCALED else 1)
+            self._keep.extend(grads)
+        elif sig:                                     # nothing fired in this chunk: the flag alone
+            m.signal(sig[0], sig[1], sig[2], -1, 0, csh)
+            self.launches += 1
+        if sync and self.is_server and (self.pipeline or last):
+            lo, hi = self.chunk_tiles[k] if self.pipeline else (0, self.layout.ntiles)
+            inv = (1.0 / n) if self.opt.average else 1.0
+            prof = self._prof.enabled
+            ev_a = self._prof.mark(cs) if prof else None
+            self.plan.launch(epoch, self._get_hypers(), (1 << n) - 1, inv, 1 if n > 1 else 0,
+                             (0 if n == 1 else (1 if self.mode == "ps" else 2)) if last else 0,
+                             active_ptr=active_ptr, timeout_s=self.timeout_s,
+                             wait_mask=((1 << n) - 1) & ~(1 << self.rank), stream=csh,
+                             tile_begin=lo, tile_end=hi, wait_value=self._progress(epoch, k))
+            self.launches += 1
+            if prof:
+                self._update_spans.append((ev_a, self._prof.mark(cs)))
 
     def _before_first_encode(self):
         """Queued on the comm stream before this step's first write into the wire arena."""
@@ -380,6 +478,12 @@ class DeviceEngine:
             self.launches += 1
 
     # ----------------------------------------------------------------------------------- step
+    def _get_hypers(self):
+        """This step's per-group hyper-parameter tuples (sampled once per step, at the first chunk that needs them)."""
+        if self._step_hyp is None:
+            self._step_hyp = self._hypers()
+        return self._step_hyp
+
     def _hypers(self) -> List[List[float]]:
         o = self.opt
         out = []
@@ -432,73 +536,62 @@ class DeviceEngine:
                 self.wire_arena[s.first_tile * self.bpt: (s.first_tile + s.ntiles) * self.bpt].zero_()
         return self.active_dev.data_ptr()
 
+    def _flush_rest(self, cs, joined: bool):
+        """step(): chunks that did not complete during backward (always the last one's tail when every parameter
+        fired from the final hook; all of them when some parameter got no gradient, ``ps.py:178-179``)."""
+        if self._next_chunk >= self.nchunks:
+            if not self._active_all:                  # every parameter fired again: forget the frozen-set cache
+                self._active_all, self._last_fired = True, None
+            return
+        if len(self._fired) == self.layout.nparams and self._active_all:
+            active_ptr = 0                            # the common case: every parameter got a gradient
+        else:
+            with torch.cuda.stream(cs):
+                active_ptr = self._handle_inactive()  # before the flag: a tile the server reads must be final
+        while self._next_chunk < self.nchunks:
+            self._flush_chunk(self._next_chunk, joined=joined, active_ptr=active_ptr)
+
     def step(self) -> Dict[str, float]:
-        o = self.opt
         t0 = time.time()
         data = {"comm_wait": 0.0, "optim_step_time": 0.0, "decode_time": 0.0,
                 "iallgather_prepare_time": 0.0, "isend_time": 0.0}
         if self.mode == "async" and self.size > 1:
             return self._step_async(data)
         epoch = self._epoch + 1
-        m, cs, csh = self.m, self.comm_stream, self._cs
+        m, cs = self.m, self.comm_stream
         prof = self._prof.enabled
         cur = torch.cuda.current_stream(self.device)
         ev = self._event(timing=prof)
         ev.record(cur)                       # backward is complete up to here
-        cs.wait_event(ev)
-        sig_base = self._sig_base
-        # the launching rank's own gradient is ordered by the stream, so it neither signals nor waits itself
-        must_signal = self.size > 1 and not (self.mode == "ps" and self.rank == 0)
-        targets = [sig_base[0]] if self.mode == "ps" else [b for r, b in enumerate(sig_base) if r != self.rank]
-        if not self._first_flush_done:
-            self._first_flush_done = True
-            self._before_first_encode()
-        if len(self._fired) == self.layout.nparams and self._active_all:
-            active_ptr = 0                            # the common case: every parameter got a gradient
-        else:
-            with torch.cuda.stream(cs):
-                active_ptr = self._handle_inactive()  # before the flag: a tile the server reads must be final
-        fused = must_signal and bool(self._pending)
-        self._flush(signal=(targets, m.SIG_GRAD_READY + self.rank, epoch) if fused else None, joined=True)
+        pending = self._next_chunk < self.nchunks
+        if pending:
+            cs.wait_event(ev)
         data["code_wait"] = time.time() - t0
-        t1 = time.time()
-        ev_a = self._prof.mark(cs)
-        if must_signal and not fused:
-            m.signal(targets, m.SIG_GRAD_READY + self.rank, epoch, -1, 0, csh)
-            self.launches += 1
-        data["isend_time"] = time.time() - t1
         t2 = time.time()
-        ev_b = self._prof.mark(cs)
-        if self.is_server:
-            n = self.size
-            inv = (1.0 / n) if o.average else 1.0
-            self.plan.launch(epoch, self._hypers(), (1 << n) - 1, inv, 1 if n > 1 else 0,
-                             0 if n == 1 else (1 if self.mode == "ps" else 2),
-                             active_ptr=active_ptr, timeout_s=self.timeout_s,
-                             wait_mask=((1 << n) - 1) & ~(1 << self.rank), stream=csh)
-            self.launches += 1
-        else:
-            self._hypers()                   # keep per-group step counters aligned with the server
+        self._flush_rest(cs, joined=True)
+        self._get_hypers()                   # workers too: keeps the per-group step counters aligned with the server
         data["optim_step_time"] = time.time() - t2
-        if prof:
-            ev_c = self._prof.mark(cs)
-            self._prof.span("dev_signal_time", ev_a, ev_b)
-            self._prof.span("dev_gather_update_bcast_time", ev_b, ev_c)
+        data["isend_time"] = 0.0
         done = self._event()
         done.record(cs)
         t3 = time.time()
         if self.size > 1 and self.mode == "ps" and self.rank != 0:
             if not self._gates:
                 # the req.Wait() of mpi_comms.py:121 — a one-thread kernel on the compute stream
-                m.wait_flags(sig_base[self.rank], m.SIG_PARAMS_READY, 1, epoch, self.timeout_s)
+                m.wait_flags(self._sig_base[self.rank], m.SIG_PARAMS_READY, 1, epoch, self.timeout_s)
                 self.launches += 1
-            # else: the first forward GEMM (BcastLinear) acquires the flag inside its TMA producer
+            # else: the first forward GEMM (BcastLinear / the stem) acquires the flag inside its TMA producer
         else:
             cur.wait_event(done)
         data["comm_wait"] = time.time() - t3
+        data["chunks"] = self.nchunks
         if prof:
             ev_d = self._prof.mark(cur)
             self._prof.span("dev_step_tail_time", ev, ev_d)     # backward-done → parameters usable, on the compute stream
+            if self._update_spans:
+                self._prof.span("dev_gather_update_bcast_time", *self._update_spans[-1])   # the LAST chunk's kernel
+                self._prof.span("dev_update_pipeline_time", self._update_spans[0][0], self._update_spans[-1][1])
+            self._update_spans = []
             data.update(self._prof.harvest())                   # device timings of the most recent COMPLETED step
         self._end_of_step(data, done)
         return data
@@ -519,8 +612,49 @@ class DeviceEngine:
         self._prev_done = done
         self._raw_bytes = 0
         self._first_flush_done = False
+        self._step_hyp = None
+        self._next_chunk = 0
+        self._chunk_left = [len(c) for c in self.chunks]
+        for it in self._chunk_items:
+            it.clear()
         if os.environ.get("PSB200_CHECK") == "1":
             self.check()
+        elif self.size > 1 and self._epoch % self._err_every == 0:
+            self._poll_error()
+
+    def _poll_error(self):
+        """Surface device-side time-outs WITHOUT a sync: every ``PSB200_ERROR_POLL`` steps an async copy of SIG_ERROR
+        lands in pinned memory; the previous poll's value is read once its event has completed."""
+        if self._err_event is not None and self._err_event.query():
+            err = int(self._err_host[0])
+            if err:
+                raise RuntimeError(f"rank {self.rank}: a device-side wait timed out (code {err}) — a peer is stalled or "
+                                   f"dead; synchronisation is disabled until recover() (PSB200_DEVICE_TIMEOUT="
+                                   f"{self.timeout_s:.0f} s)")
+            self._err_event = None
+        if self._err_event is None:
+            with torch.cuda.stream(self.comm_stream):
+                self._err_host.copy_(self.signal[self.m.SIG_ERROR: self.m.SIG_ERROR + 1], non_blocking=True)
+                self._err_event = torch.cuda.Event()
+                self._err_event.record(self.comm_stream)
+
+    def recover(self):
+        """Explicit recovery after a surfaced time-out: every rank clears its error slot (collective)."""
+        torch.cuda.synchronize(self.device)
+        self.signal[self.m.SIG_ERROR] = 0
+        self._err_host.zero_()
+        self._err_event = None
+        torch.cuda.synchronize(self.device)
+        self.world.barrier()
+
+    def resync_master(self):
+        """Re-seed the fp32 master weights from the (bf16/fp16) parameters — call after changing parameters in place
+        behind the optimizer's back (``model.load_state_dict`` without ``opt.load_state_dict``, manual re-init, EMA
+        swaps): every update writes master → parameters, so un-synced edits would be overwritten."""
+        if self.master is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+            with torch.no_grad():
+                self.master.copy_(self.param_arena)
 
     # ------------------------------------------------------------------------------ async mode
     def _step_async(self, data):
@@ -529,16 +663,15 @@ class DeviceEngine:
         cs = self.comm_stream
         cur = torch.cuda.current_stream(self.device)
         if self.rank != 0:
-            self._flush()
             epoch = self._epoch + 1
             ev = torch.cuda.Event()
             ev.record(cur)
             cs.wait_event(ev)
+            self._flush_rest(cs, joined=True)        # chunks not yet encoded during backward (+ inactive parameters)
             with torch.cuda.stream(cs):
-                if not self._first_flush_done:
+                if not self._first_flush_done:       # no parameter produced a gradient at all
                     self._first_flush_done = True
                     self._before_first_encode()
-                self._handle_inactive()
                 # publish "gradient `epoch` is in my arena"
                 self.m.signal([sig_base[0]], self.m.SIG_GRAD_READY + self.rank, epoch)
                 self.launches += 1
@@ -548,7 +681,11 @@ class DeviceEngine:
             return data                      # never waits for NEW parameters (inconsistent reads unless consistent=True)
         # ---- rank 0: the server ----
         self._fired = set()
-        self._pending, self._pending_bytes, self._keep = [], 0, []
+        self._keep = []
+        self._next_chunk = 0
+        self._chunk_left = [len(c) for c in self.chunks]
+        for it in self._chunk_items:
+            it.clear()
         n = self.size
         cand = ((1 << n) - 1) & ~1
         for r in self._async_done_workers:
@@ -624,10 +761,23 @@ class DeviceEngine:
         self._gates.append(layer)
 
     def gate(self):
-        """``(flag_ptr, epoch)`` the next forward must observe before reading broadcast weights."""
+        """``(flag_ptr, epoch)`` the next forward must observe before reading broadcast weights.  Taking it marks the
+        current epoch's broadcast as acquired by a gated kernel (see :meth:`ensure_params`)."""
         if self.size == 1 or self.mode != "ps" or self.rank == 0 or self._epoch == 0:
             return 0, 0
+        self._gate_epoch = self._epoch
         return self.arena.local_ptr + self.off_signal + 8 * self.m.SIG_PARAMS_READY, self._epoch
+
+    def ensure_params(self):
+        """For forwards that bypass the gated kernel (eval mode, unsupported shapes) while a gate is registered: queue
+        the plain wait kernel on the current stream unless this epoch's broadcast was already acquired."""
+        if self.size == 1 or self.mode != "ps" or self.rank == 0 or self._epoch == 0 or not self._gates:
+            return
+        if getattr(self, "_gate_epoch", -1) == self._epoch:
+            return
+        self._gate_epoch = self._epoch
+        self.m.wait_flags(self._sig_base[self.rank], self.m.SIG_PARAMS_READY, 1, self._epoch, self.timeout_s)
+        self.launches += 1
 
     def peer_param_ptr(self, param: torch.Tensor, rank: int) -> int:
         """Address of ``param`` inside rank ``rank``'s parameter arena as mapped in this process."""

@@ -15,7 +15,7 @@ Here all parameters live in ONE flat arena so a single kernel launch covers the 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import torch
 
@@ -30,7 +30,8 @@ class ParamSlot:
     group: int
     first_tile: int
     ntiles: int
-    numel: int
+    numel: int            # elements the parameter occupies in the arena (its storage span if it has a custom placement)
+    strides: Optional[tuple] = None   # custom placement: the parameter is as_strided(shape, strides) over `numel` elements
 
     @property
     def offset(self) -> int:      # element offset in the arena
@@ -48,9 +49,20 @@ class FlatLayout:
         self.by_id: Dict[int, ParamSlot] = {}
         t = 0
         for i, (gi, p) in enumerate(ordered):
-            n = p.numel()
+            n, strides = p.numel(), None
+            # A module may ask for a custom physical placement of its parameter inside the arena
+            # (``param.ps_arena_layout = (strides, span_numel)``): e.g. the ResNet stem keeps its [64,3,7,7] weight in the
+            # zero-padded [64,176] GEMM layout its tcgen05 kernel TMA-loads, so the PS broadcast lands the weight directly in
+            # the form the first forward GEMM consumes (no per-step re-layout).  Elements of the span the view does not
+            # cover are padding: zero, zero gradient, untouched by SGD/Adam (0 stays 0).
+            hint = getattr(p, "ps_arena_layout", None)
+            if hint is not None:
+                strides, n = tuple(int(x) for x in hint[0]), int(hint[1])
+                reach = 1 + sum((sz - 1) * st for sz, st in zip(p.shape, strides))
+                if len(strides) != p.dim() or reach > n:
+                    raise ValueError(f"ps_arena_layout of {names.get(id(p))!r} does not fit its span")
             nt = max(1, (n + TILE - 1) // TILE)
-            s = ParamSlot(i, names.get(id(p), f"param{i}"), p, gi, t, nt, n)
+            s = ParamSlot(i, names.get(id(p), f"param{i}"), p, gi, t, nt, n, strides)
             self.slots.append(s)
             self.by_id[id(p)] = s
             t += nt

@@ -64,6 +64,26 @@ def _tag_name(param: torch.Tensor, name: str) -> None:
         param.__dict__["name"] = name
 
 
+def _accepts_name(fn) -> bool:
+    """Does ``encode`` take a ``name=`` keyword (user codings written against the reference's ``encode(grad, **kw)`` do;
+    a bare ``encode(grad)`` must keep working)?"""
+    target = getattr(fn, "func", fn)
+    cached = getattr(target, "_psb_accepts_name", None)
+    if cached is not None:
+        return cached
+    import inspect
+    try:
+        params = inspect.signature(fn).parameters
+        ok = "name" in params or any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values())
+    except (TypeError, ValueError):
+        ok = False
+    try:
+        target.__dict__["_psb_accepts_name"] = ok
+    except Exception:
+        pass
+    return ok
+
+
 class MPI_PS(torch.optim.Optimizer):
     """Parameter-server data-parallel optimizer wrapper (``/root/reference/ps.py:53-193``).
 
@@ -80,6 +100,12 @@ class MPI_PS(torch.optim.Optimizer):
         (``README.md:79-81``)
     level : host engine byte-compression level (0 = framing only, as the reference's default)
     profile : device engine — record CUDA-event section timings into ``data`` (one step late)
+    pipeline : device engine, sync modes — gather / update / broadcast each CHUNK of the arena as soon as its
+        gradients exist, under the rest of backward (the reference posts one non-blocking collective per parameter and
+        consumes each as it completes, ``ps.py:140-148,159-162``).  Parameters of finished chunks are therefore
+        rewritten DURING ``backward()`` and the hyper-parameters are sampled at the first chunk: set the learning rate
+        before ``backward()``, and do not read parameters between ``backward()`` and ``step()``.  ``pipeline=False``
+        restores one fused launch inside ``step()``.
     coalesce : host engine — ship all parameters' messages of a step as ONE framed message instead of one
         collective per parameter (the reference's behaviour, ``ps.py:140-148``); same numerics, far fewer round trips
     """
@@ -101,6 +127,7 @@ class MPI_PS(torch.optim.Optimizer):
                  profile: bool = False,
                  reduce: str = "auto",
                  coalesce: bool = False,
+                 pipeline: bool = True,
                  **kwargs):
         if mode not in _MODES:
             raise ValueError(f"mode must be one of {_MODES}")
@@ -109,6 +136,7 @@ class MPI_PS(torch.optim.Optimizer):
         self.mode, self.average, self.level = mode, bool(average), int(level)
         self.consistent, self.profile = bool(consistent), bool(profile)
         self.coalesce = bool(coalesce)
+        self.pipeline = bool(pipeline)
 
         named_params = list(named_params)
         self._named = OrderedDict()
@@ -207,6 +235,9 @@ class MPI_PS(torch.optim.Optimizer):
     # -------------------------------------------------------------- encode pipeline (C5)
     def format_for_send(self, grad, encode=None, format=None, **kwargs):
         """Pool-thread body: ``encode`` then serialise + frame (``ps.py:92-96``)."""
+        name = kwargs.pop("name", None)
+        if name is not None and _accepts_name(encode):
+            kwargs["name"] = name          # stateful codings (TopK error feedback) key their residual by parameter
         code = encode(grad.data, **kwargs)
         fmt = format if format is not None else partial(comms.format_for_send, level=self.level)
         msg, data = fmt(code)
@@ -214,7 +245,7 @@ class MPI_PS(torch.optim.Optimizer):
 
     def async_code(self, grad, *args, name=None, **kwargs):
         """Backward hook: queue the encode on the pool and remember hook-firing order (``ps.py:98-101``)."""
-        future = self.pool.submit(self.format_for_send, grad, *args, **kwargs)
+        future = self.pool.submit(self.format_for_send, grad, *args, name=name, **kwargs)
         self.futures += [future]
         self.names += [name]
 

@@ -31,10 +31,10 @@ def _sass(obj):
 
 
 def test_sass_shows_blackwell_paths():
-    gemm, psk = ext.OBJ / "bcast_gemm.o", ext.OBJ / "ps_kernels.o"
-    if not gemm.exists() or not psk.exists():
+    gemm, gemm2, psk = ext.OBJ / "bcast_gemm.o", ext.OBJ / "bcast_gemm2.o", ext.OBJ / "ps_kernels.o"
+    if not gemm.exists() or not psk.exists() or not gemm2.exists():
         pytest.skip("object files not present (built elsewhere)")
-    s = _sass(gemm)
+    s = _sass(gemm) + _sass(gemm2)
     assert "sm_100a" in s or "SM100" in s.upper() or "EF_CUDA_SM100" in s
     for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D", "UTMALDG.2D.2CTA", "LDTM", "UTCBAR.2CTA.MULTICAST"):
         assert mnemonic in s, f"{mnemonic} missing from bcast_gemm SASS"
@@ -44,9 +44,9 @@ def test_sass_shows_blackwell_paths():
     assert "HMMA" not in s.replace("UTCHMMA", "")      # no legacy mma.sync tensor path in the GEMM
 
 
-def test_sass_of_the_experimental_kernels():
-    """The opt-in kernels (fused stem, GEMM epilogue variants) are real tcgen05 / TMA code too, and spill nothing."""
-    stem, gexp = ext.OBJ / "stem_kernels.o", ext.OBJ / "bcast_gemm_exp.o"
+def test_sass_of_the_fused_stem_and_gemm_epilogues():
+    """The fused stem and the cta_group::2 GEMM (TMA-store epilogue) are real tcgen05 / TMA code, and spill nothing."""
+    stem, gexp = ext.OBJ / "stem_kernels.o", ext.OBJ / "bcast_gemm2.o"
     if not stem.exists() or not gexp.exists():
         pytest.skip("object files not present (built elsewhere)")
     s = _sass(stem)
@@ -55,7 +55,7 @@ def test_sass_of_the_experimental_kernels():
     g = _sass(gexp)
     for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTMASTG.2D", "LDTM"):
         assert mnemonic in g, f"{mnemonic} missing from bcast_gemm_exp SASS"
-    for log in ("stem_kernels.nvcc.log", "bcast_gemm_exp.nvcc.log", "bn_kernels.nvcc.log"):
+    for log in ("stem_kernels.nvcc.log", "bcast_gemm2.nvcc.log", "bn_kernels.nvcc.log"):
         p = ext.OBJ / log
         if p.exists():
             for line in p.read_text().splitlines():

@@ -207,3 +207,37 @@ def test_timings_summary_and_chrome_trace(tmp_path):
     ev = json.load(open(out))["traceEvents"]
     assert ev and all(e["ph"] == "X" and e["dur"] > 0 for e in ev)
     opt.close()
+
+
+def test_topk_error_feedback_through_host_optimizer():
+    """the host-engine hook must hand the parameter NAME to encode() so TopK(error_feedback=True) keeps one
+    residual per parameter (id(grad) of a temporary is recycled across parameters: shape errors / mixed residuals)."""
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=64)
+    code = ps.TopK(ratio=0.05, error_feedback=True)
+    opt = ps.SGD(model.named_parameters(), model.parameters(), lr=0.1, code=code, engine="host", mode="allgather")
+    x, y = torch.randn(16, 1, 28, 28), torch.randint(0, 10, (16,))
+    for _ in range(3):
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(model(x), y).backward()
+        opt.step()
+    names = {n for n, _ in model.named_parameters()}
+    assert set(code._residual) == names                      # one residual per parameter, keyed by name, no growth
+    for n, p in model.named_parameters():
+        assert code._residual[n].numel() == p.numel()
+    opt.close()
+
+
+def test_user_encode_without_name_kwarg_still_works():
+    class Bare(ps.Coding):
+        def encode(self, grad):                              # no **kwargs: must not be handed name=
+            return {"g": grad.clone()}
+
+        def decode(self, code, cuda=False):
+            return torch.as_tensor(code["g"])
+
+    model = mnist_mlp(hidden=16)
+    opt = ps.SGD(model.named_parameters(), model.parameters(), lr=0.1, code=Bare(), engine="host")
+    torch.nn.functional.cross_entropy(model(torch.randn(4, 1, 28, 28)), torch.randint(0, 10, (4,))).backward()
+    opt.step()
+    opt.close()
