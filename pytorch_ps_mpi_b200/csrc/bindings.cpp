@@ -55,6 +55,7 @@ at::Tensor blob_tensor(uint64_t ptr, std::vector<int64_t> shape, at::ScalarType 
 struct UpdatePlan {
   UpdateArgs a{};
   int kind = 0, wire = 0, opt = 0, grid = 0;
+  int64_t window_bytes = 128ll << 20;
 
   void set_rank_ptrs(int r, uint64_t wire_p, uint64_t scales_p, uint64_t param_p, uint64_t signal_p) {
     if (r < 0 || r >= PSB_MAX_RANKS) throw std::runtime_error("rank out of range");
@@ -94,8 +95,28 @@ struct UpdatePlan {
     a.average_dynamic = average_dynamic;
     a.active = reinterpret_cast<const uint8_t*>(active_ptr);
     a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
-    psb_launch_update(pick_stream(stream), kind, wire, opt, a, std::min(grid, a.tile_end - a.tile_begin));
-    check_launch("psb_update_kernel launch");
+    // Window the chunk: one launch touches at most `window_bytes` of every rank's wire arena.  A single kernel that walks
+    // >= 1 GB of mapped peer memory on each of 8 ranks falls off a TLB cliff (194 GB/s, profiles/bw_sweep_n8.json);
+    // back-to-back launches over <= 128 MB windows do not.  Only the first window waits for the flags (the rest is
+    // stream-ordered behind it) and only the last one raises PARAMS_READY / CONSUMED / ACK.
+    const int64_t per_tile = std::max<int64_t>(a.bytes_per_tile, 1);
+    // (sparse wires have tiny tiles: also bound the window by the parameter bytes it publishes through peer / multicast memory)
+    const int win = (int)std::max<int64_t>(1, std::min<int64_t>(window_bytes / per_tile, 4 * window_bytes / (PSB_TILE * 4)));
+    const int lo = a.tile_begin, hi = a.tile_end;
+    const int wait_grads_all = a.wait_grads, signal_all = a.signal_mode;
+    const uint32_t ack_all = a.ack_mask;
+    for (int b = lo; b < hi; b += win) {
+      a.tile_begin = b;
+      a.tile_end = std::min(hi, b + win);
+      const bool first = b == lo, last = a.tile_end == hi;
+      a.wait_grads = first ? wait_grads_all : 0;
+      a.signal_mode = last ? signal_all : 0;
+      a.ack_mask = last ? ack_all : 0;
+      a.ack_last = last ? 1 : 0;
+      psb_launch_update(pick_stream(stream), kind, wire, opt, a, std::min(grid, a.tile_end - a.tile_begin));
+      check_launch("psb_update_kernel launch");
+    }
+    a.tile_begin = lo, a.tile_end = hi, a.wait_grads = wait_grads_all, a.signal_mode = signal_all, a.ack_mask = ack_all;
   }
 };
 
@@ -151,11 +172,12 @@ void encode(int kind, int wire, const std::vector<at::Tensor>& grads, const std:
 }
 
 void signal(const std::vector<uint64_t>& targets, int slot, uint64_t value, int extra_slot, uint64_t extra_value,
-            uint64_t stream) {
+            uint64_t stream, uint64_t version_local, int version_slot) {
   std::vector<uint64_t*> t;
   for (auto p : targets) t.push_back(reinterpret_cast<uint64_t*>(p));
   psb_launch_signal(pick_stream(stream), t.data(), (int)t.size(), slot, value,
-                    extra_slot >= 0 ? reinterpret_cast<uint64_t*>(1) : nullptr, extra_slot < 0 ? 0 : extra_slot, extra_value);
+                    extra_slot >= 0 ? reinterpret_cast<uint64_t*>(1) : nullptr, extra_slot < 0 ? 0 : extra_slot, extra_value,
+                    reinterpret_cast<uint64_t*>(version_local), version_slot);
   check_launch("psb_signal_kernel launch");
 }
 
@@ -165,10 +187,25 @@ void wait_flags(uint64_t signal_local, int slot0, uint32_t mask, uint64_t want, 
   check_launch("psb_wait_kernel launch");
 }
 
-void select_ready(uint64_t signal_local, uint64_t consumed, uint32_t cand_mask, int quota, uint64_t out, double timeout_s) {
-  psb_launch_select(cur_stream(), reinterpret_cast<const uint64_t*>(signal_local), reinterpret_cast<uint64_t*>(consumed),
-                    cand_mask, quota, reinterpret_cast<uint64_t*>(out), (unsigned long long)(timeout_s * 1e9));
+void select_ready(uint64_t signal_local, uint64_t consumed, uint32_t cand_mask, int quota, uint64_t out, double timeout_s,
+                  uint64_t version, const std::vector<uint64_t>& begin_targets, uint64_t stream) {
+  std::vector<uint64_t*> bt;
+  for (auto p : begin_targets) bt.push_back(reinterpret_cast<uint64_t*>(p));
+  psb_launch_select(pick_stream(stream), reinterpret_cast<const uint64_t*>(signal_local), reinterpret_cast<uint64_t*>(consumed),
+                    cand_mask, quota, reinterpret_cast<uint64_t*>(out), (unsigned long long)(timeout_s * 1e9), version,
+                    bt.data(), (int)bt.size());
   check_launch("psb_select_kernel launch");
+}
+
+void snapshot(uint64_t signal_local, uint64_t stage, uint64_t shadow, uint64_t params, uint64_t nbytes, uint64_t scratch,
+              int attempts, uint64_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  psb_launch_snapshot(pick_stream(stream), reinterpret_cast<const uint64_t*>(signal_local), reinterpret_cast<const void*>(stage),
+                      reinterpret_cast<void*>(shadow), reinterpret_cast<void*>(params), (size_t)nbytes,
+                      reinterpret_cast<unsigned long long*>(scratch), attempts, sms);
+  check_launch("psb_snapshot launch");
 }
 
 }  // namespace
@@ -220,6 +257,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("wire", &UpdatePlan::wire)
       .def_readwrite("opt", &UpdatePlan::opt)
       .def_readwrite("grid", &UpdatePlan::grid)
+      .def_readwrite("window_bytes", &UpdatePlan::window_bytes)
       .def("set_rank_ptrs", &UpdatePlan::set_rank_ptrs)
       .def("configure",
            [](UpdatePlan& p, int world, int rank, int ntiles, int bytes_per_tile, int cap, int param_dt, int bcast, int reduce,
@@ -253,9 +291,16 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("sig_targets") = std::vector<uint64_t>{}, py::arg("sig_slot") = 0, py::arg("sig_value") = 0,
         py::arg("sig_counter") = 0, py::arg("stream") = 0);
   m.def("signal", &signal, py::arg("targets"), py::arg("slot"), py::arg("value"), py::arg("extra_slot") = -1,
-        py::arg("extra_value") = 0, py::arg("stream") = 0);
+        py::arg("extra_value") = 0, py::arg("stream") = 0, py::arg("version_local") = 0, py::arg("version_slot") = 0);
   m.def("wait_flags", &wait_flags, py::arg("signal_local"), py::arg("slot0"), py::arg("mask"), py::arg("want"),
         py::arg("timeout_s"), py::arg("stream") = 0);
-  m.def("select_ready", &select_ready);
+  m.def("select_ready", &select_ready, py::arg("signal_local"), py::arg("consumed"), py::arg("cand_mask"), py::arg("quota"),
+        py::arg("out"), py::arg("timeout_s"), py::arg("version") = 0, py::arg("begin_targets") = std::vector<uint64_t>{},
+        py::arg("stream") = 0);
+  m.def("snapshot", &snapshot, py::arg("signal_local"), py::arg("stage"), py::arg("shadow"), py::arg("params"), py::arg("nbytes"),
+        py::arg("scratch"), py::arg("attempts") = 2, py::arg("stream") = 0,
+        "consistent reads: device-side sequence-lock snapshot staging → shadow → parameters (no host reads)");
+  m.attr("SIG_STAGE_BEGIN") = SIG_STAGE_BEGIN;
+  m.attr("SIG_SEEN_VERSION") = SIG_SEEN_VERSION;
   bind_gemm(m);
 }

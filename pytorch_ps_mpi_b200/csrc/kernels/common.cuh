@@ -41,6 +41,7 @@ enum : int { REDUCE_P2P = 0, REDUCE_NVLS = 1 };
 #define SIG_ERROR 200         // non-zero → a spin timed out somewhere
 #define SIG_VERSION 201       // async: parameter version published by the PS
 #define SIG_STAGE_BEGIN 202   // async + consistent reads: version the PS STARTED publishing (sequence lock with SIG_VERSION)
+#define SIG_SEEN_VERSION 203  // async worker, local: parameter version sampled when the previous gradient was posted
 #define SIG_ACK 256           // [256, 320): async: PS consumed rank r's gradient of epoch e
 #define SIG_GRAD_VERSION 320  // [320, 384): async: parameter version rank r's gradient was computed on
 

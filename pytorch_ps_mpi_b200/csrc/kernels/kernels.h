@@ -68,6 +68,8 @@ struct UpdateArgs {
   int32_t wait_grads;                  // spin on SIG_GRAD_READY of every contributor first
   int32_t signal_mode;                 // 0 none | 1 SIG_PARAMS_READY → all | 2 SIG_CONSUMED[rank] → all
   uint32_t ack_mask;                   // async: ranks to acknowledge (SIG_ACK) when done
+  int32_t ack_last;                    // 1 on the last window of a launch sequence: the async contributors (chosen on the
+                                       // device, select_out) are acknowledged only then
   uint64_t version;                    // async: value published to SIG_VERSION
   const uint64_t* select_out;          // async: device-side {mask, count, epochs…} from psb_select_kernel (or nullptr)
   int32_t average_dynamic;             // async: divide by the selected count
@@ -78,13 +80,21 @@ void psb_launch_absmax(cudaStream_t s, const EncodeArgs& a);
 void psb_launch_encode(cudaStream_t s, int kind, int wire, const EncodeArgs& a);
 void psb_launch_update(cudaStream_t s, int kind, int wire, int opt, const UpdateArgs& a, int grid);
 void psb_launch_signal(cudaStream_t s, uint64_t* const* targets, int ntargets, int slot, uint64_t value,
-                       uint64_t* extra_slot_base, int extra_slot, uint64_t extra_value);
+                       uint64_t* extra_slot_base, int extra_slot, uint64_t extra_value, uint64_t* version_local = nullptr,
+                       int version_slot = 0);
 void psb_launch_wait(cudaStream_t s, const uint64_t* signal_local, int slot0, uint32_t mask, uint64_t want,
                      unsigned long long timeout_ns);
 // async PS: block until >= quota workers of `cand_mask` have SIG_GRAD_READY > consumed[r]; writes the
 // chosen mask + their epochs to `out` (out[0]=mask, out[1]=count, out[2+r]=epoch of rank r)
+// (out[40] = finished mask, out[41] = version, out[44+r] = staleness of rank r's gradient; opens the consistent-read sequence
+//  lock on `begin_targets` when something was selected)
 void psb_launch_select(cudaStream_t s, const uint64_t* signal_local, uint64_t* consumed, uint32_t cand_mask,
-                       int quota, uint64_t* out, unsigned long long timeout_ns);
+                       int quota, uint64_t* out, unsigned long long timeout_ns, uint64_t version = 0,
+                       uint64_t* const* begin_targets = nullptr, int nbegin = 0);
+// consistent reads: `attempts` x (fetch staging → shadow under the sequence lock, commit shadow → params); scratch = 6 x u64
+// initialised to {0, ~0, 0, 0, 0, 0}; scratch[5] = the adopted version
+void psb_launch_snapshot(cudaStream_t s, const uint64_t* signal_local, const void* stage, void* shadow, void* params, size_t nbytes,
+                         unsigned long long* scratch, int attempts, int num_sms);
 int psb_update_max_grid(int kind, int wire, int opt);
 
 // bcast_gemm.cu — tcgen05 / TMEM / TMA GEMM whose weight tiles are gated on the PS broadcast epoch

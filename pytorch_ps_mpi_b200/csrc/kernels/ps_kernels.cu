@@ -13,6 +13,7 @@
 //     (multimem.st through the switch, or unicast peer stores), then raises the epoch flag.
 //   * MPI requests / req.Wait() (ps.py:146, mpi_comms.py:110,121)  → monotonically increasing epoch
 //     flags in the symmetric signal pad (st.release.sys / ld.acquire.sys), bounded spins.
+#include <algorithm>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(PSB_THREADS, 3) psb_update_kernel(const __grid
   float inv_count = a.inv_count;
   if (a.select_out != nullptr) {   // async: the contributor set was chosen on the device
     contrib = (uint32_t)a.select_out[0];
-    ack = contrib;
+    ack = a.ack_last ? contrib : 0u;
     const uint32_t cnt = (uint32_t)a.select_out[1];
     if (cnt == 0) return;          // nothing to apply (all workers finished, or the select timed out)
     if (a.average_dynamic) inv_count = 1.f / (float)cnt;
@@ -613,15 +614,25 @@ struct SignalArgs {
   uint64_t* extra_base;
   int32_t extra_slot;
   uint64_t extra_value;
+  // async staleness accounting: when set, the kernel first posts "the parameter version this gradient was computed on"
+  // (sampled into `version_local[SIG_SEEN_VERSION]` when the PREVIOUS gradient was posted, i.e. right before the forward
+  // pass that produced this one started) into targets[t][version_slot], then re-samples the latest published version.
+  uint64_t* version_local;
+  int32_t version_slot;
 };
 
 __global__ void psb_signal_kernel(const __grid_constant__ SignalArgs a) {
   __threadfence_system();
   const int t = threadIdx.x;
+  uint64_t seen = 0;
+  if (a.version_local != nullptr) seen = ld_relaxed_sys_u64(a.version_local + SIG_SEEN_VERSION);
   if (t < a.n) {
     if (a.extra_base != nullptr && a.targets[t] != nullptr) st_release_sys(a.targets[t] + a.extra_slot, a.extra_value);
+    if (a.version_local != nullptr && a.targets[t] != nullptr) st_release_sys(a.targets[t] + a.version_slot, seen);
     if (a.targets[t] != nullptr) st_release_sys(a.targets[t] + a.slot, a.value);
   }
+  if (a.version_local != nullptr && t == 0)
+    st_release_sys(a.version_local + SIG_SEEN_VERSION, ld_acquire_sys(a.version_local + SIG_VERSION));
 }
 
 __global__ void psb_wait_kernel(const uint64_t* signal_local, int slot0, uint32_t mask, uint64_t want,
@@ -633,9 +644,30 @@ __global__ void psb_wait_kernel(const uint64_t* signal_local, int slot0, uint32_
 
 // async PS: wait until `quota` candidate workers (ANY source, README.md:65-70) have a gradient newer
 // than what was consumed.  Workers that posted the DONE epoch are reported in out[40] and never chosen.
+// The whole server iteration is device-resident: this kernel also
+//   * opens the consistent-read sequence lock (SIG_STAGE_BEGIN = version on every rank) iff something was selected,
+//   * records the staleness of every selected gradient (updates applied since the parameters it was computed on):
+//     out[44 + r] = (version - 1) - SIG_GRAD_VERSION[r],
+// so the host never has to look at the result before queueing the update kernel and the next select.
 #define PSB_DONE_EPOCH (1ull << 62)
-__global__ void psb_select_kernel(const uint64_t* signal_local, uint64_t* consumed, uint32_t cand_mask, int quota,
-                                  uint64_t* out, unsigned long long timeout_ns) {
+struct SelectArgs {
+  const uint64_t* signal_local;
+  uint64_t* consumed;
+  uint64_t* out;
+  uint64_t* begin_targets[PSB_MAX_RANKS];   // every rank's signal pad (consistent=True) or all nullptr
+  int32_t nbegin;
+  uint32_t cand_mask;
+  int32_t quota;
+  uint64_t version;                          // the version the following update kernel will publish
+  unsigned long long timeout_ns;
+};
+
+__global__ void psb_select_kernel(const __grid_constant__ SelectArgs a) {
+  const uint64_t* signal_local = a.signal_local;
+  uint64_t* consumed = a.consumed;
+  uint64_t* out = a.out;
+  const uint32_t cand_mask = a.cand_mask;
+  const int quota = a.quota;
   const int t = threadIdx.x;   // one warp
   uint64_t* err = const_cast<uint64_t*>(signal_local) + SIG_ERROR;
   unsigned long long t0 = 0;
@@ -654,7 +686,7 @@ __global__ void psb_select_kernel(const uint64_t* signal_local, uint64_t* consum
     unsigned long long now;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
     if (t0 == 0) t0 = now;
-    bool bad = (now - t0 > timeout_ns) || ld_relaxed_sys_u64(err) != 0;
+    bool bad = (now - t0 > a.timeout_ns) || ld_relaxed_sys_u64(err) != 0;
     if (__any_sync(0xffffffffu, bad)) {
       if (t == 0) {
         st_release_sys(err, 2ull);
@@ -681,13 +713,76 @@ __global__ void psb_select_kernel(const uint64_t* signal_local, uint64_t* consum
   if (chosen >> t & 1u) {
     consumed[t] = e;
     out[2 + t] = e;
+    const uint64_t gv = ld_acquire_sys(signal_local + SIG_GRAD_VERSION + t);
+    out[44 + t] = a.version - 1 >= gv ? a.version - 1 - gv : 0;
   }
+  if (chosen != 0 && t < a.nbegin && a.begin_targets[t] != nullptr)
+    st_release_sys(a.begin_targets[t] + SIG_STAGE_BEGIN, a.version);   // sequence lock: BEGIN(v) … stores … VERSION(v)
   if (t == 0) {
     if (chosen) consumed[63] = (uint64_t)(31 - __clz(chosen));
     out[0] = chosen;
     out[1] = (uint64_t)cnt;
     out[40] = fin;
+    out[41] = a.version;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// consistent reads (async, README.md:79-81 "a buffered broadcast"): device-side sequence-lock snapshot
+// ------------------------------------------------------------------------------------------
+// The server publishes version v into every rank's STAGING arena between SIG_STAGE_BEGIN = v and SIG_VERSION = v.
+// A worker adopts whole versions only, with no host involvement:
+//   psb_snapshot_fetch   every CTA: read BEGIN / VERSION; if they agree on a version newer than the adopted one, copy its
+//                        slice staging → shadow and re-read BEGIN; any disagreement (publication in progress, torn copy,
+//                        CTAs that saw different versions) vetoes.  The last CTA writes the verdict: status = v or 0.
+//   psb_snapshot_commit  if status != 0: shadow → live parameter arena (purely local, the server never writes there), and the
+//                        adopted version becomes v.  A vetoed attempt leaves the live parameters on the previous whole version.
+struct SnapshotArgs {
+  const uint64_t* signal_local;
+  const uint4* stage;
+  uint4* shadow;
+  uint4* params;
+  size_t nvec;                   // 16-byte vectors
+  unsigned long long* scratch;   // [0] veto  [1] min version  [2] max version  [3] CTAs done  [4] status  [5] adopted version
+};
+
+__global__ void __launch_bounds__(256) psb_snapshot_fetch(const __grid_constant__ SnapshotArgs a) {
+  __shared__ unsigned long long s_v;
+  __shared__ int s_go;
+  if (threadIdx.x == 0) {
+    const uint64_t vb = ld_acquire_sys(a.signal_local + SIG_STAGE_BEGIN), ve = ld_acquire_sys(a.signal_local + SIG_VERSION);
+    s_v = ve;
+    s_go = (vb == ve) && (ve != a.scratch[5]) && (ve != 0);
+  }
+  __syncthreads();
+  const unsigned long long v = s_v;
+  bool veto = !s_go;
+  if (s_go) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.nvec; i += (size_t)gridDim.x * blockDim.x)
+      a.shadow[i] = ld_sys_v4(a.stage + i);       // coherent loads: the server's multimem.st / peer stores land here
+    __syncthreads();
+    if (threadIdx.x == 0) veto = ld_acquire_sys(a.signal_local + SIG_STAGE_BEGIN) != v;
+  }
+  if (threadIdx.x == 0) {
+    if (veto) atomicOr(a.scratch + 0, 1ull);
+    atomicMin(a.scratch + 1, v);
+    atomicMax(a.scratch + 2, v);
+    __threadfence();
+    if (atomicAdd(a.scratch + 3, 1ull) == gridDim.x - 1) {
+      __threadfence();
+      const bool ok = a.scratch[0] == 0 && a.scratch[1] == a.scratch[2];
+      a.scratch[4] = ok ? a.scratch[1] : 0ull;
+      a.scratch[0] = 0, a.scratch[1] = ~0ull, a.scratch[2] = 0, a.scratch[3] = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) psb_snapshot_commit(const __grid_constant__ SnapshotArgs a) {
+  const unsigned long long v = a.scratch[4];
+  if (v == 0) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.nvec; i += (size_t)gridDim.x * blockDim.x)
+    a.params[i] = a.shadow[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.scratch[5] = v;     // stream-ordered: the next fetch reads it after this kernel
 }
 
 template <int KIND, int WIRE, int OPT>
@@ -757,7 +852,8 @@ int psb_update_max_grid(int kind, int wire, int opt) {
 }
 
 void psb_launch_signal(cudaStream_t s, uint64_t* const* targets, int ntargets, int slot, uint64_t value,
-                       uint64_t* extra_slot_base, int extra_slot, uint64_t extra_value) {
+                       uint64_t* extra_slot_base, int extra_slot, uint64_t extra_value, uint64_t* version_local,
+                       int version_slot) {
   SignalArgs a{};
   a.n = ntargets;
   for (int i = 0; i < ntargets && i < PSB_MAX_RANKS; ++i) a.targets[i] = targets[i];
@@ -766,8 +862,27 @@ void psb_launch_signal(cudaStream_t s, uint64_t* const* targets, int ntargets, i
   a.extra_base = extra_slot_base;
   a.extra_slot = extra_slot;
   a.extra_value = extra_value;
+  a.version_local = version_local;
+  a.version_slot = version_slot;
   psb_signal_kernel<<<1, 32, 0, s>>>(a);
   psb_count_launch(1);
+}
+
+void psb_launch_snapshot(cudaStream_t s, const uint64_t* signal_local, const void* stage, void* shadow, void* params, size_t nbytes,
+                         unsigned long long* scratch, int attempts, int num_sms) {
+  SnapshotArgs a{};
+  a.signal_local = signal_local;
+  a.stage = reinterpret_cast<const uint4*>(stage);
+  a.shadow = reinterpret_cast<uint4*>(shadow);
+  a.params = reinterpret_cast<uint4*>(params);
+  a.nvec = nbytes / 16;
+  a.scratch = scratch;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_sms * 4, (a.nvec + 255) / 256));
+  for (int i = 0; i < attempts; ++i) {
+    psb_snapshot_fetch<<<grid, 256, 0, s>>>(a);
+    psb_snapshot_commit<<<grid, 256, 0, s>>>(a);
+    psb_count_launch(2);
+  }
 }
 
 void psb_launch_wait(cudaStream_t s, const uint64_t* signal_local, int slot0, uint32_t mask, uint64_t want,
@@ -777,7 +892,18 @@ void psb_launch_wait(cudaStream_t s, const uint64_t* signal_local, int slot0, ui
 }
 
 void psb_launch_select(cudaStream_t s, const uint64_t* signal_local, uint64_t* consumed, uint32_t cand_mask,
-                       int quota, uint64_t* out, unsigned long long timeout_ns) {
-  psb_select_kernel<<<1, 32, 0, s>>>(signal_local, consumed, cand_mask, quota, out, timeout_ns);
+                       int quota, uint64_t* out, unsigned long long timeout_ns, uint64_t version,
+                       uint64_t* const* begin_targets, int nbegin) {
+  SelectArgs a{};
+  a.signal_local = signal_local;
+  a.consumed = consumed;
+  a.out = out;
+  a.cand_mask = cand_mask;
+  a.quota = quota;
+  a.version = version;
+  a.timeout_ns = timeout_ns;
+  a.nbegin = nbegin;
+  for (int i = 0; i < nbegin && i < PSB_MAX_RANKS; ++i) a.begin_targets[i] = begin_targets[i];
+  psb_select_kernel<<<1, 32, 0, s>>>(a);
   psb_count_launch(1);
 }

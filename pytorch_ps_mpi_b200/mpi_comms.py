@@ -199,9 +199,17 @@ def igather(obj, name="", root: int = 0, level: int = 0):
     """
     tr = _tp.get_transport()
     t = [time.time()]
-    send, _ = serialization.dumps_framed(obj, level=level)     # level 0: serialise + frame in one buffer
-    t += [time.time()]
-    t += [time.time()]
+    if level <= 0:
+        # level 0: serialise + frame in ONE pass over one buffer — there is no separate compression stage to time, so
+        # compress_time is reported as exactly 0.0 (the reference's level-0 blosc pass is a memcpy, mpi_comms.py:18-26)
+        send, _ = serialization.dumps_framed(obj, level=0)
+        t += [time.time()]
+        t += [t[-1]]
+    else:
+        raw = serialization.dumps(obj)                          # pickle_time: the serialisation alone
+        t += [time.time()]
+        send = serialization.frame(raw, level=level)            # compress_time: byte-shuffle + deflate
+        t += [time.time()]
     max_bytes[name] = max(max_bytes.get(name, 0), len(send))
     tag = _next_tag()
     t += [time.time()]

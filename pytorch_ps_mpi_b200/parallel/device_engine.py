@@ -248,7 +248,15 @@ class DeviceEngine:
         self._select_out = torch.zeros(64, dtype=torch.int64, device=self.device)
         self._select_host = torch.zeros(64, dtype=torch.int64).pin_memory()
         self._async_done_workers: set = set()
+        self._async_depth = max(1, int(os.environ.get("PSB200_ASYNC_DEPTH", "4")))
+        self._async_ring = [{"host": torch.zeros(64, dtype=torch.int64).pin_memory(), "event": torch.cuda.Event(), "version": 0}
+                            for _ in range(self._async_depth + 1)]
+        self._async_pending: list = []
+        self._async_i = 0
+        self._async_applied = 0
+        self._async_last = {"contributors": [], "param_version": 0, "staleness": {}, "updates_applied": 0}
         self._snap_version = 0
+        self._snap_shadow = None
         self._step_hyp = None
         self._update_spans: list = []
         # device-timeout surfacing: an async copy of SIG_ERROR into pinned memory every few steps, read one poll late
@@ -672,14 +680,17 @@ class DeviceEngine:
                 if not self._first_flush_done:       # no parameter produced a gradient at all
                     self._first_flush_done = True
                     self._before_first_encode()
-                # publish "gradient `epoch` is in my arena"
-                self.m.signal([sig_base[0]], self.m.SIG_GRAD_READY + self.rank, epoch)
+                # publish "gradient `epoch` is in my arena" + the parameter version it was computed on (staleness accounting)
+                self.m.signal([sig_base[0]], self.m.SIG_GRAD_READY + self.rank, epoch, -1, 0, 0,
+                              self.arena.local_ptr + self.off_signal, self.m.SIG_GRAD_VERSION + self.rank)
                 self.launches += 1
             if self.consistent:
                 data["param_version"] = self._snapshot()
             self._end_of_step(data)
             return data                      # never waits for NEW parameters (inconsistent reads unless consistent=True)
-        # ---- rank 0: the server ----
+        # ---- rank 0: the server — device-resident: select → (open sequence lock) → update → ack are all queued without
+        # looking at their result; results come back through a ring of pinned slots, read when their event has completed.
+        # The host only blocks when it is `_async_depth` iterations AHEAD of the GPU (never the other way round). ----
         self._fired = set()
         self._keep = []
         self._next_chunk = 0
@@ -687,72 +698,103 @@ class DeviceEngine:
         for it in self._chunk_items:
             it.clear()
         n = self.size
+        self._async_harvest(block=False)
         cand = ((1 << n) - 1) & ~1
         for r in self._async_done_workers:
             cand &= ~(1 << r)
         if cand == 0:
+            self._async_harvest(block=True, everything=True)
+            data.update(self._async_last)
             data["ps_done"] = True
+            data["engine"] = "device"
             return data
         quota = max(1, min(o.quota, bin(cand).count("1")))
         t0 = time.time()
+        slot = self._async_ring[self._async_i % len(self._async_ring)]
+        self._async_i += 1
+        self.version += 1
+        hyp = self._hypers()
+        self.m.select_ready(sig_base[0], self._consumed.data_ptr(), cand, quota, self._select_out.data_ptr(),
+                            self.timeout_s, self.version, sig_base if self.consistent else [], self._cs)
+        self.plan.launch(o.steps, hyp, 0, 1.0, 0, 1, 0, self.version, self._select_out.data_ptr(),
+                         1 if o.average else 0, 0, self.timeout_s, stream=self._cs)
+        self.launches += 2
         with torch.cuda.stream(cs):
-            self.m.select_ready(sig_base[0], self._consumed.data_ptr(), cand, quota,
-                                self._select_out.data_ptr(), self.timeout_s)
-            self.version += 1
-            if self.consistent:   # sequence lock: BEGIN(v) … stores … VERSION(v); a reader needs BEGIN == VERSION around its copy
-                self.m.signal(sig_base, self.m.SIG_VERSION + 1, self.version)
-                self.launches += 1
-            self.plan.launch(o.steps, self._hypers(), 0, 1.0, 0, 1, 0, self.version,
-                             self._select_out.data_ptr(), 1 if o.average else 0, 0, self.timeout_s)
-            self.launches += 2
-            self._select_host.copy_(self._select_out, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(cs)
-        done.synchronize()                   # the server loop is host-driven (it has nothing else to do)
+            slot["host"].copy_(self._select_out, non_blocking=True)
+        slot["event"].record(cs)
+        slot["version"] = self.version
+        self._async_pending.append(slot)
+        if len(self._async_pending) >= self._async_depth:
+            self._async_harvest(block=True)          # the host is a full ring ahead of the device: wait for the oldest
         data["comm_wait"] = time.time() - t0
-        mask = int(self._select_host[0].item())
-        finished = int(self._select_host[40].item())
-        for r in range(n):
-            if finished >> r & 1:
-                self._async_done_workers.add(r)
-        data["contributors"] = [r for r in range(n) if mask >> r & 1]
-        if not data["contributors"]:
-            if self.consistent:              # nothing was written: close the sequence lock again
-                with torch.cuda.stream(cs):
-                    self.m.signal(sig_base, self.m.SIG_VERSION + 1, self.version - 1)
-            self.version -= 1                # nothing was applied
-            for gi in range(len(self._group_steps)):
-                self._group_steps[gi] -= 1
-        data["param_version"] = self.version
-        data["ps_done"] = len(self._async_done_workers) >= n - 1 and not data["contributors"]
+        data.update(self._async_last)                # contributors / staleness / version of the latest COMPLETED update
+        data["param_version_queued"] = self.version
+        data["ps_done"] = False
         self._epoch += 1
         data["engine"] = "device"
         return data
 
-    # ------------------------------------------------------------------ consistent reads (async)
-    def _snapshot(self, max_tries: int = 1000) -> int:
-        """Adopt the newest COMPLETE parameter version from the staging copy (host-driven sequence lock).
+    def _async_harvest(self, block: bool, everything: bool = False):
+        """Consume completed server iterations in order (``block``: wait for the oldest; ``everything``: drain)."""
+        n = self.size
+        while self._async_pending:
+            slot = self._async_pending[0]
+            if not slot["event"].query():
+                if not block:
+                    return
+                slot["event"].synchronize()
+            self._async_pending.pop(0)
+            h = slot["host"]
+            mask, cnt, finished = int(h[0]), int(h[1]), int(h[40])
+            for r in range(n):
+                if finished >> r & 1:
+                    self._async_done_workers.add(r)
+            contributors = [r for r in range(n) if mask >> r & 1]
+            if cnt == 0:
+                # nothing was applied (every worker finished, or the select timed out): the kernels returned early, the
+                # sequence lock was never opened, no version was published — take the host-side prediction back
+                self.version -= 1
+                for gi in range(len(self._group_steps)):
+                    self._group_steps[gi] -= 1
+            else:
+                self._async_applied += 1
+                self._async_last = {"contributors": contributors, "param_version": slot["version"],
+                                    "staleness": {r: int(h[44 + r]) for r in contributors},
+                                    "updates_applied": self._async_applied}
+            if not everything:
+                block = False                        # at most one blocking wait per call
 
-        The server writes ``BEGIN = v`` before and ``VERSION = v`` after publishing version ``v`` into the staging
-        arena.  A copy is a consistent snapshot iff ``BEGIN == VERSION`` before it starts and ``BEGIN`` is unchanged
-        after it finishes; otherwise it is retried.  Costs two tiny device→host reads per step — the price of
-        ``consistent=True`` (the default inconsistent mode never synchronises)."""
+    # ------------------------------------------------------------------ consistent reads (async)
+    def _snapshot(self, block: bool = False) -> int:
+        """Adopt the newest COMPLETE parameter version from the staging copy — entirely on the device.
+
+        The server writes ``BEGIN = v`` before and ``VERSION = v`` after publishing version ``v`` into the staging arena.
+        ``psb_snapshot_fetch`` copies staging → a local shadow buffer iff ``BEGIN == VERSION`` before and ``BEGIN`` is unchanged
+        after (every CTA must agree); ``psb_snapshot_commit`` then copies shadow → the live parameter arena.  A vetoed attempt
+        leaves the parameters on the previous whole version, so the model never reads a torn set.  No host reads: the adopted
+        version comes back through an async copy into pinned memory and is reported one call late (``block=True``: wait)."""
         m = self.m
-        cs = self.comm_stream
-        for _ in range(max_tries):
-            v_end = int(self.signal[m.SIG_VERSION].item())
-            v_begin = int(self.signal[m.SIG_VERSION + 1].item())
-            if v_begin != v_end:                       # the server is in the middle of publishing v_begin
-                time.sleep(20e-6)
-                continue
-            if v_end == self._snap_version:
-                return v_end                           # nothing new since the last snapshot
-            self.param_arena.copy_(self.stage_arena)
-            torch.cuda.current_stream(self.device).synchronize()
-            if int(self.signal[m.SIG_VERSION + 1].item()) == v_end:
-                self._snap_version = v_end
-                return v_end
-        raise RuntimeError("consistent snapshot did not stabilise (server publishing faster than one copy)")
+        cur = torch.cuda.current_stream(self.device)
+        if self._snap_shadow is None:
+            self._snap_shadow = torch.empty_like(self.param_arena)
+            self._snap_scratch = torch.tensor([0, -1, 0, 0, 0, 0], dtype=torch.int64, device=self.device)
+            self._snap_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self._snap_event = None
+        nbytes = self.param_arena.numel() * self.psz
+        m.snapshot(self.arena.local_ptr + self.off_signal, self.stage_arena.data_ptr(), self._snap_shadow.data_ptr(),
+                   self.param_arena.data_ptr(), nbytes, self._snap_scratch.data_ptr(),
+                   int(os.environ.get("PSB200_SNAPSHOT_ATTEMPTS", "2")), cur.cuda_stream)
+        self.launches += 4
+        if self._snap_event is None or self._snap_event.query() or block:
+            if self._snap_event is not None and self._snap_event.query():
+                self._snap_version = int(self._snap_host[0])
+            self._snap_host.copy_(self._snap_scratch[5:6], non_blocking=True)
+            self._snap_event = torch.cuda.Event()
+            self._snap_event.record(cur)
+        if block:
+            self._snap_event.synchronize()
+            self._snap_version = int(self._snap_host[0])
+        return self._snap_version
 
     # -------------------------------------------------------------- broadcast-gated GEMM support
     def register_gate(self, layer) -> None:
@@ -807,7 +849,7 @@ class DeviceEngine:
             torch.cuda.synchronize(self.device)
             self.world.barrier()
             if self.consistent:              # everybody leaves with the server's final parameters
-                self._snapshot()
+                self._snapshot(block=True)
         finally:
             # parameters keep their arena views alive; detach them so the block can be freed
             with torch.no_grad():

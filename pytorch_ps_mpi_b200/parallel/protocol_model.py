@@ -36,7 +36,7 @@ import sys
 from dataclasses import dataclass, field
 from typing import Dict, FrozenSet, Iterable, List, Optional, Sequence, Tuple
 
-__all__ = ["Violation", "Result", "Model", "build_ps", "build_allgather", "build_async", "build_stem_pipeline", "build_stem_wgrad_pipeline",
+__all__ = ["Violation", "Result", "Model", "build_ps", "build_ps_unpipelined", "build_allgather", "build_allgather_unpipelined", "build_async", "build_stem_pipeline", "build_stem_wgrad_pipeline",
            "check", "MODES"]
 
 DONE = 1 << 62          # device_engine._DONE_EPOCH / PSB_DONE_EPOCH
@@ -485,8 +485,77 @@ def _backward(m: Model, r: int, e: int, comp: list, comm: list, expect, *, prev_
     comm.append(("rel", [(("gradB", r, e), "r", None), (("wire", r), "w", e)]))
 
 
+def _backward_chunks(m: Model, r: int, e: int, comp: list, *, prev_done: bool):
+    """forward + backward of step e on the compute stream, seen by the PIPELINED engine: the arena is two chunks, A (the
+    layers whose gradients come first) and B.  Forward reads both; backward reads A's weights while it produces gradA
+    (hook fires → ``mid``), then B's weights while it produces gradB (→ ``bwd``)."""
+    if prev_done and e > 1:
+        comp.append(("wev", ("done", r, e - 1)))                   # _flush_chunk: at most one step ahead of the comm stream
+    comp.append(("acq", [(("paramsA", r), "r", e - 1), (("paramsB", r), "r", e - 1), (("gradA", r, e), "w", None)]))
+    comp.append(("rel", [(("paramsA", r), "r", None), (("gradA", r, e), "w", e)]))
+    comp.append(("rec", ("mid", r, e)))
+    comp.append(("acq", [(("gradB", r, e), "w", None)]))
+    comp.append(("rel", [(("paramsB", r), "r", None), (("gradB", r, e), "w", e)]))
+    comp.append(("rec", ("bwd", r, e)))
+
+
+def _chunk_final(m: Model, n: int, epochs: int):
+    def final(st, mm):
+        for p in range(n):
+            for c in ("paramsA", "paramsB"):
+                if st[2][mm.res((c, p))] != epochs:
+                    return f"rank {p} ends on {c} version {st[2][mm.res((c, p))]}, expected {epochs}"
+    m.final_checks.append(final)
+
+
 def build_ps(n: int, epochs: int, drop: Optional[str] = None) -> Model:
-    """``mode='ps'``: rank 0 gathers, updates and publishes (``DeviceEngine.step``; ``psb_update_kernel`` signal_mode 1).
+    """``mode='ps'`` with the per-chunk update pipeline (``DeviceEngine._flush_chunk``): rank 0 gathers / updates /
+    publishes chunk A as soon as every rank's GRAD_READY progress value says "chunk A of step e is in my arena" — while
+    every rank's backward is still running on chunk B — then chunk B, then raises PARAMS_READY.  GRAD_READY carries the
+    monotone value ``(e-1)*2 + chunk + 1``.
+
+    ``drop``: ``'params_ready'`` (workers do not wait for the broadcast), ``'grad_ready'`` (the server does not wait for
+    chunk B's flags), ``'grad_ready_a'`` (nor for chunk A's), ``'bwd_event'`` (the last encode does not wait for backward),
+    ``'mid_event'`` (chunk A is encoded / flagged before its gradients exist), ``'progress_off_by_one'`` (chunk B's update
+    waits for chunk A's value) — each must be caught."""
+    m = Model()
+    prog = lambda e, c: (e - 1) * 2 + c + 1      # noqa: E731
+    for r in range(n):
+        comp, comm = [], []
+        for e in range(1, epochs + 1):
+            if r != 0 and e > 1 and drop != "params_ready":
+                comp.append(("wait", ("PARAMS_READY", r), e - 1))      # psb_wait_kernel (or the gated first GEMM)
+            if r == 0 and e > 1:
+                comp.append(("wev", ("done", 0, e - 1)))               # cur.wait_event(done)
+            _backward_chunks(m, r, e, comp, prev_done=(r != 0))
+            for c, (ev, grad, wire, par) in enumerate((("mid", "gradA", "wireA", "paramsA"), ("bwd", "gradB", "wire", "paramsB"))):
+                if not ((drop == "bwd_event" and ev == "bwd") or (drop == "mid_event" and ev == "mid")):
+                    comm.append(("wev", (ev, r, e)))
+                comm.append(("acq", [((grad, r, e), "r", e), ((wire, r), "w", None)]))      # psb_encode_kernel, chunk c
+                comm.append(("rel", [((grad, r, e), "r", None), ((wire, r), "w", e)]))
+                if r != 0:
+                    comm.append(("sig", ("GRAD_READY", 0, r), prog(e, c)))                    # its last CTA raises the flag
+                    continue
+                skip = (drop == "grad_ready" and c == 1) or (drop == "grad_ready_a" and c == 0)
+                if not skip:
+                    want = prog(e, 0) if (drop == "progress_off_by_one" and c == 1) else prog(e, c)
+                    for p in range(1, n):
+                        comm.append(("wait", ("GRAD_READY", 0, p), want))
+                reads = [((wire, p), "r", e) for p in range(n)]                               # psb_update_kernel, chunk c
+                comm.append(("acq", reads + [((par, p), "w", None) for p in range(n)]))
+                comm.append(("rel", [(k, md, None) for k, md, _ in reads] + [((par, p), "w", e) for p in range(n)]))
+            if r == 0:
+                for p in range(n):
+                    comm.append(("sig", ("PARAMS_READY", p), e))                              # raised by the LAST chunk's kernel
+            comm.append(("rec", ("done", r, e)))
+        m.add(f"r{r}.compute", comp)
+        m.add(f"r{r}.comm", comm)
+    _chunk_final(m, n, epochs)
+    return m
+
+
+def build_ps_unpipelined(n: int, epochs: int, drop: Optional[str] = None) -> Model:
+    """``mode='ps'``, ``pipeline=False``: rank 0 gathers, updates and publishes in ONE launch inside ``step()``.
 
     ``drop``: ``'params_ready'`` (workers do not wait for the broadcast), ``'grad_ready'`` (the server does not
     wait for the gradients), ``'bwd_event'`` (the last encode does not wait for backward) — each must be caught."""
@@ -527,7 +596,47 @@ def build_ps(n: int, epochs: int, drop: Optional[str] = None) -> Model:
 
 
 def build_allgather(n: int, epochs: int, drop: Optional[str] = None) -> Model:
-    """``mode='allgather'``: every rank pulls all wire tiles and updates its own replica (signal_mode 2).
+    """``mode='allgather'`` with the per-chunk pipeline: every rank pulls all ranks' wire tiles of chunk A and updates chunk A
+    of its own replica while backward still runs on chunk B, then chunk B (signal_mode 2 on the last chunk).
+
+    ``drop``: ``'consumed'`` (re-encode without waiting for the readers), ``'grad_ready'`` (chunk B's flags),
+    ``'grad_ready_a'`` (chunk A's flags)."""
+    m = Model()
+    prog = lambda e, c: (e - 1) * 2 + c + 1      # noqa: E731
+    for r in range(n):
+        comp, comm = [], []
+        peers = [p for p in range(n) if p != r]
+        for e in range(1, epochs + 1):
+            if e > 1:
+                comp.append(("wev", ("done", r, e - 1)))               # cur.wait_event(done)
+            _backward_chunks(m, r, e, comp, prev_done=False)
+            for c, (ev, grad, wire, par) in enumerate((("mid", "gradA", "wireA", "paramsA"), ("bwd", "gradB", "wire", "paramsB"))):
+                comm.append(("wev", (ev, r, e)))
+                if c == 0 and e > 1 and drop != "consumed":
+                    comm.extend(("wait", ("CONSUMED", r, p), e - 1) for p in peers)          # _before_first_encode
+                comm.append(("acq", [((grad, r, e), "r", e), ((wire, r), "w", None)]))
+                comm.append(("rel", [((grad, r, e), "r", None), ((wire, r), "w", e)]))
+                for p in peers:
+                    comm.append(("sig", ("GRAD_READY", p, r), prog(e, c)))
+                if not ((drop == "grad_ready" and c == 1) or (drop == "grad_ready_a" and c == 0)):
+                    for p in peers:
+                        comm.append(("wait", ("GRAD_READY", r, p), prog(e, c)))
+                reads = [((wire, p), "r", e) for p in range(n)]
+                comm.append(("acq", reads + [((par, r), "w", None)]))
+                comm.append(("rel", [(k, md, None) for k, md, _ in reads] + [((par, r), "w", e)]))
+            for p in range(n):
+                comm.append(("sig", ("CONSUMED", p, r), e))
+            comm.append(("rec", ("done", r, e)))
+        m.add(f"r{r}.compute", comp)
+        m.add(f"r{r}.comm", comm)
+    _chunk_final(m, n, epochs)
+    return m
+
+
+def build_allgather_unpipelined(n: int, epochs: int, drop: Optional[str] = None) -> Model:
+    """``mode='allgather'``, ``pipeline=False`` (one chunk): every rank pulls all wire tiles and updates its own replica in one
+    launch (signal_mode 2).  This is where the CONSUMED wait is load-bearing: with >= 2 pipelined chunks the in-order comm
+    streams already imply it (the checker accepts the pipelined model without it), with one chunk they do not.
 
     ``drop``: ``'consumed'`` (re-encode without waiting for the readers), ``'grad_ready'``."""
     m = Model()
@@ -561,6 +670,7 @@ def build_allgather(n: int, epochs: int, drop: Optional[str] = None) -> Model:
                 return f"rank {p} ends on parameter version {st[2][mm.res(('params', p))]}, expected {epochs}"
     m.final_checks.append(final)
     return m
+
 
 
 def build_async(n: int, epochs: int, quota: int = 1, consistent: bool = False, drop: Optional[str] = None) -> Model:
@@ -720,7 +830,8 @@ def build_stem_wgrad_pipeline(n: int = 1, epochs: int = 4, drop: Optional[str] =
     return m
 
 
-MODES = {"ps": build_ps, "allgather": build_allgather, "async": build_async, "stem_pipeline": build_stem_pipeline,
+MODES = {"ps": build_ps, "ps_unpipelined": build_ps_unpipelined, "allgather": build_allgather,
+         "allgather_unpipelined": build_allgather_unpipelined, "async": build_async, "stem_pipeline": build_stem_pipeline,
          "stem_wgrad_pipeline": build_stem_wgrad_pipeline}
 
 

@@ -557,13 +557,17 @@ class MPI_PS(torch.optim.Optimizer):
             self._async_param_sends = []
 
     def serve(self, max_updates: Optional[int] = None) -> int:
-        """Async PS loop for rank 0: apply updates until every worker called ``close()``."""
+        """Async PS loop for rank 0: apply updates until every worker called ``close()``; returns the number of updates
+        APPLIED (the device engine queues server iterations ahead of the GPU, so that is not the number of ``step()`` calls)."""
         n = 0
-        while max_updates is None or n < max_updates:
+        while True:
             _, data = self.step()
-            if data.get("ps_done"):
+            if "updates_applied" in data:
+                n = data["updates_applied"]
+            elif not data.get("ps_done"):
+                n += 1
+            if data.get("ps_done") or (max_updates is not None and n >= max_updates):
                 break
-            n += 1
         return n
 
     # --------------------------------------------------------------------- checkpointing

@@ -115,6 +115,20 @@ def test_engine_two_ranks_one_gpu(mode, optim, coding, dtype):
     spawn(_mp.gpu_train, 2, (mode, optim, coding, dtype), env=ONE_GPU, timeout=240)
 
 
+@pytest.mark.parametrize("mode,optim,coding,dtype", [("ps", "sgd", "identity", "fp32"), ("ps", "adam", "cast", "bf16"),
+                                                      ("ps", "sgd", "topk", "bf16"), ("allgather", "sgd", "scale", "fp32"),
+                                                      ("allgather", "adam", "topk", "fp32")])
+def test_engine_pipelined_chunks_two_ranks_one_gpu(mode, optim, coding, dtype):
+    """Per-chunk pipeline: 8 KB chunks split the 4-tensor MLP into several chunks (chunks hold whole parameters), each with
+    its own encode launch, progress flag value and update launch (/root/reference/ps.py:140-148,159-162 per chunk)."""
+    env = dict(ONE_GPU, PSB200_CHUNK_BYTES="8192", PSB200_EXPECT_CHUNKS="2")
+    spawn(_mp.gpu_train, 2, (mode, optim, coding, dtype, "auto", 128), env=env, timeout=240)
+
+
+def test_engine_unpipelined_two_ranks_one_gpu():
+    spawn(_mp.gpu_train, 2, ("ps", "sgd", "identity", "bf16"), env=dict(ONE_GPU, PSB200_PIPELINE="0"), timeout=240)
+
+
 def test_engine_three_ranks_allgather_one_gpu():
     spawn(_mp.gpu_train, 3, ("allgather", "adam", "identity", "fp32"), env=ONE_GPU, timeout=240)
 
@@ -134,6 +148,14 @@ def test_engine_async_consistent_reads_one_gpu():
 def test_engine_multi_gpu(mode, optim, coding, dtype):
     n = min(torch.cuda.device_count(), 4)
     spawn(_mp.gpu_train, n, (mode, optim, coding, dtype), env={"PSB200_DEVICE_TIMEOUT": "20"}, timeout=300)
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("reduce", ["auto", "p2p"])
+def test_big_bf16_arena_multi_gpu(reduce):
+    """>= 50 M-element bf16 arena, many chunks; auto = multimem.ld_reduce at N >= 4 (bf16 wire), p2p = rank-ordered pull."""
+    n = min(torch.cuda.device_count(), 8)
+    spawn(_mp.gpu_train_big, n, (reduce,), env={"PSB200_DEVICE_TIMEOUT": "30"}, timeout=420)
 
 
 def test_checkpoint_resume_two_ranks_one_gpu():

@@ -12,8 +12,12 @@ from pytorch_ps_mpi_b200.parallel import protocol_model as pm
     ("ps", 2, 3, {}),
     ("ps", 3, 2, {}),
     ("ps", 4, 1, {}),
+    ("ps_unpipelined", 3, 2, {}),
     ("allgather", 2, 3, {}),
     ("allgather", 3, 2, {}),
+    ("allgather_unpipelined", 3, 2, {}),
+    # with >= 2 pipelined chunks the in-order comm streams already imply the CONSUMED wait (it is load-bearing for 1 chunk)
+    ("allgather", 2, 2, {"drop": "consumed"}),
     ("async", 2, 3, {}),
     ("async", 3, 2, {"quota": 1}),
     ("async", 3, 2, {"quota": 2}),
@@ -34,9 +38,18 @@ def test_protocol_holds(mode, n, epochs, kw):
     ("ps", 2, 2, {"drop": "grad_ready"}, {"race", "version"}),
     # the last encode launch does not wait for backward to finish
     ("ps", 2, 1, {"drop": "bwd_event"}, {"race", "version"}),
+    # pipelined: the server updates chunk A / chunk B before every rank's flag carries that chunk's progress value
+    ("ps", 2, 2, {"drop": "grad_ready_a"}, {"race", "version"}),
+    ("ps", 2, 2, {"drop": "progress_off_by_one"}, {"race", "version"}),
+    # pipelined: chunk A is encoded and flagged before backward produced its gradients
+    ("ps", 2, 1, {"drop": "mid_event"}, {"race", "version"}),
+    ("ps_unpipelined", 2, 2, {"drop": "params_ready"}, {"race", "version"}),
+    ("ps_unpipelined", 2, 2, {"drop": "grad_ready"}, {"race", "version"}),
     # a rank re-encodes while a peer still reads its previous wire tiles
-    ("allgather", 2, 2, {"drop": "consumed"}, {"race", "version"}),
+    ("allgather_unpipelined", 2, 2, {"drop": "consumed"}, {"race", "version"}),
+    ("allgather_unpipelined", 2, 2, {"drop": "grad_ready"}, {"race", "version"}),
     ("allgather", 2, 2, {"drop": "grad_ready"}, {"race", "version"}),
+    ("allgather", 2, 2, {"drop": "grad_ready_a"}, {"race", "version"}),
     # async: re-encode before the server consumed the previous gradient
     ("async", 2, 2, {"drop": "ack"}, {"race", "version", "final", "ack"}),
     # async: DONE posted before the last gradient was consumed → the gradient is lost
