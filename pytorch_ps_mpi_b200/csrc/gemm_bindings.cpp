@@ -124,6 +124,8 @@ std::vector<at::Tensor> bn_forward(const at::Tensor& x, c10::optional<at::Tensor
   auto scratch = at::empty({6 * C}, fo);   // sums[2C] | mean | rstd | scale | shift
   float* sp = scratch.data_ptr<float>();
   at::Tensor mean = scratch.narrow(0, 2 * C, C), rstd = scratch.narrow(0, 3 * C, C);
+  // ReLU + training: a 1-bit-per-element mask (y > 0) for the backward, which then never re-reads y
+  at::Tensor mask = (relu && training) ? at::empty({pixels * (C / 8)}, x.options().dtype(at::kByte)) : at::Tensor();
   if (!training) {   // inference: scale/shift from the running statistics
     auto r = (running_var + eps).rsqrt();
     auto sc = gamma.to(at::kFloat) * r;
@@ -132,15 +134,22 @@ std::vector<at::Tensor> bn_forward(const at::Tensor& x, c10::optional<at::Tensor
   }
   psb_bn_forward(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), rp, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
                  sp, sp + 2 * C, sp + 3 * C, sp + 4 * C, sp + 5 * C, running_mean.data_ptr<float>(),
-                 running_var.data_ptr<float>(), pixels, C, (float)eps, (float)momentum, relu ? 1 : 0, training ? 1 : 0);
+                 running_var.data_ptr<float>(), pixels, C, (float)eps, (float)momentum, relu ? 1 : 0, training ? 1 : 0,
+                 mask.defined() ? mask.data_ptr() : nullptr);
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_bn_forward: ", cudaGetErrorString(e));
-  return {y, mean, rstd};
+  return {y, mean, rstd, mask};
 }
 
 // returns (dx, dres or undefined, dgamma, dbeta)
+// `out_dgamma` / `out_dbeta` (optional): where to write the parameter gradients — the PS device engine hands out views of its
+// wire arena (DeviceEngine.grad_out) so these gradients need no encode pass.
 std::vector<at::Tensor> bn_backward(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& y, const at::Tensor& gamma,
-                                    const at::Tensor& mean, const at::Tensor& rstd, bool relu, bool has_res) {
+                                    const at::Tensor& mean, const at::Tensor& rstd, bool relu, bool has_res,
+                                    c10::optional<at::Tensor> out_dgamma, c10::optional<at::Tensor> out_dbeta) {
+  // relu: `y` is either the saved output (bf16, same shape as x) or the forward's 1-bit mask (uint8, numel/8 bytes)
+  const bool masked = relu && y.scalar_type() == at::kByte;
+  if (masked) TORCH_CHECK(y.numel() * 8 == x.numel() && y.is_contiguous(), "bn_backward: mask size mismatch");
   check_nhwc(dy, "dy");
   check_nhwc(x, "x");
   const int C = (int)x.size(1);
@@ -148,12 +157,21 @@ std::vector<at::Tensor> bn_backward(const at::Tensor& dy, const at::Tensor& x, c
   auto dx = at::empty_like(x);
   at::Tensor dres;
   if (has_res) dres = at::empty_like(x);
-  auto dgamma = at::empty_like(gamma), dbeta = at::empty_like(gamma);
+  auto pick = [&](c10::optional<at::Tensor>& o) {
+    if (o.has_value() && o->defined()) {
+      TORCH_CHECK(o->is_cuda() && o->scalar_type() == gamma.scalar_type() && o->numel() == gamma.numel() && o->is_contiguous(),
+                  "bn_backward: out gradient must be a contiguous tensor like gamma");
+      return *o;
+    }
+    return at::empty_like(gamma);
+  };
+  auto dgamma = pick(out_dgamma), dbeta = pick(out_dbeta);
   auto scratch = at::empty({5 * C}, x.options().dtype(at::kFloat));
   float* sp = scratch.data_ptr<float>();
-  psb_bn_backward(c10::cuda::getCurrentCUDAStream().stream(), dy.data_ptr(), x.data_ptr(), relu ? y.data_ptr() : nullptr,
-                  gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), sp, sp + 2 * C, dx.data_ptr(),
-                  has_res ? dres.data_ptr() : nullptr, dgamma.data_ptr(), dbeta.data_ptr(), pixels, C, relu ? 1 : 0);
+  psb_bn_backward(c10::cuda::getCurrentCUDAStream().stream(), dy.data_ptr(), x.data_ptr(),
+                  (relu && !masked) ? y.data_ptr() : nullptr, gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), sp,
+                  sp + 2 * C, dx.data_ptr(), has_res ? dres.data_ptr() : nullptr, dgamma.data_ptr(), dbeta.data_ptr(), pixels, C,
+                  relu ? 1 : 0, masked ? y.data_ptr() : nullptr);
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_bn_backward: ", cudaGetErrorString(e));
   return {dx, dres, dgamma, dbeta};
@@ -269,13 +287,14 @@ std::vector<at::Tensor> bn_forward_presummed(const at::Tensor& x, c10::optional<
   auto y = at::empty_like(x);
   auto scratch = at::empty({4 * C}, x.options().dtype(at::kFloat));   // mean | rstd | scale | shift
   float* sp = scratch.data_ptr<float>();
+  at::Tensor mask = relu ? at::empty({pixels * (C / 8)}, x.options().dtype(at::kByte)) : at::Tensor();
   psb_bn_forward_presummed(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), rp, gamma.data_ptr(), beta.data_ptr(),
                            y.data_ptr(), sums.data_ptr<float>(), sp, sp + C, sp + 2 * C, sp + 3 * C,
                            running_mean.data_ptr<float>(), running_var.data_ptr<float>(), pixels, C, (float)eps, (float)momentum,
-                           relu ? 1 : 0);
+                           relu ? 1 : 0, mask.defined() ? mask.data_ptr() : nullptr);
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_bn_forward_presummed: ", cudaGetErrorString(e));
-  return {y, scratch.narrow(0, 0, C), scratch.narrow(0, C, C)};
+  return {y, scratch.narrow(0, 0, C), scratch.narrow(0, C, C), mask};
 }
 
 // fused stem: x [N,3,H,W] bf16 channels-last, w2d [64,176] bf16 (ops/stem.py layout)
@@ -326,6 +345,26 @@ at::Tensor stem_wgrad(const at::Tensor& x, const at::Tensor& gy) {
   return partial;
 }
 
+// Σ over the per-CTA partials of psb_stem_wgrad_kernel, transposed and cast: [grid,176,64] fp32 → dW2d [64,176] bf16, written
+// into `out` when given (the wire-arena slot of the stem weight: no encode pass) — one kernel instead of sum + t + to.
+at::Tensor stem_wgrad_finalize(const at::Tensor& partial, c10::optional<at::Tensor> out) {
+  TORCH_CHECK(partial.is_cuda() && partial.scalar_type() == at::kFloat && partial.dim() == 3 && partial.size(1) == 176 &&
+                  partial.size(2) == 64 && partial.is_contiguous(), "partial must be [grid,176,64] fp32");
+  at::Tensor o;
+  if (out.has_value() && out->defined()) {
+    TORCH_CHECK(out->is_cuda() && out->scalar_type() == at::kBFloat16 && out->numel() == 64 * 176 && out->is_contiguous(),
+                "out must be a contiguous bf16 tensor of 64*176 elements");
+    o = out->view({64, 176});
+  } else {
+    o = at::empty({64, 176}, partial.options().dtype(at::kBFloat16));
+  }
+  psb_stem_wgrad_finalize_launch(c10::cuda::getCurrentCUDAStream().stream(), partial.data_ptr<float>(), (int)partial.size(0),
+                                 o.data_ptr());
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "psb_stem_wgrad_finalize: ", cudaGetErrorString(e));
+  return o;
+}
+
 at::Tensor im2col_stem(const at::Tensor& x) {
   check_nhwc(x, "x");
   TORCH_CHECK(x.size(1) == 3, "stem input must have 3 channels");
@@ -366,10 +405,14 @@ void bind_gemm(py::module_& m) {
   m.def("stem_fwd", &stem_fwd, py::arg("x"), py::arg("w2d"), py::arg("want_sums") = true, py::arg("flag_ptr") = 0,
         py::arg("epoch") = 0, py::arg("timeout_s") = 30.0,
         "fused implicit-GEMM ResNet stem (+ BN statistics) on tcgen05; flag_ptr/epoch: PARAMS_READY gate of the weight load");
+  m.def("stem_wgrad_finalize", &stem_wgrad_finalize, py::arg("partial"), py::arg("out") = c10::nullopt,
+        "sum the per-CTA partials → dW2d [64,176] bf16 (optionally straight into the PS wire arena)");
   m.def("stem_wgrad", &stem_wgrad, "implicit weight gradient of the stem → per-CTA fp32 partials [grid,176,64]");
   m.def("bnpool_forward", &bnpool_forward, "EXPERIMENTAL: BatchNorm + ReLU + 3x3/s2 max-pool forward in one pass");
   m.def("bnpool_backward", &bnpool_backward, "EXPERIMENTAL: backward of bnpool_forward (no materialised pool gradient)");
-  m.def("bn_backward", &bn_backward, "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");
+  m.def("bn_backward", &bn_backward, py::arg("dy"), py::arg("x"), py::arg("y"), py::arg("gamma"), py::arg("mean"), py::arg("rstd"),
+        py::arg("relu"), py::arg("has_res"), py::arg("out_dgamma") = c10::nullopt, py::arg("out_dbeta") = c10::nullopt,
+        "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");
   m.def("bcast_gemm", &bcast_gemm, py::arg("x"), py::arg("w_ptr"), py::arg("N"), py::arg("K"), py::arg("bias"),
         py::arg("relu"), py::arg("flag_ptr") = 0, py::arg("epoch") = 0, py::arg("timeout_s") = 30.0, py::arg("variant") = 0,
         "tcgen05/TMEM/TMA GEMM whose weight tiles are gated on the PS broadcast epoch flag");

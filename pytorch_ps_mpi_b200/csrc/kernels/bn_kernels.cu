@@ -125,7 +125,8 @@ template <bool RES, bool RELU>
 __global__ void __launch_bounds__(BN_THREADS) psb_bn_apply(const __nv_bfloat16* __restrict__ x,
                                                             const __nv_bfloat16* __restrict__ res,
                                                             const float* __restrict__ scale, const float* __restrict__ shift,
-                                                            __nv_bfloat16* __restrict__ y, BnGeom g) {
+                                                            __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ mask, BnGeom g) {
+  // `mask` (RELU, training): one bit per element, y > 0 — the backward reads this 1/16-size tensor instead of y
   const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
   if (ty >= g.lanes) return;
   float sc[8], sh[8];
@@ -148,14 +149,34 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bn_apply(const __nv_bfloat16* 
       a[j] = v;
     }
     st8(y + off, a);
+    if (RELU && mask != nullptr) {
+      uint32_t m = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m |= (__bfloat162float(__float2bfloat16_rn(a[j])) > 0.f ? 1u : 0u) << j;
+      mask[p * g.groups + tx] = (uint8_t)m;
+    }
   }
 }
 
 // ---- backward -----------------------------------------------------------------------------
-template <bool RELU>
+// ReLU mask of 8 consecutive channels: from the 1-bit mask tensor (MASKED) or from the saved output y
+template <bool MASKED>
+__device__ __forceinline__ uint32_t relu_bits(const __nv_bfloat16* __restrict__ y, const uint8_t* __restrict__ mask, long long p,
+                                              long long off, int groups, int tx) {
+  if (MASKED) return mask[p * groups + tx];
+  float o[8];
+  ld8_stream(y + off, o);
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m |= (o[j] > 0.f ? 1u : 0u) << j;
+  return m;
+}
+
+template <bool RELU, bool MASKED>
 __global__ void __launch_bounds__(BN_THREADS) psb_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dy,
                                                                  const __nv_bfloat16* __restrict__ x,
                                                                  const __nv_bfloat16* __restrict__ y,
+                                                                 const uint8_t* __restrict__ mask,
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                  float* __restrict__ sums, BnGeom g) {
   extern __shared__ float smem[];
@@ -173,32 +194,34 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bn_bwd_reduce(const __nv_bfloa
   if (ty < g.lanes) {
     long long p = p0 + ty;
     for (; p + (long long)g.lanes < p1; p += 2LL * g.lanes) {
-      float d[2][8], a[2][8], o[2][8];
+      float d[2][8], a[2][8];
+      uint32_t mk[2] = {0xffu, 0xffu};
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const long long off = (p + (long long)u * g.lanes) * g.C + tx * 8;
+        const long long pp = p + (long long)u * g.lanes;
+        const long long off = pp * g.C + tx * 8;
         ld8_stream(dy + off, d[u]);
         ld8_stream(x + off, a[u]);
-        if (RELU) ld8_stream(y + off, o[u]);
+        if (RELU) mk[u] = relu_bits<MASKED>(y, mask, pp, off, g.groups, tx);
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float dd = (RELU && !(o[u][j] > 0.f)) ? 0.f : d[u][j];
+          const float dd = (RELU && !(mk[u] >> j & 1u)) ? 0.f : d[u][j];
           s[j] += dd;
           q[j] = fmaf(dd, (a[u][j] - mu[j]) * rs[j], q[j]);
         }
     }
     for (; p < p1; p += g.lanes) {
       const long long off = p * g.C + tx * 8;
-      float d[8], a[8], o[8];
+      float d[8], a[8];
       ld8_stream(dy + off, d);
       ld8_stream(x + off, a);
-      if (RELU) ld8_stream(y + off, o);
+      const uint32_t mk = RELU ? relu_bits<MASKED>(y, mask, p, off, g.groups, tx) : 0xffu;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float dd = (RELU && !(o[j] > 0.f)) ? 0.f : d[j];
+        const float dd = (RELU && !(mk >> j & 1u)) ? 0.f : d[j];
         s[j] += dd;
         q[j] = fmaf(dd, (a[j] - mu[j]) * rs[j], q[j]);
       }
@@ -228,10 +251,11 @@ __global__ void psb_bn_bwd_finalize(const float* __restrict__ sums, const __nv_b
   if (dbeta) dbeta[c] = __float2bfloat16_rn(sdy);
 }
 
-template <bool RES, bool RELU>
+template <bool RES, bool RELU, bool MASKED>
 __global__ void __launch_bounds__(BN_THREADS) psb_bn_bwd_apply(const __nv_bfloat16* __restrict__ dy,
                                                                 const __nv_bfloat16* __restrict__ x,
-                                                                const __nv_bfloat16* __restrict__ y, const float* __restrict__ ca,
+                                                                const __nv_bfloat16* __restrict__ y,
+                                                                const uint8_t* __restrict__ mask, const float* __restrict__ ca,
                                                                 const float* __restrict__ cb, const float* __restrict__ cc,
                                                                 __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
                                                                 BnGeom g) {
@@ -247,13 +271,13 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bn_bwd_apply(const __nv_bfloat
   const long long stride = (long long)gridDim.x * g.lanes;
   for (long long p = (long long)blockIdx.x * g.lanes + ty; p < g.pixels; p += stride) {
     const long long off = p * g.C + tx * 8;
-    float d[8], xv[8], o[8];
+    float d[8], xv[8];
     ld8_stream(dy + off, d);
     ld8_stream(x + off, xv);
-    if (RELU) ld8_stream(y + off, o);
+    const uint32_t mk = RELU ? relu_bits<MASKED>(y, mask, p, off, g.groups, tx) : 0xffu;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (RELU && !(o[j] > 0.f)) d[j] = 0.f;
+      if (RELU && !(mk >> j & 1u)) d[j] = 0.f;
       xv[j] = fmaf(d[j], a[j], fmaf(xv[j], b[j], c[j]));
     }
     st8(dx + off, xv);
@@ -276,82 +300,103 @@ struct BnPoolGeom {
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-__global__ void __launch_bounds__(256) psb_bnrelu_pool_fwd(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
-                                                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
-                                                           uint8_t* __restrict__ arg, BnPoolGeom g) {
-  const long long total = (long long)g.N * g.OH * g.OW * g.groups;
-  int cur = -1;
+// One CTA walks whole OUTPUT rows (n, oh): row / column indices are 32-bit and computed once per row / pixel (the first
+// version did a 64-bit div/mod chain per 16 bytes and ran at 1.5 TB/s; bench/bnpool_check.py).  tx = channel group of 8,
+// ty = pixel lane; a warp covers 32 / groups consecutive pixels = contiguous NHWC bytes.
+__global__ void __launch_bounds__(BN_THREADS) psb_bnrelu_pool_fwd(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+                                                                  uint8_t* __restrict__ arg, BnPoolGeom g, int lanes) {
+  const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
+  if (ty >= lanes) return;
   float sc[8], sh[8];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % g.groups);
-    if (cg != cur) {
-      cur = cg;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sc[j] = scale[cg * 8 + j], sh[j] = shift[cg * 8 + j];
-    }
-    long long p = i / g.groups;
-    const int ow = (int)(p % g.OW);
-    p /= g.OW;
-    const int oh = (int)(p % g.OH);
-    const int n = (int)(p / g.OH);
-    float best[8];
-    uint32_t pos[8];
+  for (int j = 0; j < 8; ++j) sc[j] = scale[tx * 8 + j], sh[j] = shift[tx * 8 + j];
+  const int rows = g.N * g.OH;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / g.OH, oh = row - n * g.OH;
+    const int h0 = oh * 2 - 1;
+    const __nv_bfloat16* xin = x + (size_t)n * g.H * g.W * g.C + tx * 8;
+    for (int ow = ty; ow < g.OW; ow += lanes) {
+      const int w0 = ow * 2 - 1;
+      float best[8];
+      uint32_t pos[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) best[j] = -INFINITY, pos[j] = 255;
+      for (int j = 0; j < 8; ++j) best[j] = -INFINITY, pos[j] = 255;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int h = oh * 2 - 1 + kh;
-      if (h < 0 || h >= g.H) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h = h0 + kh;
+        if (h < 0 || h >= g.H) continue;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int w = ow * 2 - 1 + kw;
-        if (w < 0 || w >= g.W) continue;
-        float v[8];
-        ld8(x + (((long long)n * g.H + h) * g.W + w) * g.C + cg * 8, v);
+        for (int kw = 0; kw < 3; ++kw) {
+          const int w = w0 + kw;
+          if (w < 0 || w >= g.W) continue;
+          float v[8];
+          ld8(xin + ((size_t)h * g.W + w) * g.C, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = bf16_round(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f));
-          if (z > best[j]) {             // strictly greater: the first maximum wins ties (ATen's rule)
-            best[j] = z;
-            pos[j] = kh * 3 + kw;
+          for (int j = 0; j < 8; ++j) {
+            const float z = bf16_round(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f));
+            if (z > best[j]) {             // strictly greater: the first maximum wins ties (ATen's rule)
+              best[j] = z;
+              pos[j] = kh * 3 + kw;
+            }
           }
         }
       }
+      const size_t o = ((size_t)row * g.OW + ow) * g.C + tx * 8;
+      st8(y + o, best);
+      *reinterpret_cast<uint2*>(arg + o) =
+          make_uint2(pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24), pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24));
     }
-    const long long o = (((long long)n * g.OH + oh) * g.OW + ow) * g.C + cg * 8;
-    st8(y + o, best);
-    *reinterpret_cast<uint2*>(arg + o) =
-        make_uint2(pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24), pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24));
   }
 }
 
-// gradient reaching the (never materialised) BN+ReLU output at input pixel (n, h, w), channels cg*8..+7
-__device__ __forceinline__ void gather_pool_grad(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ arg,
-                                                 const BnPoolGeom& g, int n, int h, int w, int cg, float* acc) {
+// The pooling windows that contain input index i (stride 2, pad 1, kernel 3): output a = i >> 1 with tap k = 1 (i even) or
+// 2 (i odd), and — for odd i only — output a + 1 with tap 0.  Kept in scalars (no dynamically indexed arrays: the first
+// row-based version spilled them to local memory and ran 2x slower).
+struct PoolWin {
+  int o0, k0, o1;      // first window (always valid when o0 < limit), second window (tap 0) valid iff v1
+  bool v0, v1;
+};
+__device__ __forceinline__ PoolWin pool_windows(int i, int olimit) {
+  PoolWin r;
+  r.o0 = i >> 1;
+  r.k0 = 1 + (i & 1);
+  r.v0 = r.o0 < olimit;
+  r.o1 = r.o0 + 1;
+  r.v1 = (i & 1) && r.o1 < olimit;
+  return r;
+}
+
+// add the gradient of pooled output (orow, ocol) to acc where its argmax is tap `want`
+__device__ __forceinline__ void gather_one(const __nv_bfloat16* __restrict__ dy_n, const uint8_t* __restrict__ arg_n,
+                                           const BnPoolGeom& g, int orow, int ocol, uint32_t want, int cg, float* acc) {
+  const size_t o = ((size_t)orow * g.OW + ocol) * g.C + cg * 8;
+  const uint2 pr = *reinterpret_cast<const uint2*>(arg_n + o);
+  const uint32_t w4 = want * 0x01010101u;
+  const uint32_t x0 = pr.x ^ w4, x1 = pr.y ^ w4;
+  // a zero byte in x0 / x1 = an arg position equal to `want`
+  if ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1)) & 0x80808080u) {
+    float d[8];
+    ld8(dy_n + o, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if ((((j < 4 ? x0 : x1) >> (8 * (j & 3))) & 0xffu) == 0u) acc[j] += d[j];
+  }
+}
+
+// gradient reaching the (never materialised) BN+ReLU output at input pixel (row windows `rw`, column w), channels cg*8..+7
+__device__ __forceinline__ void gather_pool_grad(const __nv_bfloat16* __restrict__ dy_n, const uint8_t* __restrict__ arg_n,
+                                                 const BnPoolGeom& g, const PoolWin& rw, int w, int cg, float* acc) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const int oh0 = h >> 1, ow0 = w >> 1;          // windows covering (h, w): oh*2-1 <= h <= oh*2+1
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    const int oh = oh0 + a;
-    const int kh = h - (oh * 2 - 1);
-    if (oh >= g.OH || kh < 0 || kh > 2) continue;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int ow = ow0 + b;
-      const int kw = w - (ow * 2 - 1);
-      if (ow >= g.OW || kw < 0 || kw > 2) continue;
-      const long long o = (((long long)n * g.OH + oh) * g.OW + ow) * g.C + cg * 8;
-      const uint2 pr = *reinterpret_cast<const uint2*>(arg + o);
-      float d[8];
-      ld8(dy + o, d);
-      const uint32_t want = (uint32_t)(kh * 3 + kw);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t pj = ((j < 4 ? pr.x : pr.y) >> (8 * (j & 3))) & 0xffu;
-        if (pj == want) acc[j] += d[j];
-      }
-    }
+  const PoolWin cw = pool_windows(w, g.OW);
+  if (rw.v0) {
+    if (cw.v0) gather_one(dy_n, arg_n, g, rw.o0, cw.o0, (uint32_t)(rw.k0 * 3 + cw.k0), cg, acc);
+    if (cw.v1) gather_one(dy_n, arg_n, g, rw.o0, cw.o1, (uint32_t)(rw.k0 * 3), cg, acc);
+  }
+  if (rw.v1) {
+    if (cw.v0) gather_one(dy_n, arg_n, g, rw.o1, cw.o0, (uint32_t)cw.k0, cg, acc);
+    if (cw.v1) gather_one(dy_n, arg_n, g, rw.o1, cw.o1, 0u, cg, acc);
   }
 }
 
@@ -373,23 +418,24 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bnpool_bwd_reduce(const __nv_b
     sc[j] = scale[tx * 8 + j];
     sh[j] = shift[tx * 8 + j];
   }
-  const long long per_cta = (g.pixels + gridDim.x - 1) / gridDim.x;
-  const long long p0 = (long long)blockIdx.x * per_cta;
-  const long long p1 = p0 + per_cta < g.pixels ? p0 + per_cta : g.pixels;
   if (ty < g.lanes) {
-    for (long long p = p0 + ty; p < p1; p += g.lanes) {
-      const int w = (int)(p % pg.W);
-      const long long t = p / pg.W;
-      const int h = (int)(t % pg.H), n = (int)(t / pg.H);
-      float d[8], a[8];
-      gather_pool_grad(dy, arg, pg, n, h, w, tx, d);
-      ld8_stream(x + p * g.C + tx * 8, a);
+    const int rows = pg.N * pg.H;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int n = row / pg.H, h = row - n * pg.H;
+      const PoolWin rw = pool_windows(h, pg.OH);
+      const size_t on = (size_t)n * pg.OH * pg.OW * pg.C;
+      const __nv_bfloat16* xr = x + (size_t)row * pg.W * pg.C + tx * 8;
+      for (int w = ty; w < pg.W; w += g.lanes) {
+        float d[8], a[8];
+        gather_pool_grad(dy + on, arg + on, pg, rw, w, tx, d);
+        ld8_stream(xr + (size_t)w * pg.C, a);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float o = bf16_round(fmaxf(fmaf(a[j], sc[j], sh[j]), 0.f));
-        const float dd = o > 0.f ? d[j] : 0.f;
-        s[j] += dd;
-        q[j] = fmaf(dd, (a[j] - mu[j]) * rs[j], q[j]);
+        for (int j = 0; j < 8; ++j) {
+          const float o = bf16_round(fmaxf(fmaf(a[j], sc[j], sh[j]), 0.f));
+          const float dd = o > 0.f ? d[j] : 0.f;
+          s[j] += dd;
+          q[j] = fmaf(dd, (a[j] - mu[j]) * rs[j], q[j]);
+        }
       }
     }
   }
@@ -415,22 +461,25 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bnpool_bwd_apply(const __nv_bf
     sc[j] = scale[tx * 8 + j];
     sh[j] = shift[tx * 8 + j];
   }
-  const long long stride = (long long)gridDim.x * g.lanes;
-  for (long long p = (long long)blockIdx.x * g.lanes + ty; p < g.pixels; p += stride) {
-    const int w = (int)(p % pg.W);
-    const long long t = p / pg.W;
-    const int h = (int)(t % pg.H), n = (int)(t / pg.H);
-    float d[8], xv[8];
-    gather_pool_grad(dy, arg, pg, n, h, w, tx, d);
-    const long long off = p * g.C + tx * 8;
-    ld8_stream(x + off, xv);
+  const int rows = pg.N * pg.H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / pg.H, h = row - n * pg.H;
+    const PoolWin rw = pool_windows(h, pg.OH);
+    const size_t on = (size_t)n * pg.OH * pg.OW * pg.C;
+    const size_t xoff = (size_t)row * pg.W * pg.C + tx * 8;
+    for (int w = ty; w < pg.W; w += g.lanes) {
+      float d[8], xv[8];
+      gather_pool_grad(dy + on, arg + on, pg, rw, w, tx, d);
+      const size_t off = xoff + (size_t)w * pg.C;
+      ld8_stream(x + off, xv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float o = bf16_round(fmaxf(fmaf(xv[j], sc[j], sh[j]), 0.f));
-      const float dd = o > 0.f ? d[j] : 0.f;
-      xv[j] = fmaf(dd, a[j], fmaf(xv[j], b[j], c[j]));
+      for (int j = 0; j < 8; ++j) {
+        const float o = bf16_round(fmaxf(fmaf(xv[j], sc[j], sh[j]), 0.f));
+        const float dd = o > 0.f ? d[j] : 0.f;
+        xv[j] = fmaf(dd, a[j], fmaf(xv[j], b[j], c[j]));
+      }
+      st8(dx + off, xv);
     }
-    st8(dx + off, xv);
   }
 }
 
@@ -458,7 +507,8 @@ int grid_for(long long pixels, const BnGeom& g) {
 // C must be a multiple of 8 and <= 2048 (groups <= 256)
 void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y,
                     float* sums /*2C, zeroed here*/, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
-                    float* running_var, long long pixels, int C, float eps, float momentum, int relu, int training) {
+                    float* running_var, long long pixels, int C, float eps, float momentum, int relu, int training, void* mask) {
+  auto MK = reinterpret_cast<uint8_t*>(mask);
   const BnGeom g = geom(pixels, C);
   const int grid = grid_for(pixels, g);
   auto X = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -473,11 +523,11 @@ void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* 
                                                      running_mean, running_var, C, pixels, eps, momentum);
   }
   if (res != nullptr) {
-    if (relu) psb_bn_apply<true, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
-    else psb_bn_apply<true, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
+    if (relu) psb_bn_apply<true, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, MK, g);
+    else psb_bn_apply<true, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, MK, g);
   } else {
-    if (relu) psb_bn_apply<false, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
-    else psb_bn_apply<false, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
+    if (relu) psb_bn_apply<false, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, MK, g);
+    else psb_bn_apply<false, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, MK, g);
   }
 }
 
@@ -486,7 +536,8 @@ void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* 
 void psb_bn_forward_presummed(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y,
                               const float* sums /*2C, filled by the producer*/, float* mean, float* rstd, float* scale,
                               float* shift, float* running_mean, float* running_var, long long pixels, int C, float eps,
-                              float momentum, int relu) {
+                              float momentum, int relu, void* mask) {
+  auto MK = reinterpret_cast<uint8_t*>(mask);
   const BnGeom g = geom(pixels, C);
   const int grid = grid_for(pixels, g);
   auto X = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -497,17 +548,18 @@ void psb_bn_forward_presummed(cudaStream_t s, const void* x, const void* res, co
                                                    reinterpret_cast<const __nv_bfloat16*>(beta), mean, rstd, scale, shift,
                                                    running_mean, running_var, C, pixels, eps, momentum);
   if (res != nullptr) {
-    if (relu) psb_bn_apply<true, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
-    else psb_bn_apply<true, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
+    if (relu) psb_bn_apply<true, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, MK, g);
+    else psb_bn_apply<true, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, MK, g);
   } else {
-    if (relu) psb_bn_apply<false, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
-    else psb_bn_apply<false, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, g);
+    if (relu) psb_bn_apply<false, true><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, MK, g);
+    else psb_bn_apply<false, false><<<grid, BN_THREADS, 0, s>>>(X, R, scale, shift, Y, MK, g);
   }
 }
 
 void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* y, const void* gamma, const float* mean,
                      const float* rstd, float* sums /*2C*/, float* coef /*3C*/, void* dx, void* dres, void* dgamma, void* dbeta,
-                     long long pixels, int C, int relu) {
+                     long long pixels, int C, int relu, const void* mask) {
+  auto MK = reinterpret_cast<const uint8_t*>(mask);
   const BnGeom g = geom(pixels, C);
   const int grid = grid_for(pixels, g);
   auto DY = reinterpret_cast<const __nv_bfloat16*>(dy);
@@ -516,20 +568,26 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
   psb_count_launch(3);
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
   const size_t sm = sizeof(float) * g.lanes * C;
-  if (relu) psb_bn_bwd_reduce<true><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, mean, rstd, sums, g);
-  else psb_bn_bwd_reduce<false><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, mean, rstd, sums, g);
+  if (relu && MK) psb_bn_bwd_reduce<true, true><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
+  else if (relu) psb_bn_bwd_reduce<true, false><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
+  else psb_bn_bwd_reduce<false, false><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
   psb_bn_bwd_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd, coef,
                                                        coef + C, coef + 2 * C, reinterpret_cast<__nv_bfloat16*>(dgamma),
                                                        reinterpret_cast<__nv_bfloat16*>(dbeta), C, pixels);
   auto DX = reinterpret_cast<__nv_bfloat16*>(dx);
   auto DR = reinterpret_cast<__nv_bfloat16*>(dres);
+#define PSB_APPLY(RES_, RELU_, MASKED_) \
+  psb_bn_bwd_apply<RES_, RELU_, MASKED_><<<grid, BN_THREADS, 0, s>>>(DY, X, Y, MK, coef, coef + C, coef + 2 * C, DX, DR, g)
   if (dres != nullptr) {
-    if (relu) psb_bn_bwd_apply<true, true><<<grid, BN_THREADS, 0, s>>>(DY, X, Y, coef, coef + C, coef + 2 * C, DX, DR, g);
-    else psb_bn_bwd_apply<true, false><<<grid, BN_THREADS, 0, s>>>(DY, X, Y, coef, coef + C, coef + 2 * C, DX, DR, g);
+    if (relu && MK) PSB_APPLY(true, true, true);
+    else if (relu) PSB_APPLY(true, true, false);
+    else PSB_APPLY(true, false, false);
   } else {
-    if (relu) psb_bn_bwd_apply<false, true><<<grid, BN_THREADS, 0, s>>>(DY, X, Y, coef, coef + C, coef + 2 * C, DX, DR, g);
-    else psb_bn_bwd_apply<false, false><<<grid, BN_THREADS, 0, s>>>(DY, X, Y, coef, coef + C, coef + 2 * C, DX, DR, g);
+    if (relu && MK) PSB_APPLY(false, true, true);
+    else if (relu) PSB_APPLY(false, true, false);
+    else PSB_APPLY(false, false, false);
   }
+#undef PSB_APPLY
 }
 
 // ---- EXPERIMENTAL fused BN + ReLU + 3x3/s2/p1 max-pool (training) -------------------------------------------------
@@ -550,10 +608,9 @@ void psb_bnpool_forward(cudaStream_t s, const void* x, const void* gamma, const 
                                                    reinterpret_cast<const __nv_bfloat16*>(beta), mean, rstd, scale, shift,
                                                    running_mean, running_var, C, pixels, eps, momentum);
   BnPoolGeom pg{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
-  const long long total = (long long)N * pg.OH * pg.OW * pg.groups;
-  long long want = (total + 255) / 256, cap = (long long)grid_for(pixels, g) * 2;
-  psb_bnrelu_pool_fwd<<<(int)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, s>>>(
-      X, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<uint8_t*>(arg), pg);
+  const int rows_out = N * pg.OH, cap = grid_for(pixels, g);
+  psb_bnrelu_pool_fwd<<<rows_out < cap ? rows_out : cap, BN_THREADS, 0, s>>>(
+      X, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<uint8_t*>(arg), pg, g.lanes);
 }
 
 void psb_bnpool_backward(cudaStream_t s, const void* dy, const void* arg, const void* x, const void* gamma, const float* mean,
@@ -568,10 +625,12 @@ void psb_bnpool_backward(cudaStream_t s, const void* dy, const void* arg, const 
   auto X = reinterpret_cast<const __nv_bfloat16*>(x);
   psb_count_launch(3);
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
-  psb_bnpool_bwd_reduce<<<grid, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(DY, A, X, scale, shift, mean, rstd, sums, g, pg);
+  const int rows_in = N * H;
+  const int grid_rows = rows_in < grid ? rows_in : grid;
+  psb_bnpool_bwd_reduce<<<grid_rows, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(DY, A, X, scale, shift, mean, rstd, sums, g, pg);
   psb_bn_bwd_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd, coef,
                                                        coef + C, coef + 2 * C, reinterpret_cast<__nv_bfloat16*>(dgamma),
                                                        reinterpret_cast<__nv_bfloat16*>(dbeta), C, pixels);
-  psb_bnpool_bwd_apply<<<grid, BN_THREADS, 0, s>>>(DY, A, X, scale, shift, coef, coef + C, coef + 2 * C,
+  psb_bnpool_bwd_apply<<<grid_rows, BN_THREADS, 0, s>>>(DY, A, X, scale, shift, coef, coef + C, coef + 2 * C,
                                                    reinterpret_cast<__nv_bfloat16*>(dx), g, pg);
 }

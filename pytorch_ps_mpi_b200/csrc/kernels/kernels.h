@@ -120,13 +120,15 @@ void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms,
 // bn_kernels.cu — fused channels-last bf16 BatchNorm (+residual, +ReLU), forward and backward
 void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y, float* sums,
                     float* mean, float* rstd, float* scale, float* shift, float* running_mean, float* running_var,
-                    long long pixels, int C, float eps, float momentum, int relu, int training);
+                    long long pixels, int C, float eps, float momentum, int relu, int training,
+                    void* mask = nullptr /* [pixels * C/8] bytes: 1 bit per element, y > 0 (relu + training) */);
 void psb_bn_forward_presummed(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y,
                               const float* sums, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
-                              float* running_var, long long pixels, int C, float eps, float momentum, int relu);
+                              float* running_var, long long pixels, int C, float eps, float momentum, int relu,
+                              void* mask = nullptr);
 void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* y, const void* gamma, const float* mean,
                      const float* rstd, float* sums, float* coef, void* dx, void* dres, void* dgamma, void* dbeta,
-                     long long pixels, int C, int relu);
+                     long long pixels, int C, int relu, const void* mask = nullptr /* the forward's ReLU bit mask, replaces y */);
 
 // EXPERIMENTAL fused BN + ReLU + 3x3/s2/p1 max-pool (bn_kernels.cu)
 void psb_bnpool_forward(cudaStream_t s, const void* x, const void* gamma, const void* beta, void* y, void* arg, float* sums,
@@ -149,6 +151,7 @@ void psb_stem_fwd_launch(cudaStream_t s, const void* tmap_w, const void* tmap_y,
                          int num_sms, const uint64_t* ready_flag, uint64_t ready_epoch, unsigned long long timeout_ns);
 
 int psb_stem_wgrad_grid(int N, int H, int num_sms);
+void psb_stem_wgrad_finalize_launch(cudaStream_t s, const float* partial, int grid, void* out_bf16);
 void psb_stem_wgrad_launch(cudaStream_t s, const void* tmap_g, const void* x, float* partial, int N, int H, int W, int num_sms);
 
 // process-wide count of OUR kernel launches (every psb_* launcher adds to it; bench.py reports the delta)

@@ -465,7 +465,33 @@ psb_stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
   }
 }
 
+// dW2d[co][k] = Σ_cta partial[cta][k][co]  (fp32 sum in CTA order → deterministic), cast to bf16.
+// Thread t handles (k = t / 64, co = t % 64): the reads of one warp are 128 contiguous bytes of each partial.
+__global__ void __launch_bounds__(256) psb_stem_wgrad_finalize_kernel(const float* __restrict__ partial, int grid,
+                                                                      __nv_bfloat16* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= SK * 64) return;
+  const int k = t >> 6, co = t & 63;
+  float acc = 0.f;
+  int g = 0;
+  for (; g + 4 <= grid; g += 4) {
+    const float a0 = partial[(size_t)(g + 0) * SK * 64 + t], a1 = partial[(size_t)(g + 1) * SK * 64 + t],
+                a2 = partial[(size_t)(g + 2) * SK * 64 + t], a3 = partial[(size_t)(g + 3) * SK * 64 + t];
+    acc += a0;
+    acc += a1;
+    acc += a2;
+    acc += a3;
+  }
+  for (; g < grid; ++g) acc += partial[(size_t)g * SK * 64 + t];
+  out[co * SK + k] = __float2bfloat16_rn(acc);
+}
+
 }  // namespace
+
+void psb_stem_wgrad_finalize_launch(cudaStream_t s, const float* partial, int grid, void* out_bf16) {
+  psb_count_launch(1);
+  psb_stem_wgrad_finalize_kernel<<<(SK * 64 + 255) / 256, 256, 0, s>>>(partial, grid, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+}
 
 int psb_stem_fwd_smem_bytes() { return STEM_SMEM; }
 

@@ -24,12 +24,15 @@ class _FusedBN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, training, sums=None):
         m = ext.cuda()
-        if sums is not None and training:    # EXPERIMENTAL: Σx / Σx² came out of the producer's epilogue (fused stem)
-            y, mean, rstd = m.bn_forward_presummed(x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, sums)
+        if sums is not None and training:    # Σx / Σx² came out of the producer's epilogue (fused stem)
+            y, mean, rstd, mask = m.bn_forward_presummed(x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, sums)
         else:
-            y, mean, rstd = m.bn_forward(x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, training)
-        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
+            y, mean, rstd, mask = m.bn_forward(x, res, gamma, beta, running_mean, running_var, eps, momentum, relu, training)
+        # ReLU: the backward needs only the sign of y — a 1-bit mask (1/16 of y's bytes) written by the forward kernel
+        ctx.save_for_backward(x, (mask if mask is not None else y) if relu else None, gamma, mean, rstd)
         ctx.relu, ctx.has_res = relu, res is not None
+        # PS device engine attached (Identity wire): dgamma / dbeta are written straight into the wire arena (no encode pass)
+        ctx.gout = (getattr(gamma, "ps_grad_out", None), getattr(beta, "ps_grad_out", None))
         return y
 
     @staticmethod
@@ -38,7 +41,9 @@ class _FusedBN(torch.autograd.Function):
         m = ext.cuda()
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
-        dx, dres, dgamma, dbeta = m.bn_backward(dy, x, y if ctx.relu else x, gamma, mean, rstd, ctx.relu, ctx.has_res)
+        og = ctx.gout[0]() if ctx.gout[0] is not None else None
+        ob = ctx.gout[1]() if ctx.gout[1] is not None else None
+        dx, dres, dgamma, dbeta = m.bn_backward(dy, x, y if ctx.relu else x, gamma, mean, rstd, ctx.relu, ctx.has_res, og, ob)
         return dx, (dres if ctx.has_res else None), dgamma, dbeta, None, None, None, None, None, None, None
 
 

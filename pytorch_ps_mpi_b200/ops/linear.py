@@ -32,6 +32,7 @@ class _BcastLinearFn(torch.autograd.Function):
         y = m.bcast_gemm(x2d, w_ptr or weight.data_ptr(), N, K, bias, relu, flag_ptr, epoch, 30.0, variant)
         ctx.save_for_backward(x2d, weight, y if relu else None)
         ctx.relu, ctx.has_bias = relu, bias is not None
+        ctx.gout = getattr(weight, "ps_grad_out", None) if weight.is_contiguous() else None
         return y
 
     @staticmethod
@@ -40,7 +41,11 @@ class _BcastLinearFn(torch.autograd.Function):
         if ctx.relu:
             gy = gy * (y > 0).to(gy.dtype)
         gx = gy @ weight if ctx.needs_input_grad[0] else None
-        gw = gy.t() @ x2d if ctx.needs_input_grad[1] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            out = ctx.gout() if ctx.gout is not None else None
+            # PS device engine attached (Identity wire): the dW GEMM writes straight into the wire arena (no encode pass)
+            gw = torch.mm(gy.t(), x2d, out=out) if out is not None else gy.t() @ x2d
         gb = gy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return gx, gw, gb, None, None, None, None, None
 

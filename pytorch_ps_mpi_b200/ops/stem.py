@@ -81,6 +81,7 @@ class _StemFused(torch.autograd.Function):
         y, sums = ext.cuda().stem_fwd(x, _w2d_of(weight), True, flag_ptr, epoch, 900.0)
         ctx.save_for_backward(x)
         ctx.cout = weight.shape[0]
+        ctx.gout = getattr(weight, "ps_grad_out", None) if in_gemm_layout(weight) else None
         ctx.mark_non_differentiable(sums)
         return y, sums
 
@@ -92,7 +93,10 @@ class _StemFused(torch.autograd.Function):
             if not gy.is_contiguous(memory_format=torch.channels_last):
                 gy = gy.contiguous(memory_format=torch.channels_last)
             if _IMPLICIT_WGRAD:
-                gw2d = stem_wgrad_implicit(x, gy)
+                out = ctx.gout() if ctx.gout is not None else None     # the stem weight's wire-arena slot (GEMM layout) or None
+                if out is not None:
+                    out = torch.as_strided(out, (ctx.cout * STEM_K,), (1,))
+                gw2d = stem_wgrad_implicit(x, gy, out)
             else:
                 a = ext.cuda().im2col_stem(x)
                 g2 = gy.permute(0, 2, 3, 1).reshape(-1, gy.shape[1])      # NHWC view of the channels-last gradient
@@ -102,10 +106,12 @@ class _StemFused(torch.autograd.Function):
         return None, gw, None, None
 
 
-def stem_wgrad_implicit(x: torch.Tensor, gy: torch.Tensor) -> torch.Tensor:
-    """``dW2d [64,176]`` (bf16) of the stem from ``psb_stem_wgrad_kernel`` — no patch matrix."""
-    partial = ext.cuda().stem_wgrad(x, gy)                                # [grid,176,64] fp32
-    return partial.sum(0).t().to(gy.dtype)
+def stem_wgrad_implicit(x: torch.Tensor, gy: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """``dW2d [64,176]`` (bf16) of the stem from ``psb_stem_wgrad_kernel`` — no patch matrix.  ``out``: a contiguous
+    bf16 buffer of 64*176 elements to write into (the PS wire arena slot of the weight)."""
+    m = ext.cuda()
+    partial = m.stem_wgrad(x, gy)                                         # [grid,176,64] fp32
+    return m.stem_wgrad_finalize(partial, out)                            # Σ partials, transpose, cast: one kernel
 
 
 def stem_fused_supported(x: torch.Tensor, conv: torch.nn.Conv2d) -> bool:

@@ -115,6 +115,7 @@ class DeviceEngine:
 
         # ---- move the model's parameters into the parameter arena (zero-copy from now on) ----
         with torch.no_grad():
+            self.wire_arena.zero_()          # tile padding must be (and then stays) zero: see grad_out()
             self.param_arena.zero_()
             for s in L.slots:
                 flat = self.param_arena[s.offset: s.offset + s.numel]
@@ -255,6 +256,16 @@ class DeviceEngine:
         self._async_i = 0
         self._async_applied = 0
         self._async_last = {"contributors": [], "param_version": 0, "staleness": {}, "updates_applied": 0}
+        # K10 "no separate serialization pass": producers we own (our BN / stem / linear backward kernels) write their
+        # gradient straight into this rank's wire arena when the wire layout IS the gradient layout
+        self._direct_ok = (self.kind == KIND_DENSE and self.wire == wire_code_of(self.dtype) and self.mode == "ps"
+                           and os.environ.get("PSB200_DIRECT_GRAD", "1") != "0")
+        self.direct_grads = 0
+        self.direct_names: set = set()
+        if self._direct_ok:
+            import functools
+            for sl in self.layout.slots:
+                sl.param.ps_grad_out = functools.partial(self.grad_out, sl.param)
         self._snap_version = 0
         self._snap_shadow = None
         self._step_hyp = None
@@ -368,11 +379,46 @@ class DeviceEngine:
         self._expose_state()
 
     # ------------------------------------------------------------------------------- backward
+    def grad_out(self, param: torch.nn.Parameter) -> Optional[torch.Tensor]:
+        """Where the producer of ``param``'s gradient may write it DIRECTLY: a view of this rank's wire arena with the
+        parameter's shape and physical layout — or ``None`` (coded wires, other modes).
+
+        With Identity / same-dtype wires the wire tile of a parameter is bit-for-bit its gradient, so a kernel we own
+        (fused BN backward, the stem's implicit weight gradient, ``BcastLinear``'s dW GEMM with ``out=``) can skip the
+        ``psb_encode_kernel`` copy: ``on_grad`` recognises the pointer and only counts the parameter as arrived.  Safe in
+        ``mode='ps'`` only: a worker's backward starts after it observed PARAMS_READY (the server finished reading the
+        previous wire tiles); in ``allgather`` mode peers may still be reading them (CONSUMED is awaited on the comm stream)."""
+        if not self._direct_ok or self._closed:
+            return None
+        sl = self.layout.by_id.get(id(param))
+        if sl is None:
+            return None
+        flat = self.wire_arena[sl.first_tile * self.bpt: sl.first_tile * self.bpt + sl.numel * self.psz].view(self.dtype)
+        return self._like(flat, param) if sl.strides is None else torch.as_strided(flat, param.shape, sl.strides)
+
     def on_grad(self, grad: torch.Tensor, name: str, param: torch.nn.Parameter):
         """Backward hook (``ps.py:98-101``): file the gradient under its chunk; every chunk that is now complete (in
         arena order) is encoded — and on the server gathered / updated / broadcast — right away, under backward."""
         s = self.layout.by_id[id(param)]
         g = grad.detach()
+        if self._direct_ok and g.data_ptr() == self._wire_ptr + s.first_tile * self.bpt and g.dtype == self.dtype \
+                and g.stride() == param.stride():
+            # the producer already wrote this gradient into the wire arena (grad_out): nothing to encode
+            if s.index in self._fired:
+                raise RuntimeError(f"parameter {name!r} produced two gradients before step()")
+            self._fired.add(s.index)
+            k = self._chunk_of[s.index]
+            self._chunk_left[k] -= 1
+            self._raw_bytes += s.numel * self.psz
+            self.direct_grads += 1
+            self.direct_names.add(name)
+            if param.grad is not None:
+                # AccumulateGrad would add the incoming gradient INTO param.grad in place — and both may alias the same wire
+                # tile (zero_grad(set_to_none=False)): drop the old one so the new gradient is assigned, not accumulated
+                param.grad = None
+            while self._next_chunk < self.nchunks and self._chunk_left[self._next_chunk] == 0:
+                self._flush_chunk(self._next_chunk)
+            return
         if g.dtype != self.dtype:
             g = g.to(self.dtype)
         if s.strides is not None:
@@ -855,4 +901,8 @@ class DeviceEngine:
             with torch.no_grad():
                 for s in self.layout.slots:
                     s.param.data = s.param.data.clone()
+                    if hasattr(s.param, "ps_grad_out"):
+                        del s.param.ps_grad_out
+                    if s.param.grad is not None and self._direct_ok:
+                        s.param.grad = None          # may alias the wire arena that is about to be unmapped
             self.arena.close()

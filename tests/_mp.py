@@ -256,8 +256,11 @@ def gpu_train(rank, size, mode, optim, coding, dtype_name, reduce="auto", hidden
                 assert torch.equal(got.to(dtype).float(), p.detach().float().cpu())
     if dtype == torch.float32:
         want = _oracle_sum_ref(size, steps, optim, hyper, factory, hidden)
+        # int8 abs-max quantisation: a CPU-recomputed gradient that differs in its last bit can land on the other side of a
+        # rounding boundary (one step of amax/127, times lr) — oracle (a) above, fed the ACTUAL gradients, stays tight
+        atol_b = 2e-4 if coding == "scale" else 2e-5
         for p, q in zip(model.parameters(), want):
-            assert torch.allclose(p.detach().cpu(), q, rtol=2e-4, atol=2e-5), (mode, optim, coding, (p.detach().cpu() - q).abs().max())
+            assert torch.allclose(p.detach().cpu(), q, rtol=2e-4, atol=atol_b), (mode, optim, coding, (p.detach().cpu() - q).abs().max())
     info = {"provider": eng.arena.provider, "multicast": eng.arena.has_multicast, "bcast": eng.bcast, "reduce": eng.reduce,
             "chunks": eng.nchunks, "pipeline": eng.pipeline}
     if rank == 0:

@@ -211,3 +211,59 @@ def test_device_engine_with_lr_scheduler():
     for p, q in zip(a, b):
         assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
     o.close()
+
+
+def test_direct_gradient_placement_matches_encode_path(monkeypatch):
+    """K10: producers we own (fused BN backward, stem implicit wgrad) write their gradients straight into the wire arena;
+    the result must be bit-identical to the psb_encode_kernel copy path, and the encode batches must shrink."""
+    from pytorch_ps_mpi_b200 import models
+
+    def run(direct):
+        monkeypatch.setenv("PSB200_DIRECT_GRAD", "1" if direct else "0")
+        dev = torch.device("cuda", 0)
+        torch.manual_seed(0)
+        model = models.resnet18(num_classes=10).to(dev).to(memory_format=torch.channels_last).bfloat16()
+        named = list(model.named_parameters())
+        opt = ps.SGD(named, [p for _, p in named], lr=0.05, momentum=0.9, weight_decay=1e-4, engine="device")
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(8, 3, 64, 64, generator=g).to(dev).bfloat16().contiguous(memory_format=torch.channels_last)
+        y = torch.randint(0, 10, (8,), generator=g).to(dev)
+        for _ in range(3):
+            opt.zero_grad(set_to_none=True)
+            torch.nn.functional.cross_entropy(model(x).float(), y).backward()
+            opt.step()
+        torch.cuda.synchronize()
+        out = [p.detach().float().clone() for _, p in named]
+        n_direct = opt._engine.direct_grads
+        missing = [n for n, p in named if (".bn" in n or n.startswith("bn") or "downsample.1" in n or n == "conv1.weight")
+                   and n not in opt._engine.direct_names]
+        assert not direct or not missing, f"not placed directly: {missing}"
+        opt.close()
+        return out, n_direct
+
+    a, na = run(True)
+    b, nb = run(False)
+    assert nb == 0 and na >= 3 * 41, (na, nb)      # 20 BN layers x (gamma, beta) + the stem weight, every step
+    for p, q in zip(a, b):
+        assert torch.equal(p, q)
+
+
+def test_stem_weight_lives_in_gemm_layout_in_the_arena():
+    from pytorch_ps_mpi_b200 import models
+    from pytorch_ps_mpi_b200.ops.stem import STEM_STRIDES, in_gemm_layout
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = models.resnet18(num_classes=10).to(dev).to(memory_format=torch.channels_last).bfloat16()
+    ref = model.conv1.weight.detach().float().clone()
+    named = list(model.named_parameters())
+    opt = ps.SGD(named, [p for _, p in named], lr=0.0, engine="device")
+    w = model.conv1.weight
+    assert in_gemm_layout(w) and tuple(w.stride()) == STEM_STRIDES
+    assert torch.equal(w.detach().float(), ref)                          # same logical values
+    w2d = torch.as_strided(w.detach(), (64, 176), (176, 1))
+    assert float(w2d[:, 168:].abs().max()) == 0.0                        # the K padding is zero
+    assert float(w2d.reshape(64, 7 * 24 + 8)[:, :168].reshape(64, 7, 24)[:, :, 21:].abs().max()) == 0.0
+    sd = opt.state_dict()
+    opt.load_state_dict(sd)
+    opt.close()
+    assert torch.equal(model.conv1.weight.detach().float(), ref)

@@ -86,7 +86,10 @@ def test_fused_bn_relu_maxpool(shape):
     x = _cl((torch.randn(n, c, h, w, device=dev) * 2 + 0.3).bfloat16())
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     ya, yb = pool(bn_a(xa)), fused_bn_relu_maxpool(xb, bn_b)
-    assert torch.equal(ya, yb), "same bf16 rounding point: the forward must be bit-identical"
+    # same bf16 rounding point, but each path sums its own batch statistics with float atomics (order-dependent in the last
+    # bit): identical up to a rare 1-ulp flip of a bf16 output
+    assert float((ya.float() - yb.float()).abs().max()) <= 2.0 ** -7 * float(ya.float().abs().max())
+    assert float((ya != yb).float().mean()) < 1e-3
     g = torch.randn_like(ya)
     ya.backward(g)
     yb.backward(g)
