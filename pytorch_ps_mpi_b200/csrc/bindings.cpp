@@ -68,7 +68,7 @@ struct UpdatePlan {
   void launch(uint64_t epoch, const std::vector<std::vector<double>>& groups, uint32_t contrib_mask, double inv_count,
               int wait_grads, int signal_mode, uint32_t ack_mask, uint64_t version, uint64_t select_out,
               int average_dynamic, uint64_t active_ptr, double timeout_s, uint32_t wait_mask, uint64_t stream,
-              int tile_begin, int tile_end, uint64_t wait_value) {
+              int tile_begin, int tile_end, uint64_t wait_value, uint64_t param_hyper) {
     if (groups.size() > PSB_MAX_GROUPS) throw std::runtime_error("too many param groups for one launch");
     for (size_t i = 0; i < groups.size(); ++i) {
       const auto& g = groups[i];
@@ -94,6 +94,7 @@ struct UpdatePlan {
     a.select_out = reinterpret_cast<const uint64_t*>(select_out);
     a.average_dynamic = average_dynamic;
     a.active = reinterpret_cast<const uint8_t*>(active_ptr);
+    a.param_hyper = reinterpret_cast<const float2*>(param_hyper);
     a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
     // Window the chunk: one launch touches at most `window_bytes` of every rank's wire arena.  A single kernel that walks
     // >= 1 GB of mapped peer memory on each of 8 ranks falls off a TLB cliff (194 GB/s, profiles/bw_sweep_n8.json);
@@ -281,7 +282,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("inv_count"), py::arg("wait_grads"), py::arg("signal_mode"), py::arg("ack_mask") = 0,
            py::arg("version") = 0, py::arg("select_out") = 0, py::arg("average_dynamic") = 0, py::arg("active_ptr") = 0,
            py::arg("timeout_s") = 30.0, py::arg("wait_mask") = 0xffffffffu, py::arg("stream") = 0,
-           py::arg("tile_begin") = 0, py::arg("tile_end") = -1, py::arg("wait_value") = 0);
+           py::arg("tile_begin") = 0, py::arg("tile_end") = -1, py::arg("wait_value") = 0, py::arg("param_hyper") = 0);
 
   m.def("update_max_grid", &psb_update_max_grid);
   m.def("launch_count", []() { return (uint64_t)psb_launch_count(); }, "kernels of ours launched by this process so far");

@@ -350,53 +350,45 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bnrelu_pool_fwd(const __nv_bfl
   }
 }
 
-// The pooling windows that contain input index i (stride 2, pad 1, kernel 3): output a = i >> 1 with tap k = 1 (i even) or
-// 2 (i odd), and — for odd i only — output a + 1 with tap 0.  Kept in scalars (no dynamically indexed arrays: the first
-// row-based version spilled them to local memory and ran 2x slower).
-struct PoolWin {
-  int o0, k0, o1;      // first window (always valid when o0 < limit), second window (tap 0) valid iff v1
-  bool v0, v1;
-};
-__device__ __forceinline__ PoolWin pool_windows(int i, int olimit) {
-  PoolWin r;
-  r.o0 = i >> 1;
-  r.k0 = 1 + (i & 1);
-  r.v0 = r.o0 < olimit;
-  r.o1 = r.o0 + 1;
-  r.v1 = (i & 1) && r.o1 < olimit;
-  return r;
-}
-
-// add the gradient of pooled output (orow, ocol) to acc where its argmax is tap `want`
-__device__ __forceinline__ void gather_one(const __nv_bfloat16* __restrict__ dy_n, const uint8_t* __restrict__ arg_n,
-                                           const BnPoolGeom& g, int orow, int ocol, uint32_t want, int cg, float* acc) {
-  const size_t o = ((size_t)orow * g.OW + ocol) * g.C + cg * 8;
-  const uint2 pr = *reinterpret_cast<const uint2*>(arg_n + o);
-  const uint32_t w4 = want * 0x01010101u;
-  const uint32_t x0 = pr.x ^ w4, x1 = pr.y ^ w4;
-  // a zero byte in x0 / x1 = an arg position equal to `want`
-  if ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1)) & 0x80808080u) {
-    float d[8];
-    ld8(dy_n + o, d);
+// ---- backward of the fused BN + ReLU + max-pool, organised by 2x2 input QUADS (H and W even) ------------------------------
+// The quad of input pixels (h0..h0+1, w0..w0+1), h0 / w0 even, is covered by exactly the four pooling windows
+// (oh0 + a, ow0 + b), oh0 = h0/2, ow0 = w0/2, a, b in {0,1}, and the nine taps of those windows that fall INTO the quad
+// partition 0..8:  window (0,0): taps 4,5,7,8 → pixels (0,0),(0,1),(1,0),(1,1);  (0,1): taps 3,6 → (0,1),(1,1);
+// (1,0): taps 1,2 → (1,0),(1,1);  (1,1): tap 0 → (1,1).  So one thread loads 4 x (arg 8 B + dy 16 B) for 4 pixels x 8 channels
+// (the per-pixel gather of the first version loaded 2.25 windows per pixel behind data-dependent branches and was latency-bound:
+// 1.15 ms vs 0.71 ms unfused, bench/bnpool_check.py), all loads issued before any is consumed.
+__device__ __forceinline__ void quad_pool_grad(const __nv_bfloat16* __restrict__ dy_n, const uint8_t* __restrict__ arg_n,
+                                               const BnPoolGeom& g, int oh0, int ow0, int cg, float (&d)[4][8]) {
+  uint2 pr[4];
+  uint4 dv[4];
+  bool ok[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if ((((j < 4 ? x0 : x1) >> (8 * (j & 3))) & 0xffu) == 0u) acc[j] += d[j];
-  }
-}
-
-// gradient reaching the (never materialised) BN+ReLU output at input pixel (row windows `rw`, column w), channels cg*8..+7
-__device__ __forceinline__ void gather_pool_grad(const __nv_bfloat16* __restrict__ dy_n, const uint8_t* __restrict__ arg_n,
-                                                 const BnPoolGeom& g, const PoolWin& rw, int w, int cg, float* acc) {
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const PoolWin cw = pool_windows(w, g.OW);
-  if (rw.v0) {
-    if (cw.v0) gather_one(dy_n, arg_n, g, rw.o0, cw.o0, (uint32_t)(rw.k0 * 3 + cw.k0), cg, acc);
-    if (cw.v1) gather_one(dy_n, arg_n, g, rw.o0, cw.o1, (uint32_t)(rw.k0 * 3), cg, acc);
-  }
-  if (rw.v1) {
-    if (cw.v0) gather_one(dy_n, arg_n, g, rw.o1, cw.o0, (uint32_t)cw.k0, cg, acc);
-    if (cw.v1) gather_one(dy_n, arg_n, g, rw.o1, cw.o1, 0u, cg, acc);
+    for (int b = 0; b < 2; ++b) {
+      const int i = a * 2 + b;
+      ok[i] = (oh0 + a < g.OH) && (ow0 + b < g.OW);
+      pr[i] = make_uint2(0xffffffffu, 0xffffffffu);          // tap 255 matches nothing
+      dv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[i]) {
+        const size_t o = ((size_t)(oh0 + a) * g.OW + (ow0 + b)) * g.C + cg * 8;
+        pr[i] = *reinterpret_cast<const uint2*>(arg_n + o);
+        dv[i] = *reinterpret_cast<const uint4*>(dy_n + o);
+      }
+    }
+  float f[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) unpack_bf16x8(dv[i], f[i]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = ((j < 4 ? pr[i].x : pr[i].y) >> (8 * (j & 3))) & 0xffu;
+    d[0][j] = (t[0] == 4u ? f[0][j] : 0.f);
+    d[1][j] = (t[0] == 5u ? f[0][j] : 0.f) + (t[1] == 3u ? f[1][j] : 0.f);
+    d[2][j] = (t[0] == 7u ? f[0][j] : 0.f) + (t[2] == 1u ? f[2][j] : 0.f);
+    d[3][j] = (t[0] == 8u ? f[0][j] : 0.f) + (t[1] == 6u ? f[1][j] : 0.f) + (t[2] == 2u ? f[2][j] : 0.f) +
+              (t[3] == 0u ? f[3][j] : 0.f);
   }
 }
 
@@ -419,23 +411,27 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bnpool_bwd_reduce(const __nv_b
     sh[j] = shift[tx * 8 + j];
   }
   if (ty < g.lanes) {
-    const int rows = pg.N * pg.H;
+    const int hp = pg.H >> 1, wq = pg.W >> 1;
+    const int rows = pg.N * hp;                                  // row PAIRS
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-      const int n = row / pg.H, h = row - n * pg.H;
-      const PoolWin rw = pool_windows(h, pg.OH);
+      const int n = row / hp, oh0 = row - n * hp;
       const size_t on = (size_t)n * pg.OH * pg.OW * pg.C;
-      const __nv_bfloat16* xr = x + (size_t)row * pg.W * pg.C + tx * 8;
-      for (int w = ty; w < pg.W; w += g.lanes) {
-        float d[8], a[8];
-        gather_pool_grad(dy + on, arg + on, pg, rw, w, tx, d);
-        ld8_stream(xr + (size_t)w * pg.C, a);
+      const __nv_bfloat16* xr = x + ((size_t)n * pg.H + 2 * oh0) * pg.W * pg.C + tx * 8;
+      for (int qd = ty; qd < wq; qd += g.lanes) {
+        float d[4][8], a[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float o = bf16_round(fmaxf(fmaf(a[j], sc[j], sh[j]), 0.f));
-          const float dd = o > 0.f ? d[j] : 0.f;
-          s[j] += dd;
-          q[j] = fmaf(dd, (a[j] - mu[j]) * rs[j], q[j]);
-        }
+        for (int p = 0; p < 4; ++p)
+          ld8_stream(xr + ((size_t)(p >> 1) * pg.W + 2 * qd + (p & 1)) * pg.C, a[p]);
+        quad_pool_grad(dy + on, arg + on, pg, oh0, qd, tx, d);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float o = bf16_round(fmaxf(fmaf(a[p][j], sc[j], sh[j]), 0.f));
+            const float dd = o > 0.f ? d[p][j] : 0.f;
+            s[j] += dd;
+            q[j] = fmaf(dd, (a[p][j] - mu[j]) * rs[j], q[j]);
+          }
       }
     }
   }
@@ -461,24 +457,28 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bnpool_bwd_apply(const __nv_bf
     sc[j] = scale[tx * 8 + j];
     sh[j] = shift[tx * 8 + j];
   }
-  const int rows = pg.N * pg.H;
+  const int hp = pg.H >> 1, wq = pg.W >> 1;
+  const int rows = pg.N * hp;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int n = row / pg.H, h = row - n * pg.H;
-    const PoolWin rw = pool_windows(h, pg.OH);
+    const int n = row / hp, oh0 = row - n * hp;
     const size_t on = (size_t)n * pg.OH * pg.OW * pg.C;
-    const size_t xoff = (size_t)row * pg.W * pg.C + tx * 8;
-    for (int w = ty; w < pg.W; w += g.lanes) {
-      float d[8], xv[8];
-      gather_pool_grad(dy + on, arg + on, pg, rw, w, tx, d);
-      const size_t off = xoff + (size_t)w * pg.C;
-      ld8_stream(x + off, xv);
+    const size_t xbase = ((size_t)n * pg.H + 2 * oh0) * pg.W * pg.C + tx * 8;
+    for (int qd = ty; qd < wq; qd += g.lanes) {
+      float d[4][8], xv[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float o = bf16_round(fmaxf(fmaf(xv[j], sc[j], sh[j]), 0.f));
-        const float dd = o > 0.f ? d[j] : 0.f;
-        xv[j] = fmaf(dd, a[j], fmaf(xv[j], b[j], c[j]));
+      for (int p = 0; p < 4; ++p)
+        ld8_stream(x + xbase + ((size_t)(p >> 1) * pg.W + 2 * qd + (p & 1)) * pg.C, xv[p]);
+      quad_pool_grad(dy + on, arg + on, pg, oh0, qd, tx, d);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float o = bf16_round(fmaxf(fmaf(xv[p][j], sc[j], sh[j]), 0.f));
+          const float dd = o > 0.f ? d[p][j] : 0.f;
+          xv[p][j] = fmaf(dd, a[j], fmaf(xv[p][j], b[j], c[j]));
+        }
+        st8(dx + xbase + ((size_t)(p >> 1) * pg.W + 2 * qd + (p & 1)) * pg.C, xv[p]);
       }
-      st8(dx + off, xv);
     }
   }
 }
@@ -625,7 +625,8 @@ void psb_bnpool_backward(cudaStream_t s, const void* dy, const void* arg, const 
   auto X = reinterpret_cast<const __nv_bfloat16*>(x);
   psb_count_launch(3);
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
-  const int rows_in = N * H;
+  // (H and W must be even: the quad decomposition above; the Python side falls back to the unfused pair otherwise)
+  const int rows_in = N * (H / 2);
   const int grid_rows = rows_in < grid ? rows_in : grid;
   psb_bnpool_bwd_reduce<<<grid_rows, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(DY, A, X, scale, shift, mean, rstd, sums, g, pg);
   psb_bn_bwd_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd, coef,

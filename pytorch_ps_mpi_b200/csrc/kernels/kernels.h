@@ -49,6 +49,7 @@ struct UpdateArgs {
   float* buf2;                         // max_exp_avg_sq
   const TileInfo* tiles;
   const uint8_t* active;               // per-parameter "got a gradient this step" (nullptr = all)
+  const float2* param_hyper;           // per-parameter {step_size, first_step} overriding the group's (nullptr = uniform)
   uint64_t* signal_local;
   uint64_t* signal_peer[PSB_MAX_RANKS];
   unsigned int* done_counter;          // zero before launch; the kernel leaves it zero

@@ -305,7 +305,15 @@ __device__ __forceinline__ void decode_dense(const uint4& v0, const uint4& v1, f
 template <int OPT>
 __device__ __forceinline__ void apply_and_publish(const UpdateArgs& a, const TileInfo& ti, size_t e0, float inv_count,
                                                   const float* acc, float* w, float* m, float* v, float* vm) {
-  const GroupHyper h = a.groups[ti.group];
+  GroupHyper h = a.groups[ti.group];
+  if (a.param_hyper != nullptr) {
+    // parameters whose step count differs from their group's (a gradient that first arrived late, a layer that was frozen
+    // for a while): the reference keeps state PER PARAMETER (/root/reference/ps.py:203-205,226-241), so the bias-corrected
+    // Adam step size and SGD's first-step momentum rule come from a per-parameter table
+    const float2 ph = a.param_hyper[ti.param];
+    h.step_size = ph.x;
+    h.first_step = ph.y != 0.f;
+  }
   float g[PSB_EPT];
 #pragma unroll
   for (int j = 0; j < PSB_EPT; ++j) g[j] = acc[j] * inv_count;
@@ -576,6 +584,11 @@ __global__ void __launch_bounds__(PSB_THREADS, 3) psb_update_kernel(const __grid
   }
 
   // ---- completion: the last CTA raises the epoch flags ----
+  // Launches that raise nothing (every pipeline chunk but the last; any launch at N = 1) skip the block: the system-scope
+  // fence + completion atomic cost each CTA a round trip its warps wait out at the barrier (ncu: `barrier` was the top
+  // stall of a 2-3-tile chunk launch).  Their stores are ordered before the last chunk's flag by the stream: a kernel's
+  // writes — peer and multimem stores included — are complete when the kernel is.
+  if (a.signal_mode == 0 && ack == 0u) return;
   __syncthreads();
   if (tid == 0) {
     __threadfence_system();

@@ -58,14 +58,29 @@ def spawn(fn: Callable, nprocs: int, args: Sequence = (), env: Optional[dict] = 
         p = ctx.Process(target=_entry, args=(r, fn, nprocs, port, tuple(args), dict(env or {}), errq))
         p.start()
         procs.append(p)
+    # ONE deadline for the whole group, and fail fast: as soon as any rank exits non-zero the others (which would sit in a
+    # barrier / device spin until their own time-outs) are terminated — a single failing rank used to cost nprocs x timeout
+    import time as _time
     failed = []
-    for p in procs:
-        p.join(timeout)
-        if p.is_alive():
-            failed.append(f"rank pid {p.pid} timed out after {timeout}s")
+    deadline = _time.time() + timeout
+    while True:
+        alive = [p for p in procs if p.is_alive()]
+        if not alive:
+            break
+        if any(p.exitcode not in (None, 0) for p in procs):
+            _time.sleep(2.0)                      # let the failing rank's traceback reach the queue
+            break
+        if _time.time() > deadline:
+            failed.append(f"{len(alive)} rank(s) still running after {timeout}s")
+            break
+        _time.sleep(0.05)
     for p in procs:
         if p.is_alive():
             p.terminate()          # exact processes we started
+    for p in procs:
+        p.join(10)
+        if p.is_alive():
+            p.kill()
             p.join(5)
     msgs = []
     while not errq.empty():

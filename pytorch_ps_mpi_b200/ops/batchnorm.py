@@ -68,8 +68,11 @@ class _FusedBNReLUPool(torch.autograd.Function):
 def fused_bn_relu_maxpool(x: torch.Tensor, bn: "FusedBatchNormAct2d", sums: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``max_pool2d(relu(bn(x)), 3, 2, 1)`` in training mode without materialising the BN output (experimental)."""
     assert bn.training and bn.relu and _kernel_ok(x, None, bn.weight)
+    if x.shape[2] % 2 or x.shape[3] % 2:       # the fused backward works on 2x2 input quads: odd sizes take the unfused pair
+        from .pooling import FusedMaxPool2d
+        return FusedMaxPool2d(3, 2, 1)(bn(x, sums=sums) if sums is not None else bn(x))
     if bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+        bn._nbt_pending += 1
     return _FusedBNReLUPool.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
                                   bn.momentum if bn.momentum is not None else 0.1, sums)
 
@@ -88,6 +91,23 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
     def __init__(self, num_features, eps=1e-5, momentum=0.1, relu: bool = False, **kw):
         super().__init__(num_features, eps=eps, momentum=momentum, affine=True, track_running_stats=True, **kw)
         self.relu = relu
+        # num_batches_tracked is only an input of the computation when momentum is None (cumulative average); with a fixed
+        # momentum it is bookkeeping, so the kernel path counts on the host and writes the buffer when somebody looks
+        # (state_dict / eval fallback) instead of launching one tiny add kernel per layer per step (20 per ResNet-18 step)
+        self._nbt_pending = 0
+
+    def _flush_batches_tracked(self):
+        if self._nbt_pending and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(self._nbt_pending)
+        self._nbt_pending = 0
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        self._flush_batches_tracked()
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._nbt_pending = 0
+        super()._load_from_state_dict(*args, **kwargs)
 
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
@@ -103,10 +123,14 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
         """``sums`` (experimental): fp32 ``[2C]`` = Σx | Σx² over N·H·W already computed by the producer of ``x``."""
         if _kernel_ok(x, residual, self.weight) and (self.training or self.running_mean is not None):
             if self.training and self.num_batches_tracked is not None:
-                self.num_batches_tracked.add_(1)
+                if self.momentum is None:
+                    self.num_batches_tracked.add_(1)
+                else:
+                    self._nbt_pending += 1
             return _FusedBN.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                                   self.eps, self.momentum if self.momentum is not None else 0.1, self.relu, self.training,
                                   sums)
+        self._flush_batches_tracked()
         rm, rv = self.running_mean, self.running_var
         w, b = self.weight, self.bias
         if rm is not None and rm.dtype != x.dtype and not x.is_cuda:

@@ -169,6 +169,13 @@ class DeviceEngine:
             self._expose_state()
         self._group_steps = [0] * len(opt.param_groups)
         self._hyper_cache = None
+        # per-parameter step counts (the reference keeps optimizer state per parameter and skips p.grad is None,
+        # ps.py:178-179,203-205,226-241).  While every parameter has fired on every step they all equal the group's count and
+        # the kernel uses the group tuple; after the first step that skipped a parameter a per-parameter table is uploaded.
+        self._param_steps = [0] * max(L.nparams, 1)
+        self._uniform_steps = True
+        self._phyper_host = torch.zeros(max(L.nparams, 1), 2, dtype=torch.float32).pin_memory()
+        self._phyper_dev = torch.zeros(max(L.nparams, 1), 2, dtype=torch.float32, device=self.device)
 
         # ---- publication / reduction strategy ----
         mc = A.has_multicast
@@ -269,6 +276,7 @@ class DeviceEngine:
         self._snap_version = 0
         self._snap_shadow = None
         self._step_hyp = None
+        self._phyper_ptr = 0
         self._update_spans: list = []
         # device-timeout surfacing: an async copy of SIG_ERROR into pinned memory every few steps, read one poll late
         self._err_host = torch.zeros(1, dtype=torch.int64).pin_memory()
@@ -346,7 +354,7 @@ class DeviceEngine:
             return
         o = self.opt
         for s in self.layout.slots:   # SGD too: the first-step momentum rule (ps.py:203-205) needs it on resume
-            o.state[s.param]["step"] = self._group_steps[s.group]
+            o.state[s.param]["step"] = self._param_steps[s.index] if self.mode != "async" else self._group_steps[s.group]
 
     def sync_state_from_torch(self, original=None):
         """After ``load_state_dict``: copy loaded tensors back into the flat (fp32) state.
@@ -370,12 +378,15 @@ class DeviceEngine:
                             self._like(buf[sl], s.param).copy_(st[key].to(buf.dtype))
                 if "step" in st:
                     self._group_steps[s.group] = max(self._group_steps[s.group], int(st["step"]))
+                    self._param_steps[s.index] = int(st["step"])
             if self.master is not None:
                 # parameters may have been re-loaded by the user: re-seed masters that lack a saved copy
                 for s in self.layout.slots:
                     src = original.get(id(s.param), {}) if original is not None else o.state.get(s.param, {})
                     if "master_param" not in src:
                         self._like(self.master[s.offset: s.offset + s.numel], s.param).copy_(s.param.data.float())
+        if any(self._param_steps[s.index] != self._group_steps[s.group] for s in self.layout.slots):
+            self._uniform_steps = False
         self._expose_state()
 
     # ------------------------------------------------------------------------------- backward
@@ -508,7 +519,8 @@ class DeviceEngine:
                              (0 if n == 1 else (1 if self.mode == "ps" else 2)) if last else 0,
                              active_ptr=active_ptr, timeout_s=self.timeout_s,
                              wait_mask=((1 << n) - 1) & ~(1 << self.rank), stream=csh,
-                             tile_begin=lo, tile_end=hi, wait_value=self._progress(epoch, k))
+                             tile_begin=lo, tile_end=hi, wait_value=self._progress(epoch, k),
+                             param_hyper=self._phyper_ptr)
             self.launches += 1
             if prof:
                 self._update_spans.append((ev_a, self._prof.mark(cs)))
@@ -536,7 +548,28 @@ class DeviceEngine:
         """This step's per-group hyper-parameter tuples (sampled once per step, at the first chunk that needs them)."""
         if self._step_hyp is None:
             self._step_hyp = self._hypers()
+            self._phyper_ptr = 0
+            if not self._uniform_steps and self.is_server:
+                self._phyper_ptr = self._upload_param_hypers()
         return self._step_hyp
+
+    def _upload_param_hypers(self) -> int:
+        """Per-parameter {step_size, first_step} for THIS step, assuming the parameter fires (tiles of parameters that do not
+        are skipped through the active mask, so their entries are never read)."""
+        o = self.opt
+        h = self._phyper_host
+        for sl in self.layout.slots:
+            t = self._param_steps[sl.index] + 1
+            g = o.param_groups[sl.group]
+            if o.optim == "adam":
+                b1, b2 = g["betas"]
+                h[sl.index, 0] = float(g["lr"]) * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+            else:
+                h[sl.index, 0] = 0.0
+            h[sl.index, 1] = 1.0 if t == 1 else 0.0
+        with torch.cuda.stream(self.comm_stream):
+            self._phyper_dev.copy_(h, non_blocking=True)
+        return self._phyper_dev.data_ptr()
 
     def _hypers(self) -> List[List[float]]:
         o = self.opt
@@ -658,6 +691,10 @@ class DeviceEngine:
         data["packaged_bytes"] = wire_bytes / nfired
         data["engine"] = "device"
         self._epoch += 1
+        if len(self._fired) != L.nparams:
+            self._uniform_steps = False              # some parameter sat this step out: per-parameter counts diverge from now on
+        for i in self._fired:
+            self._param_steps[i] += 1
         self._fired = set()
         self._keep_prev, self._keep = self._keep, []
         if done is None:                     # comm-stream completion marker of this step (see _flush)

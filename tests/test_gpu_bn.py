@@ -147,3 +147,17 @@ def test_gemm_stem_matches_conv2d():
     (gr,) = torch.autograd.grad(F.conv2d(x.float(), wref, None, 2, 3), [wref], g.bfloat16().float())
     assert gw.shape == conv.weight.shape
     assert torch.allclose(gw.float(), gr, rtol=5e-2, atol=5e-2 * gr.abs().max().item())
+
+
+def test_num_batches_tracked_is_counted_lazily():
+    """The kernel path counts training batches on the host and writes the buffer when it is looked at (state_dict)."""
+    import torch
+    from pytorch_ps_mpi_b200.ops.batchnorm import FusedBatchNormAct2d
+    dev = torch.device("cuda", 0)
+    bn = FusedBatchNormAct2d(16, relu=True).to(dev).bfloat16().train()
+    x = torch.randn(4, 16, 8, 8, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    for _ in range(3):
+        bn(x)
+    assert int(bn.state_dict()["num_batches_tracked"]) == 3
+    bn(x)
+    assert int(bn.state_dict()["num_batches_tracked"]) == 4

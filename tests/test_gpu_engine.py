@@ -267,3 +267,34 @@ def test_stem_weight_lives_in_gemm_layout_in_the_arena():
     opt.load_state_dict(sd)
     opt.close()
     assert torch.equal(model.conv1.weight.detach().float(), ref)
+
+
+@pytest.mark.parametrize("optim", ["sgd", "adam"])
+def test_late_parameter_keeps_its_own_step_count(optim):
+    """optimizer state is per PARAMETER (ps.py:178-179,203-205,226-241) — a parameter whose first gradient
+    arrives on step 3 starts its momentum with buf = d_p (dampening ignored) and Adam bias-corrects with ITS step count."""
+    dev = torch.device("cuda", 0)
+
+    def run(engine):
+        torch.manual_seed(0)
+        a = torch.nn.Parameter(torch.randn(5000, device=dev))
+        b = torch.nn.Parameter(torch.randn(3000, device=dev))
+        kw = dict(lr=0.1, momentum=0.9, dampening=0.5) if optim == "sgd" else dict(lr=0.05)
+        cls = ps.SGD if optim == "sgd" else ps.Adam
+        opt = cls([("a", a), ("b", b)], [a, b], engine=engine, **kw)
+        for s in range(6):
+            opt.zero_grad(set_to_none=True)
+            loss = (a * (s + 1.0)).sum() + ((b * b).sum() * 0.5 if s >= 2 else 0.0)
+            loss.backward()
+            opt.step()
+        torch.cuda.synchronize()
+        sd = opt.state_dict()
+        steps = [int(st["step"]) for st in sd["state"].values()] if engine == "device" else None
+        out = a.detach().clone(), b.detach().clone()
+        opt.close()
+        return out, steps
+
+    (a1, b1), steps = run("device")
+    (a2, b2), _ = run("host")
+    assert torch.allclose(a1, a2, rtol=1e-5, atol=1e-6) and torch.allclose(b1, b2, rtol=1e-5, atol=1e-6)
+    assert sorted(steps) == [4, 6]
