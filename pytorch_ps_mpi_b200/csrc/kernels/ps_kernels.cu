@@ -428,10 +428,17 @@ __global__ void __launch_bounds__(PSB_THREADS, 3) psb_update_kernel(const __grid
   }
 
   // ---- 1. the req.Wait() of the reference: every contributor's progress flag ----
+  // (the pipelined engine waits in a one-warp kernel queued just ahead of this one instead — a full update grid spinning
+  //  on its peers would hold every SM's registers while this rank's backward still runs; then only the error slot is checked:
+  //  a timed-out wait must not be followed by an update over stale tiles)
   if (a.wait_grads) {
     bool ok = true;
     if (tid < a.world && (contrib & a.wait_mask) >> tid & 1u)
       ok = spin_until_ge(a.signal_local + SIG_GRAD_READY + tid, a.wait_value, err_slot, a.timeout_ns);
+    if (!__syncthreads_and(ok)) return;
+  } else if (a.world > 1) {
+    bool ok = true;
+    if (tid == 0) ok = ld_relaxed_sys_u64(err_slot) == 0;
     if (!__syncthreads_and(ok)) return;
   }
 

@@ -515,10 +515,18 @@ class DeviceEngine:
             inv = (1.0 / n) if self.opt.average else 1.0
             prof = self._prof.enabled
             ev_a = self._prof.mark(cs) if prof else None
-            self.plan.launch(epoch, self._get_hypers(), (1 << n) - 1, inv, 1 if n > 1 else 0,
+            wait_mask = ((1 << n) - 1) & ~(1 << self.rank)
+            if n > 1:
+                # The req.Wait() for this chunk is a ONE-WARP kernel, not the update grid: 444 update CTAs spinning on the
+                # peers' flags would hold every SM's register file (3 x 256 threads x 77 registers) while this rank's own
+                # backward still has chunks k+1.. to produce — the skew between ranks would land on the critical path.
+                m.wait_flags(self.arena.local_ptr + self.off_signal, m.SIG_GRAD_READY, wait_mask, self._progress(epoch, k),
+                             self.timeout_s, csh)
+                self.launches += 1
+            self.plan.launch(epoch, self._get_hypers(), (1 << n) - 1, inv, 0,
                              (0 if n == 1 else (1 if self.mode == "ps" else 2)) if last else 0,
                              active_ptr=active_ptr, timeout_s=self.timeout_s,
-                             wait_mask=((1 << n) - 1) & ~(1 << self.rank), stream=csh,
+                             wait_mask=wait_mask, stream=csh,
                              tile_begin=lo, tile_end=hi, wait_value=self._progress(epoch, k),
                              param_hyper=self._phyper_ptr)
             self.launches += 1
