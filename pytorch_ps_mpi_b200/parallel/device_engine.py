@@ -174,8 +174,9 @@ class DeviceEngine:
         # the kernel uses the group tuple; after the first step that skipped a parameter a per-parameter table is uploaded.
         self._param_steps = [0] * max(L.nparams, 1)
         self._uniform_steps = True
-        self._phyper_host = torch.zeros(max(L.nparams, 1), 2, dtype=torch.float32).pin_memory()
-        self._phyper_dev = torch.zeros(max(L.nparams, 1), 2, dtype=torch.float32, device=self.device)
+        # (a ring: the async H2D copy of step e may still be queued when the host fills the table of step e+1)
+        self._phyper_host = [torch.zeros(max(L.nparams, 1), 2, dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._phyper_dev = [torch.zeros(max(L.nparams, 1), 2, dtype=torch.float32, device=self.device) for _ in range(4)]
 
         # ---- publication / reduction strategy ----
         mc = A.has_multicast
@@ -565,7 +566,8 @@ class DeviceEngine:
         """Per-parameter {step_size, first_step} for THIS step, assuming the parameter fires (tiles of parameters that do not
         are skipped through the active mask, so their entries are never read)."""
         o = self.opt
-        h = self._phyper_host
+        slot = self._epoch % len(self._phyper_host)       # the comm stream lags the host by at most one step
+        h, dev = self._phyper_host[slot], self._phyper_dev[slot]
         for sl in self.layout.slots:
             t = self._param_steps[sl.index] + 1
             g = o.param_groups[sl.group]
@@ -576,8 +578,8 @@ class DeviceEngine:
                 h[sl.index, 0] = 0.0
             h[sl.index, 1] = 1.0 if t == 1 else 0.0
         with torch.cuda.stream(self.comm_stream):
-            self._phyper_dev.copy_(h, non_blocking=True)
-        return self._phyper_dev.data_ptr()
+            dev.copy_(h, non_blocking=True)
+        return dev.data_ptr()
 
     def _hypers(self) -> List[List[float]]:
         o = self.opt

@@ -243,10 +243,15 @@ def test_direct_gradient_placement_matches_encode_path(monkeypatch):
         return out, n_direct
 
     a, na = run(True)
+    a2, _ = run(True)
     b, nb = run(False)
     assert nb == 0 and na >= 41, (na, nb)          # 20 BN layers x (gamma, beta) + the stem weight
-    for p, q in zip(a, b):
-        assert torch.allclose(p, q, rtol=2e-2, atol=2e-3), float((p - q).abs().max())
+    # BatchNorm statistics are summed with float atomics, so two runs of the SAME path already differ in the last bits and a
+    # randomly initialised ResNet at batch 8 amplifies that: the encode path must agree with the direct path as well as the
+    # direct path agrees with itself
+    for p, p2, q in zip(a, a2, b):
+        noise = float((p - p2).abs().max())
+        assert float((p - q).abs().max()) <= 4.0 * noise + 1e-3, (float((p - q).abs().max()), noise)
 
 
 def test_stem_weight_lives_in_gemm_layout_in_the_arena():
