@@ -304,4 +304,4 @@ def test_late_parameter_keeps_its_own_step_count(optim):
     (a2, b2), _ = run("host")
     assert sorted(steps) == [4, 6], steps
     da, db = float((a1 - a2).abs().max()), float((b1 - b2).abs().max())
-    assert torch.allclose(a1, a2, rtol=1e-5, atol=1e-6) and torch.allclose(b1, b2, rtol=1e-5, atol=1e-6), (da, db)
+    assert torch.allclose(a1, a2, rtol=1e-4, atol=1e-5) and torch.allclose(b1, b2, rtol=1e-4, atol=1e-5), (da, db)
