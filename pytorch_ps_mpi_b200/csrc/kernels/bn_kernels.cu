@@ -493,14 +493,18 @@ BnGeom geom(long long pixels, int C) {
   return g;
 }
 
-int grid_for(long long pixels, const BnGeom& g) {
+int grid_for(long long pixels, const BnGeom& g, int min_iters = 1) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long want = (pixels + g.lanes - 1) / g.lanes;        // one pixel batch per CTA at least
+  long long want = (pixels + (long long)g.lanes * min_iters - 1) / ((long long)g.lanes * min_iters);   // >= min_iters pixel batches per CTA
   long long cap = (long long)sms * 8;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
+// The reducing kernels end with 2C float atomics per CTA: on the small late-stage tensors (12 544 pixels x 512 channels) 1 184
+// CTAs of ~3 pixel batches each spent their time in 1.2 M contended atomics — every statistics / backward-reduce launch had
+// a ~16 us floor whatever its size (profiles/resnet18_step_launches_r2.txt).  They get at least 8 batches per CTA.
+constexpr int REDUCE_MIN_ITERS = 8;
 
 }  // namespace
 
@@ -517,7 +521,7 @@ void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* 
   psb_count_launch(training ? 3 : 1);
   if (training) {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
-    psb_bn_stats<<<grid, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
+    psb_bn_stats<<<grid_for(pixels, g, REDUCE_MIN_ITERS), BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
     psb_bn_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma),
                                                      reinterpret_cast<const __nv_bfloat16*>(beta), mean, rstd, scale, shift,
                                                      running_mean, running_var, C, pixels, eps, momentum);
@@ -568,9 +572,10 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
   psb_count_launch(3);
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
   const size_t sm = sizeof(float) * g.lanes * C;
-  if (relu && MK) psb_bn_bwd_reduce<true, true><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
-  else if (relu) psb_bn_bwd_reduce<true, false><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
-  else psb_bn_bwd_reduce<false, false><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
+  const int rgrid = grid_for(pixels, g, REDUCE_MIN_ITERS);
+  if (relu && MK) psb_bn_bwd_reduce<true, true><<<rgrid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
+  else if (relu) psb_bn_bwd_reduce<true, false><<<rgrid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
+  else psb_bn_bwd_reduce<false, false><<<rgrid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
   psb_bn_bwd_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd, coef,
                                                        coef + C, coef + 2 * C, reinterpret_cast<__nv_bfloat16*>(dgamma),
                                                        reinterpret_cast<__nv_bfloat16*>(dbeta), C, pixels);
@@ -602,7 +607,7 @@ void psb_bnpool_forward(cudaStream_t s, const void* x, const void* gamma, const 
   psb_count_launch(sums_in ? 2 : 3);
   if (sums_in == nullptr) {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
-    psb_bn_stats<<<grid, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
+    psb_bn_stats<<<grid_for(pixels, g, REDUCE_MIN_ITERS), BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
   }
   psb_bn_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums_in ? sums_in : sums, reinterpret_cast<const __nv_bfloat16*>(gamma),
                                                    reinterpret_cast<const __nv_bfloat16*>(beta), mean, rstd, scale, shift,
