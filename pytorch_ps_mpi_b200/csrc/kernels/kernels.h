@@ -131,14 +131,6 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
                      const float* rstd, float* sums, float* coef, void* dx, void* dres, void* dgamma, void* dbeta,
                      long long pixels, int C, int relu, const void* mask = nullptr /* the forward's ReLU bit mask, replaces y */);
 
-// EXPERIMENTAL fused BN + ReLU + 3x3/s2/p1 max-pool (bn_kernels.cu)
-void psb_bnpool_forward(cudaStream_t s, const void* x, const void* gamma, const void* beta, void* y, void* arg, float* sums,
-                        const float* sums_in, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
-                        float* running_var, int N, int H, int W, int C, float eps, float momentum);
-void psb_bnpool_backward(cudaStream_t s, const void* dy, const void* arg, const void* x, const void* gamma, const float* mean,
-                         const float* rstd, const float* scale, const float* shift, float* sums, float* coef, void* dx,
-                         void* dgamma, void* dbeta, int N, int H, int W, int C);
-
 // pool_kernels.cu — channels-last bf16 3x3/s2/p1 max pooling
 void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg, int N, int H, int W, int C);
 void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, void* dx, int N, int H, int W, int C);
