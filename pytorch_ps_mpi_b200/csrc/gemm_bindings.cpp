@@ -53,11 +53,12 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   auto y = at::empty({M, N}, x.options());
   if (M == 0) return y;
   // cta_group::2 (two SMs per 256x256 tile) whenever there are at least 256 rows; `variant & 15` forces 1-CTA (1) / 2-CTA (2).
-  // bits 4-7: epilogue of the 2-CTA kernel — 0 auto (TMA store when N % 8 == 0, else staged), 1 staged, 2 eight warps,
-  // 3 TMA store, 4 the round-1 row-strided stores;  bits 8-11: diagnostic mode (bench/gemm_variants.py)
-  const int base = variant & 15, epi_sel = (variant >> 4) & 15, dbg = (variant >> 8) & 15;
-  TORCH_CHECK(base <= 2 && epi_sel <= 4 && dbg <= 2, "unknown bcast_gemm variant ", variant);
-  TORCH_CHECK((epi_sel | dbg) == 0 || base == 2, "epilogue / diagnostic variants need the 2-CTA kernel (variant & 15 == 2)");
+  // bits 4-7: epilogue of the 2-CTA kernel — 0 auto (TMA store when N % 8 == 0, else staged), 1 staged, 3 TMA store,
+  // 4 the round-1 row-strided stores (bench/gemm_variants.py)
+  const int base = variant & 15, epi_sel = (variant >> 4) & 15;
+  TORCH_CHECK(base <= 2 && (epi_sel == 0 || epi_sel == 1 || epi_sel == 3 || epi_sel == 4) && (variant >> 8) == 0,
+              "unknown bcast_gemm variant ", variant);
+  TORCH_CHECK(epi_sel == 0 || base == 2, "epilogue variants need the 2-CTA kernel (variant & 15 == 2)");
   const int epi = epi_sel == 0 ? -1 : (epi_sel == 4 ? 0 : epi_sel);
   const bool two_cta = base == 2 || (base == 0 && M >= 256);
   CUtensorMap ma = make_map(reinterpret_cast<uint64_t>(x.data_ptr()), M, K, K, 128);
@@ -90,7 +91,7 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
       mc = make_map(reinterpret_cast<uint64_t>(y.data_ptr()), M, N, N, 32);      // box: 64 columns x 32 rows, 128B swizzle
       mcp = &mc;
     }
-    psb_launch_bcast_gemm2(stream, a, sms, epi, dbg, mcp);
+    psb_launch_bcast_gemm2(stream, a, sms, epi, mcp);
   } else {
     psb_launch_bcast_gemm(stream, a, sms);
   }

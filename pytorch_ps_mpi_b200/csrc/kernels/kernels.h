@@ -114,9 +114,8 @@ struct BcastGemmArgs {
   unsigned long long timeout_ns;
 };
 void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms);
-// bcast_gemm2.cu — the cta_group::2 kernel; epi -1 = auto (TMA-store / staged epilogue), 0..3 and dbg 1..2 = the
-// epilogue sweep / diagnostic builds of bench/gemm_variants.py
-void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out);
+// bcast_gemm2.cu — the cta_group::2 kernel; epi -1 = auto (TMA-store / staged epilogue), 0 / 1 / 3 = force (bench/gemm_variants.py)
+void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, const void* tmap_out);
 
 // bn_kernels.cu — fused channels-last bf16 BatchNorm (+residual, +ReLU), forward and backward
 void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y, float* sums,

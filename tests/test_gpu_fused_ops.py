@@ -70,7 +70,7 @@ def test_fused_stem_autograd_matches_default_path():
     assert _rel(grads[1], grads[0]) < 1e-2 and _rel(grads[2], grads[0]) < 1e-2
 
 
-@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4])   # 0 auto (TMA store / staged), 1 staged, 2 eight warps, 3 TMA store, 4 round-1
+@pytest.mark.parametrize("epi", [0, 1, 3, 4])   # 0 auto (TMA store / staged), 1 staged, 3 TMA store, 4 round-1 row-strided stores
 @pytest.mark.parametrize("mnk", [(512, 256, 128), (1000, 328, 264), (4096, 3072, 768), (300, 64, 176), (515, 330, 72)])
 def test_gemm_epilogue_variants(epi, mnk):
     from pytorch_ps_mpi_b200.ops.linear import bcast_linear
