@@ -6,10 +6,10 @@ Runs the production choice of ``psb_bcast_gemm2_kernel`` (``bcast_gemm2.cu``) ne
 
 * ``epi0`` the round-1 epilogue (lane == row, row-strided 16-byte stores),
 * ``epi1`` staged epilogue (padded smem transpose → full 128-byte lines),
-* ``epi2`` eight epilogue warps,
 * ``epi3`` TMA-store epilogue (swizzled staging, double-buffered ``cp.async.bulk.tensor`` stores; needs N % 8 == 0),
 
-each also as ``nostore`` (TMEM drained and packed, nothing written) and ``nomma`` (TMA + epilogue only).
+(the round-2 sweep also had an eight-warp epilogue and ``nostore`` / ``nomma`` diagnostic builds — rows ``epi2*`` / ``*.nostore`` /
+``*.nomma`` of ``profiles/gemm_variants_r2.jsonl``; they were deleted after the decision).
 Numerics of every storing variant are checked against an fp32 torch matmul first.  CUDA-event timing, L2 flushed
 between iterations, one JSON line per (shape, variant) on stdout and in ``gpurun_out/gemm_variants.jsonl``.
 
@@ -29,9 +29,8 @@ from pytorch_ps_mpi_b200.ops.linear import bcast_linear   # noqa: E402
 
 TWO_CTA = 2
 VARIANTS = [("prod", TWO_CTA)]            # epilogue selector 0 = the production choice (TMA store if N % 8 == 0, else staged)
-for epi, sel in ((0, 4), (1, 1), (2, 2), (3, 3)):   # kernel template EPI → selector bits of `variant`
-    for dbg, tag in ((0, ""), (1, ".nostore"), (2, ".nomma")):
-        VARIANTS.append((f"epi{epi}{tag}", TWO_CTA | sel << 4 | dbg << 8))
+for epi, sel in ((0, 4), (1, 1), (3, 3)):   # kernel template EPI → selector bits of `variant`
+    VARIANTS.append((f"epi{epi}", TWO_CTA | sel << 4))
 
 SHAPES = [("bert.ffn_in", 16384, 3072, 768), ("bert.qkv", 16384, 2304, 768), ("bert.ffn_out", 16384, 768, 3072),
           ("mlp.fc1", 8192, 4096, 784), ("stem", 256 * 112 * 112 // 8, 64, 176), ("square4096", 4096, 4096, 4096),

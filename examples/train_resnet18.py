@@ -20,6 +20,7 @@ torch.manual_seed(0)
 model = models.resnet18().to(dev).to(memory_format=torch.channels_last).bfloat16()
 opt = ps.SGD(model.named_parameters(), model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4,
              code=ps.Identity(), mode="ps", average=True, profile=True)   # engine='device' is picked automatically
+model.attach(opt)        # the fused stem kernel acquires the PS broadcast epoch itself: workers queue no wait kernel
 gen = torch.Generator().manual_seed(w.rank)
 for step in range(50):
     x = torch.randint(0, 256, (256, 3, 224, 224), dtype=torch.uint8, generator=gen).to(dev, non_blocking=True)

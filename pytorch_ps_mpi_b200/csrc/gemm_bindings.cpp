@@ -53,11 +53,12 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
   auto y = at::empty({M, N}, x.options());
   if (M == 0) return y;
   // cta_group::2 (two SMs per 256x256 tile) whenever there are at least 256 rows; `variant & 15` forces 1-CTA (1) / 2-CTA (2).
-  // bits 4-7: epilogue of the 2-CTA kernel — 0 auto (TMA store when N % 8 == 0, else staged), 1 staged, 2 eight warps,
-  // 3 TMA store, 4 the round-1 row-strided stores;  bits 8-11: diagnostic mode (bench/gemm_variants.py)
-  const int base = variant & 15, epi_sel = (variant >> 4) & 15, dbg = (variant >> 8) & 15;
-  TORCH_CHECK(base <= 2 && epi_sel <= 4 && dbg <= 2, "unknown bcast_gemm variant ", variant);
-  TORCH_CHECK((epi_sel | dbg) == 0 || base == 2, "epilogue / diagnostic variants need the 2-CTA kernel (variant & 15 == 2)");
+  // bits 4-7: epilogue of the 2-CTA kernel — 0 auto (TMA store when N % 8 == 0, else staged), 1 staged, 3 TMA store,
+  // 4 the round-1 row-strided stores (bench/gemm_variants.py)
+  const int base = variant & 15, epi_sel = (variant >> 4) & 15;
+  TORCH_CHECK(base <= 2 && (epi_sel == 0 || epi_sel == 1 || epi_sel == 3 || epi_sel == 4) && (variant >> 8) == 0,
+              "unknown bcast_gemm variant ", variant);
+  TORCH_CHECK(epi_sel == 0 || base == 2, "epilogue variants need the 2-CTA kernel (variant & 15 == 2)");
   const int epi = epi_sel == 0 ? -1 : (epi_sel == 4 ? 0 : epi_sel);
   const bool two_cta = base == 2 || (base == 0 && M >= 256);
   CUtensorMap ma = make_map(reinterpret_cast<uint64_t>(x.data_ptr()), M, K, K, 128);
@@ -90,7 +91,7 @@ at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K,
       mc = make_map(reinterpret_cast<uint64_t>(y.data_ptr()), M, N, N, 32);      // box: 64 columns x 32 rows, 128B swizzle
       mcp = &mc;
     }
-    psb_launch_bcast_gemm2(stream, a, sms, epi, dbg, mcp);
+    psb_launch_bcast_gemm2(stream, a, sms, epi, mcp);
   } else {
     psb_launch_bcast_gemm(stream, a, sms);
   }
@@ -175,55 +176,6 @@ std::vector<at::Tensor> bn_backward(const at::Tensor& dy, const at::Tensor& x, c
   cudaError_t e = cudaGetLastError();
   TORCH_CHECK(e == cudaSuccess, "psb_bn_backward: ", cudaGetErrorString(e));
   return {dx, dres, dgamma, dbeta};
-}
-
-// EXPERIMENTAL: training BatchNorm + ReLU + 3x3/s2/p1 max-pool in one pass.
-// returns (y_pooled, arg, mean, rstd, scale, shift); `sums` (optional, fp32 [2C]) skips the statistics pass
-std::vector<at::Tensor> bnpool_forward(const at::Tensor& x, const at::Tensor& gamma, const at::Tensor& beta, at::Tensor running_mean,
-                                       at::Tensor running_var, double eps, double momentum, c10::optional<at::Tensor> sums) {
-  check_nhwc(x, "x");
-  const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
-  TORCH_CHECK(C % 8 == 0 && C <= 2048, "channels must be a multiple of 8 and <= 2048");
-  TORCH_CHECK(running_mean.scalar_type() == at::kFloat && running_var.scalar_type() == at::kFloat, "running stats must be fp32");
-  const float* sums_in = nullptr;
-  if (sums.has_value() && sums->defined()) {
-    TORCH_CHECK(sums->is_cuda() && sums->scalar_type() == at::kFloat && sums->numel() == 2 * C && sums->is_contiguous(),
-                "sums must be a contiguous fp32 CUDA tensor of 2*C elements");
-    sums_in = sums->data_ptr<float>();
-  }
-  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  auto y = at::empty({N, C, OH, OW}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
-  auto arg = at::empty({N, C, OH, OW}, x.options().dtype(at::kByte).memory_format(at::MemoryFormat::ChannelsLast));
-  auto scratch = at::empty({6 * C}, x.options().dtype(at::kFloat));   // sums[2C] | mean | rstd | scale | shift
-  float* sp = scratch.data_ptr<float>();
-  psb_bnpool_forward(c10::cuda::getCurrentCUDAStream().stream(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
-                     arg.data_ptr(), sp, sums_in, sp + 2 * C, sp + 3 * C, sp + 4 * C, sp + 5 * C, running_mean.data_ptr<float>(),
-                     running_var.data_ptr<float>(), N, H, W, C, (float)eps, (float)momentum);
-  cudaError_t e = cudaGetLastError();
-  TORCH_CHECK(e == cudaSuccess, "psb_bnpool_forward: ", cudaGetErrorString(e));
-  return {y, arg, scratch.narrow(0, 2 * C, C), scratch.narrow(0, 3 * C, C), scratch.narrow(0, 4 * C, C), scratch.narrow(0, 5 * C, C)};
-}
-
-// returns (dx, dgamma, dbeta)
-std::vector<at::Tensor> bnpool_backward(const at::Tensor& dy, const at::Tensor& arg, const at::Tensor& x, const at::Tensor& gamma,
-                                        const at::Tensor& mean, const at::Tensor& rstd, const at::Tensor& scale,
-                                        const at::Tensor& shift) {
-  check_nhwc(dy, "dy");
-  check_nhwc(x, "x");
-  const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
-  TORCH_CHECK(dy.size(0) == N && dy.size(1) == C && dy.size(2) == (H - 1) / 2 + 1 && dy.size(3) == (W - 1) / 2 + 1, "dy shape mismatch");
-  TORCH_CHECK(arg.scalar_type() == at::kByte && arg.sizes() == dy.sizes() && arg.is_contiguous(at::MemoryFormat::ChannelsLast),
-              "arg must be the uint8 channels_last tensor returned by bnpool_forward");
-  auto dx = at::empty_like(x);
-  auto dgamma = at::empty_like(gamma), dbeta = at::empty_like(gamma);
-  auto scratch = at::empty({5 * C}, x.options().dtype(at::kFloat));
-  float* sp = scratch.data_ptr<float>();
-  psb_bnpool_backward(c10::cuda::getCurrentCUDAStream().stream(), dy.data_ptr(), arg.data_ptr(), x.data_ptr(), gamma.data_ptr(),
-                      mean.data_ptr<float>(), rstd.data_ptr<float>(), scale.data_ptr<float>(), shift.data_ptr<float>(), sp,
-                      sp + 2 * C, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), N, H, W, C);
-  cudaError_t e = cudaGetLastError();
-  TORCH_CHECK(e == cudaSuccess, "psb_bnpool_backward: ", cudaGetErrorString(e));
-  return {dx, dgamma, dbeta};
 }
 
 std::vector<at::Tensor> maxpool_forward(const at::Tensor& x) {
@@ -408,8 +360,6 @@ void bind_gemm(py::module_& m) {
   m.def("stem_wgrad_finalize", &stem_wgrad_finalize, py::arg("partial"), py::arg("out") = c10::nullopt,
         "sum the per-CTA partials → dW2d [64,176] bf16 (optionally straight into the PS wire arena)");
   m.def("stem_wgrad", &stem_wgrad, "implicit weight gradient of the stem → per-CTA fp32 partials [grid,176,64]");
-  m.def("bnpool_forward", &bnpool_forward, "EXPERIMENTAL: BatchNorm + ReLU + 3x3/s2 max-pool forward in one pass");
-  m.def("bnpool_backward", &bnpool_backward, "EXPERIMENTAL: backward of bnpool_forward (no materialised pool gradient)");
   m.def("bn_backward", &bn_backward, py::arg("dy"), py::arg("x"), py::arg("y"), py::arg("gamma"), py::arg("mean"), py::arg("rstd"),
         py::arg("relu"), py::arg("has_res"), py::arg("out_dgamma") = c10::nullopt, py::arg("out_dbeta") = c10::nullopt,
         "fused channels-last bf16 BatchNorm(+residual)(+ReLU) backward");

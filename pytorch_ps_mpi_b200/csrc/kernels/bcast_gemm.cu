@@ -172,7 +172,7 @@ int psb_bcast_gemm_smem_bytes() { return SMEM_BYTES; }
 
 void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms) {
   if (a.two_cta) {   // M >= 256: the cta_group::2 kernel with the TMA-store (or staged) epilogue, bcast_gemm2.cu
-    psb_launch_bcast_gemm2(s, a, num_sms, -1, 0, a.tmap_out);
+    psb_launch_bcast_gemm2(s, a, num_sms, -1, a.tmap_out);
     return;
   }
   static bool configured = false;

@@ -20,9 +20,9 @@
 //            16384x3072x768: 98.2 → 57.2 us (cuBLAS 62.4);  16384x2304x768: 74.5 → 45.9 us (cuBLAS 51.2).
 //   EPI = 1  (default otherwise)  staged epilogue: each warp transposes 32 rows x 64 columns through padded shared memory
 //            and writes full 128-byte lines (4 rows per store instruction); handles any N.
-//   EPI = 2  eight epilogue warps (two per TMEM lane quarter) — measured no better than EPI 0; kept for the sweep only.
-//   EPI = 0  the round-1 epilogue — kept for the sweep only.
-// Diagnostic modes (template DBG, bench only): 1 = drain + pack but never store, 2 = commit without issuing tcgen05.mma.
+//   EPI = 0  the round-1 epilogue — kept selectable (variant bits) as the A/B baseline of that measurement.
+// (The sweep also had an eight-epilogue-warp variant and "never store" / "never MMA" diagnostic builds; they decided nothing
+//  further — eight warps: 73.8 us on the same shape — and were deleted.  Their rows stay in profiles/gemm_variants_r2.jsonl.)
 #include "gemm_common.cuh"
 
 namespace {
@@ -30,7 +30,7 @@ namespace {
 template <int BNT, int EPI>
 struct CfgX {
   using C = Cfg2<BNT>;
-  static constexpr int EPI_WARPS = EPI == 2 ? 8 : 4;
+  static constexpr int EPI_WARPS = 4;
   static constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
   static constexpr int ROW_PITCH = 144;                                  // 128 B of bf16 + 16 B pad: conflict-free both ways
   static constexpr int BAR_BYTES = 1024;                                 // keeps the staging area 1024-byte aligned (swizzle)
@@ -63,7 +63,7 @@ __device__ __forceinline__ void finish32(const uint32_t* r, const GemmParams& p,
   }
 }
 
-template <int BNT, int EPI, int DBG>
+template <int BNT, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((CfgX<BNT, EPI>::NTHREADS), 1)
 psb_bcast_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ GemmParams p) {
@@ -150,14 +150,12 @@ psb_bcast_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           mbar_wait(&full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
-            if constexpr (DBG != 2) {
-              const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
-              const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + A2_BYTES);
+            const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
+            const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + A2_BYTES);
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                umma2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            }
-            umma_commit_2sm(&empty[stage]);      // with no MMA in flight the commit arrives at once
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            umma_commit_2sm(&empty[stage]);
             if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc]);
           }
           __syncwarp();
@@ -169,11 +167,10 @@ psb_bcast_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   } else {
     // ===================== epilogue =====================
     const int quarter = warp & 3;                                     // the TMEM lane quarter this warp may read
-    const int half = EPI == 2 ? ((warp - 2) >> 2) : 0;
-    constexpr int COLS_PER_WARP = EPI == 2 ? BN2 / 2 : BN2;
-    const int cbeg = half * COLS_PER_WARP;
+    constexpr int COLS_PER_WARP = BN2;
+    constexpr int cbeg = 0;
     const bool vec_ok = (p.N % 8) == 0;
-    const bool store = DBG != 1 || p.M < 0;                           // DBG 1: never true, but not provably so
+    constexpr bool store = true;
     uint32_t acc = 0, acc_phase = 0;
     [[maybe_unused]] uint32_t nchunk = 0;                              // EPI 3: staging-buffer parity
     for (int tile = cl; tile < num_tiles; tile += ncl) {
@@ -291,41 +288,32 @@ psb_bcast_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
-template <int BNT, int EPI, int DBG>
+template <int BNT, int EPI>
 void launch_x(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
               int clusters) {
   using X = CfgX<BNT, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<BNT, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM_BYTES);
+    cudaFuncSetAttribute(psb_bcast_gemm2_kernel<BNT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, X::SMEM_BYTES);
     configured = true;
   }
-  psb_bcast_gemm2_kernel<BNT, EPI, DBG><<<2 * clusters, X::NTHREADS, X::SMEM_BYTES, s>>>(ta, tb, tc, p);
-}
-
-template <int BNT, int EPI>
-void launch_d(cudaStream_t s, int dbg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
-              int clusters) {
-  if (dbg == 1) launch_x<BNT, EPI, 1>(s, ta, tb, tc, p, clusters);
-  else if (dbg == 2) launch_x<BNT, EPI, 2>(s, ta, tb, tc, p, clusters);
-  else launch_x<BNT, EPI, 0>(s, ta, tb, tc, p, clusters);
+  psb_bcast_gemm2_kernel<BNT, EPI><<<2 * clusters, X::NTHREADS, X::SMEM_BYTES, s>>>(ta, tb, tc, p);
 }
 
 template <int BNT>
-void launch_e(cudaStream_t s, int epi, int dbg, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+void launch_e(cudaStream_t s, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
               const GemmParams& p, int clusters) {
-  if (epi == 1) launch_d<BNT, 1>(s, dbg, ta, tb, tc, p, clusters);
-  else if (epi == 2) launch_d<BNT, 2>(s, dbg, ta, tb, tc, p, clusters);
-  else if (epi == 3) launch_d<BNT, 3>(s, dbg, ta, tb, tc, p, clusters);
-  else launch_d<BNT, 0>(s, dbg, ta, tb, tc, p, clusters);
+  if (epi == 1) launch_x<BNT, 1>(s, ta, tb, tc, p, clusters);
+  else if (epi == 3) launch_x<BNT, 3>(s, ta, tb, tc, p, clusters);
+  else launch_x<BNT, 0>(s, ta, tb, tc, p, clusters);
 }
 
 }  // namespace
 
 // `a.two_cta` must be set (the tensor maps are built for the 2-CTA box shapes).
-// epi: -1 = auto (TMA store when N % 8 == 0 and `tmap_out` is given, else staged), 0..3 = force (see top);  dbg: 0..2.
+// epi: -1 = auto (TMA store when N % 8 == 0 and `tmap_out` is given, else staged), 0 / 1 / 3 = force (see top).
 // `tmap_out` (EPI 3): CUtensorMap of the [M, N] bf16 output, box 64 columns x 32 rows, SWIZZLE_128B.
-void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out) {
+void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, const void* tmap_out) {
   if (epi < 0) epi = (tmap_out != nullptr && a.N % 8 == 0) ? 3 : 1;
   GemmParams p{};
   p.bias = a.bias;
@@ -343,7 +331,7 @@ void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms,
   const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(a.tmap_a);
   const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(a.tmap_b);
   const CUtensorMap& tc = tmap_out != nullptr ? *reinterpret_cast<const CUtensorMap*>(tmap_out) : ta;   // unused unless EPI 3
-  if (bnt == 64) launch_e<64>(s, epi, dbg, ta, tb, tc, p, clusters);
-  else if (bnt == 128) launch_e<128>(s, epi, dbg, ta, tb, tc, p, clusters);
-  else launch_e<256>(s, epi, dbg, ta, tb, tc, p, clusters);
+  if (bnt == 64) launch_e<64>(s, epi, ta, tb, tc, p, clusters);
+  else if (bnt == 128) launch_e<128>(s, epi, ta, tb, tc, p, clusters);
+  else launch_e<256>(s, epi, ta, tb, tc, p, clusters);
 }

@@ -285,204 +285,10 @@ __global__ void __launch_bounds__(BN_THREADS) psb_bn_bwd_apply(const __nv_bfloat
   }
 }
 
-// ==========================================================================================================
-// EXPERIMENTAL (opt-in, PSB200_BNPOOL=fused): BatchNorm-apply + ReLU + 3x3/s2/p1 max-pool in ONE pass, forward and
-// backward — the ResNet stem tail.  Unfused, the 411 MB BN output (batch 256) is written, read back by the pool, and
-// in backward the pool gradient is materialised (411 MB) and read twice together with the BN output (ReLU mask):
-//   forward : psb_bnrelu_pool_fwd   reads x once, writes the pooled tensor + 1-byte window positions
-//   backward: psb_bnpool_bwd_reduce / psb_bnpool_bwd_apply GATHER dy from (dy_pooled, arg) on the fly and recompute
-//             the ReLU mask from x·scale+shift, so neither the BN output nor the un-pooled gradient ever exists.
-// Values are rounded to bf16 before the max exactly as the unfused pair does, so the forward is bit-identical.
-// ==========================================================================================================
-struct BnPoolGeom {
-  int N, H, W, C, OH, OW, groups;
-};
-
-__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-
-// One CTA walks whole OUTPUT rows (n, oh): row / column indices are 32-bit and computed once per row / pixel (the first
-// version did a 64-bit div/mod chain per 16 bytes and ran at 1.5 TB/s; bench/bnpool_check.py).  tx = channel group of 8,
-// ty = pixel lane; a warp covers 32 / groups consecutive pixels = contiguous NHWC bytes.
-__global__ void __launch_bounds__(BN_THREADS) psb_bnrelu_pool_fwd(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
-                                                                  const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
-                                                                  uint8_t* __restrict__ arg, BnPoolGeom g, int lanes) {
-  const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
-  if (ty >= lanes) return;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sc[j] = scale[tx * 8 + j], sh[j] = shift[tx * 8 + j];
-  const int rows = g.N * g.OH;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int n = row / g.OH, oh = row - n * g.OH;
-    const int h0 = oh * 2 - 1;
-    const __nv_bfloat16* xin = x + (size_t)n * g.H * g.W * g.C + tx * 8;
-    for (int ow = ty; ow < g.OW; ow += lanes) {
-      const int w0 = ow * 2 - 1;
-      float best[8];
-      uint32_t pos[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) best[j] = -INFINITY, pos[j] = 255;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int h = h0 + kh;
-        if (h < 0 || h >= g.H) continue;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int w = w0 + kw;
-          if (w < 0 || w >= g.W) continue;
-          float v[8];
-          ld8(xin + ((size_t)h * g.W + w) * g.C, v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float z = bf16_round(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f));
-            if (z > best[j]) {             // strictly greater: the first maximum wins ties (ATen's rule)
-              best[j] = z;
-              pos[j] = kh * 3 + kw;
-            }
-          }
-        }
-      }
-      const size_t o = ((size_t)row * g.OW + ow) * g.C + tx * 8;
-      st8(y + o, best);
-      *reinterpret_cast<uint2*>(arg + o) =
-          make_uint2(pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24), pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24));
-    }
-  }
-}
-
-// ---- backward of the fused BN + ReLU + max-pool, organised by 2x2 input QUADS (H and W even) ------------------------------
-// The quad of input pixels (h0..h0+1, w0..w0+1), h0 / w0 even, is covered by exactly the four pooling windows
-// (oh0 + a, ow0 + b), oh0 = h0/2, ow0 = w0/2, a, b in {0,1}, and the nine taps of those windows that fall INTO the quad
-// partition 0..8:  window (0,0): taps 4,5,7,8 → pixels (0,0),(0,1),(1,0),(1,1);  (0,1): taps 3,6 → (0,1),(1,1);
-// (1,0): taps 1,2 → (1,0),(1,1);  (1,1): tap 0 → (1,1).  So one thread loads 4 x (arg 8 B + dy 16 B) for 4 pixels x 8 channels
-// (the per-pixel gather of the first version loaded 2.25 windows per pixel behind data-dependent branches and was latency-bound:
-// 1.15 ms vs 0.71 ms unfused, bench/bnpool_check.py), all loads issued before any is consumed.
-__device__ __forceinline__ void quad_pool_grad(const __nv_bfloat16* __restrict__ dy_n, const uint8_t* __restrict__ arg_n,
-                                               const BnPoolGeom& g, int oh0, int ow0, int cg, float (&d)[4][8]) {
-  uint2 pr[4];
-  uint4 dv[4];
-  bool ok[4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int i = a * 2 + b;
-      ok[i] = (oh0 + a < g.OH) && (ow0 + b < g.OW);
-      pr[i] = make_uint2(0xffffffffu, 0xffffffffu);          // tap 255 matches nothing
-      dv[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok[i]) {
-        const size_t o = ((size_t)(oh0 + a) * g.OW + (ow0 + b)) * g.C + cg * 8;
-        pr[i] = *reinterpret_cast<const uint2*>(arg_n + o);
-        dv[i] = *reinterpret_cast<const uint4*>(dy_n + o);
-      }
-    }
-  float f[4][8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) unpack_bf16x8(dv[i], f[i]);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint32_t t[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) t[i] = ((j < 4 ? pr[i].x : pr[i].y) >> (8 * (j & 3))) & 0xffu;
-    d[0][j] = (t[0] == 4u ? f[0][j] : 0.f);
-    d[1][j] = (t[0] == 5u ? f[0][j] : 0.f) + (t[1] == 3u ? f[1][j] : 0.f);
-    d[2][j] = (t[0] == 7u ? f[0][j] : 0.f) + (t[2] == 1u ? f[2][j] : 0.f);
-    d[3][j] = (t[0] == 8u ? f[0][j] : 0.f) + (t[1] == 6u ? f[1][j] : 0.f) + (t[2] == 2u ? f[2][j] : 0.f) +
-              (t[3] == 0u ? f[3][j] : 0.f);
-  }
-}
-
-// Σ dy' and Σ dy'·x̂ over all input pixels (dy' = pooled gradient gathered back, masked by the recomputed ReLU)
-__global__ void __launch_bounds__(BN_THREADS) psb_bnpool_bwd_reduce(const __nv_bfloat16* __restrict__ dy,
-                                                                     const uint8_t* __restrict__ arg,
-                                                                     const __nv_bfloat16* __restrict__ x,
-                                                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                     float* __restrict__ sums, BnGeom g, BnPoolGeom pg) {
-  extern __shared__ float smem[];
-  const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
-  float s[8], q[8], mu[8], rs[8], sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    s[j] = q[j] = 0.f;
-    mu[j] = mean[tx * 8 + j];
-    rs[j] = rstd[tx * 8 + j];
-    sc[j] = scale[tx * 8 + j];
-    sh[j] = shift[tx * 8 + j];
-  }
-  if (ty < g.lanes) {
-    const int hp = pg.H >> 1, wq = pg.W >> 1;
-    const int rows = pg.N * hp;                                  // row PAIRS
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-      const int n = row / hp, oh0 = row - n * hp;
-      const size_t on = (size_t)n * pg.OH * pg.OW * pg.C;
-      const __nv_bfloat16* xr = x + ((size_t)n * pg.H + 2 * oh0) * pg.W * pg.C + tx * 8;
-      for (int qd = ty; qd < wq; qd += g.lanes) {
-        float d[4][8], a[4][8];
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-          ld8_stream(xr + ((size_t)(p >> 1) * pg.W + 2 * qd + (p & 1)) * pg.C, a[p]);
-        quad_pool_grad(dy + on, arg + on, pg, oh0, qd, tx, d);
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float o = bf16_round(fmaxf(fmaf(a[p][j], sc[j], sh[j]), 0.f));
-            const float dd = o > 0.f ? d[p][j] : 0.f;
-            s[j] += dd;
-            q[j] = fmaf(dd, (a[p][j] - mu[j]) * rs[j], q[j]);
-          }
-      }
-    }
-  }
-  reduce_lanes_atomic(smem, s, tx, ty, g, sums);
-  reduce_lanes_atomic(smem, q, tx, ty, g, sums + g.C);
-}
-
-__global__ void __launch_bounds__(BN_THREADS) psb_bnpool_bwd_apply(const __nv_bfloat16* __restrict__ dy,
-                                                                    const uint8_t* __restrict__ arg,
-                                                                    const __nv_bfloat16* __restrict__ x,
-                                                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                    const float* __restrict__ ca, const float* __restrict__ cb,
-                                                                    const float* __restrict__ cc, __nv_bfloat16* __restrict__ dx,
-                                                                    BnGeom g, BnPoolGeom pg) {
-  const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
-  if (ty >= g.lanes) return;
-  float a[8], b[8], c[8], sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    a[j] = ca[tx * 8 + j];
-    b[j] = cb[tx * 8 + j];
-    c[j] = cc[tx * 8 + j];
-    sc[j] = scale[tx * 8 + j];
-    sh[j] = shift[tx * 8 + j];
-  }
-  const int hp = pg.H >> 1, wq = pg.W >> 1;
-  const int rows = pg.N * hp;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int n = row / hp, oh0 = row - n * hp;
-    const size_t on = (size_t)n * pg.OH * pg.OW * pg.C;
-    const size_t xbase = ((size_t)n * pg.H + 2 * oh0) * pg.W * pg.C + tx * 8;
-    for (int qd = ty; qd < wq; qd += g.lanes) {
-      float d[4][8], xv[4][8];
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-        ld8_stream(x + xbase + ((size_t)(p >> 1) * pg.W + 2 * qd + (p & 1)) * pg.C, xv[p]);
-      quad_pool_grad(dy + on, arg + on, pg, oh0, qd, tx, d);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float o = bf16_round(fmaxf(fmaf(xv[p][j], sc[j], sh[j]), 0.f));
-          const float dd = o > 0.f ? d[p][j] : 0.f;
-          xv[p][j] = fmaf(dd, a[j], fmaf(xv[p][j], b[j], c[j]));
-        }
-        st8(dx + xbase + ((size_t)(p >> 1) * pg.W + 2 * qd + (p & 1)) * pg.C, xv[p]);
-      }
-    }
-  }
-}
-
+// (A fused BatchNorm-apply + ReLU + 3x3/s2 max-pool pair lived here in round 2: per-pixel gather, then a 2x2-quad backward.
+//  It was correct but never beat the unfused kernels once those got the 1-bit ReLU mask and the quad max-pool backward —
+//  forward 0.39 vs 0.49 ms, forward+backward 1.31 vs 1.19 ms at batch 256 — and was deleted; the measurements are in
+//  profiles/bnpool_fusion_REJECTED.jsonl.)
 BnGeom geom(long long pixels, int C) {
   BnGeom g;
   g.pixels = pixels;
@@ -493,14 +299,18 @@ BnGeom geom(long long pixels, int C) {
   return g;
 }
 
-int grid_for(long long pixels, const BnGeom& g) {
+int grid_for(long long pixels, const BnGeom& g, int min_iters = 1) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long want = (pixels + g.lanes - 1) / g.lanes;        // one pixel batch per CTA at least
+  long long want = (pixels + (long long)g.lanes * min_iters - 1) / ((long long)g.lanes * min_iters);   // >= min_iters pixel batches per CTA
   long long cap = (long long)sms * 8;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
+// The reducing kernels end with 2C float atomics per CTA: on the small late-stage tensors (12 544 pixels x 512 channels) 1 184
+// CTAs of ~3 pixel batches each spent their time in 1.2 M contended atomics — every statistics / backward-reduce launch had
+// a ~16 us floor whatever its size (profiles/resnet18_step_launches_r2.txt).  They get at least 8 batches per CTA.
+constexpr int REDUCE_MIN_ITERS = 8;
 
 }  // namespace
 
@@ -517,7 +327,7 @@ void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* 
   psb_count_launch(training ? 3 : 1);
   if (training) {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
-    psb_bn_stats<<<grid, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
+    psb_bn_stats<<<grid_for(pixels, g, REDUCE_MIN_ITERS), BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
     psb_bn_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma),
                                                      reinterpret_cast<const __nv_bfloat16*>(beta), mean, rstd, scale, shift,
                                                      running_mean, running_var, C, pixels, eps, momentum);
@@ -568,9 +378,10 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
   psb_count_launch(3);
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
   const size_t sm = sizeof(float) * g.lanes * C;
-  if (relu && MK) psb_bn_bwd_reduce<true, true><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
-  else if (relu) psb_bn_bwd_reduce<true, false><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
-  else psb_bn_bwd_reduce<false, false><<<grid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
+  const int rgrid = grid_for(pixels, g, REDUCE_MIN_ITERS);
+  if (relu && MK) psb_bn_bwd_reduce<true, true><<<rgrid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
+  else if (relu) psb_bn_bwd_reduce<true, false><<<rgrid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
+  else psb_bn_bwd_reduce<false, false><<<rgrid, BN_THREADS, sm, s>>>(DY, X, Y, MK, mean, rstd, sums, g);
   psb_bn_bwd_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd, coef,
                                                        coef + C, coef + 2 * C, reinterpret_cast<__nv_bfloat16*>(dgamma),
                                                        reinterpret_cast<__nv_bfloat16*>(dbeta), C, pixels);
@@ -588,50 +399,4 @@ void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* 
     else PSB_APPLY(false, false, false);
   }
 #undef PSB_APPLY
-}
-
-// ---- EXPERIMENTAL fused BN + ReLU + 3x3/s2/p1 max-pool (training) -------------------------------------------------
-// `sums_in` != nullptr: Σx / Σx² were produced elsewhere (fused stem epilogue) and the statistics pass is skipped.
-void psb_bnpool_forward(cudaStream_t s, const void* x, const void* gamma, const void* beta, void* y, void* arg, float* sums,
-                        const float* sums_in, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
-                        float* running_var, int N, int H, int W, int C, float eps, float momentum) {
-  const long long pixels = (long long)N * H * W;
-  const BnGeom g = geom(pixels, C);
-  const int grid = grid_for(pixels, g);
-  auto X = reinterpret_cast<const __nv_bfloat16*>(x);
-  psb_count_launch(sums_in ? 2 : 3);
-  if (sums_in == nullptr) {
-    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
-    psb_bn_stats<<<grid, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(X, sums, g);
-  }
-  psb_bn_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums_in ? sums_in : sums, reinterpret_cast<const __nv_bfloat16*>(gamma),
-                                                   reinterpret_cast<const __nv_bfloat16*>(beta), mean, rstd, scale, shift,
-                                                   running_mean, running_var, C, pixels, eps, momentum);
-  BnPoolGeom pg{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
-  const int rows_out = N * pg.OH, cap = grid_for(pixels, g);
-  psb_bnrelu_pool_fwd<<<rows_out < cap ? rows_out : cap, BN_THREADS, 0, s>>>(
-      X, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<uint8_t*>(arg), pg, g.lanes);
-}
-
-void psb_bnpool_backward(cudaStream_t s, const void* dy, const void* arg, const void* x, const void* gamma, const float* mean,
-                         const float* rstd, const float* scale, const float* shift, float* sums /*2C*/, float* coef /*3C*/,
-                         void* dx, void* dgamma, void* dbeta, int N, int H, int W, int C) {
-  const long long pixels = (long long)N * H * W;
-  const BnGeom g = geom(pixels, C);
-  const int grid = grid_for(pixels, g);
-  BnPoolGeom pg{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
-  auto DY = reinterpret_cast<const __nv_bfloat16*>(dy);
-  auto A = reinterpret_cast<const uint8_t*>(arg);
-  auto X = reinterpret_cast<const __nv_bfloat16*>(x);
-  psb_count_launch(3);
-  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, s);
-  // (H and W must be even: the quad decomposition above; the Python side falls back to the unfused pair otherwise)
-  const int rows_in = N * (H / 2);
-  const int grid_rows = rows_in < grid ? rows_in : grid;
-  psb_bnpool_bwd_reduce<<<grid_rows, BN_THREADS, sizeof(float) * g.lanes * C, s>>>(DY, A, X, scale, shift, mean, rstd, sums, g, pg);
-  psb_bn_bwd_finalize<<<(C + 127) / 128, 128, 0, s>>>(sums, reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd, coef,
-                                                       coef + C, coef + 2 * C, reinterpret_cast<__nv_bfloat16*>(dgamma),
-                                                       reinterpret_cast<__nv_bfloat16*>(dbeta), C, pixels);
-  psb_bnpool_bwd_apply<<<grid_rows, BN_THREADS, 0, s>>>(DY, A, X, scale, shift, coef, coef + C, coef + 2 * C,
-                                                   reinterpret_cast<__nv_bfloat16*>(dx), g, pg);
 }

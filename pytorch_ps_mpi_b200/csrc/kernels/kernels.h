@@ -114,9 +114,8 @@ struct BcastGemmArgs {
   unsigned long long timeout_ns;
 };
 void psb_launch_bcast_gemm(cudaStream_t s, const BcastGemmArgs& a, int num_sms);
-// bcast_gemm2.cu — the cta_group::2 kernel; epi -1 = auto (TMA-store / staged epilogue), 0..3 and dbg 1..2 = the
-// epilogue sweep / diagnostic builds of bench/gemm_variants.py
-void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, int dbg, const void* tmap_out);
+// bcast_gemm2.cu — the cta_group::2 kernel; epi -1 = auto (TMA-store / staged epilogue), 0 / 1 / 3 = force (bench/gemm_variants.py)
+void psb_launch_bcast_gemm2(cudaStream_t s, const BcastGemmArgs& a, int num_sms, int epi, const void* tmap_out);
 
 // bn_kernels.cu — fused channels-last bf16 BatchNorm (+residual, +ReLU), forward and backward
 void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y, float* sums,
@@ -130,14 +129,6 @@ void psb_bn_forward_presummed(cudaStream_t s, const void* x, const void* res, co
 void psb_bn_backward(cudaStream_t s, const void* dy, const void* x, const void* y, const void* gamma, const float* mean,
                      const float* rstd, float* sums, float* coef, void* dx, void* dres, void* dgamma, void* dbeta,
                      long long pixels, int C, int relu, const void* mask = nullptr /* the forward's ReLU bit mask, replaces y */);
-
-// EXPERIMENTAL fused BN + ReLU + 3x3/s2/p1 max-pool (bn_kernels.cu)
-void psb_bnpool_forward(cudaStream_t s, const void* x, const void* gamma, const void* beta, void* y, void* arg, float* sums,
-                        const float* sums_in, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
-                        float* running_var, int N, int H, int W, int C, float eps, float momentum);
-void psb_bnpool_backward(cudaStream_t s, const void* dy, const void* arg, const void* x, const void* gamma, const float* mean,
-                         const float* rstd, const float* scale, const float* shift, float* sums, float* coef, void* dx,
-                         void* dgamma, void* dbeta, int N, int H, int W, int C);
 
 // pool_kernels.cu — channels-last bf16 3x3/s2/p1 max pooling
 void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg, int N, int H, int W, int C);

@@ -98,6 +98,105 @@ __global__ void __launch_bounds__(256) psb_maxpool_bwd(const __nv_bfloat16* __re
   }
 }
 
+// ---- row-based variants (round 2) -----------------------------------------------------------------------------------
+// The kernels above spend most of their instructions on 64-bit div/mod index chains (one per 16 bytes) and ran at 2.7 / 1.6
+// TB/s (profiles/resnet18_step_launches_r2.txt: 207 + 350 us for 565 MB each).  Here a CTA walks whole rows with 32-bit
+// indices; tx = channel group of 8, ty = pixel lane, so a warp covers 32 / groups consecutive NHWC pixels.
+__global__ void __launch_bounds__(256) psb_maxpool_fwd_rows(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                            uint8_t* __restrict__ arg, PoolGeom g, int lanes) {
+  const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
+  if (ty >= lanes) return;
+  const int rows = g.N * g.OH;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / g.OH, oh = row - n * g.OH;
+    const int h0 = oh * 2 - 1;
+    const __nv_bfloat16* xin = x + (size_t)n * g.H * g.W * g.C + tx * 8;
+    for (int ow = ty; ow < g.OW; ow += lanes) {
+      const int w0 = ow * 2 - 1;
+      float best[8];
+      uint32_t pos[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) best[j] = -INFINITY, pos[j] = 255;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h = h0 + kh;
+        if (h < 0 || h >= g.H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int w = w0 + kw;
+          if (w < 0 || w >= g.W) continue;
+          float v[8];
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(xin + ((size_t)h * g.W + w) * g.C), v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > best[j]) {          // strictly greater: the first maximum wins ties (ATen's rule)
+              best[j] = v[j];
+              pos[j] = kh * 3 + kw;
+            }
+        }
+      }
+      const size_t o = ((size_t)row * g.OW + ow) * g.C + tx * 8;
+      *reinterpret_cast<uint4*>(y + o) = make_uint4(pack_bf16x2(best[0], best[1]), pack_bf16x2(best[2], best[3]),
+                                                    pack_bf16x2(best[4], best[5]), pack_bf16x2(best[6], best[7]));
+      *reinterpret_cast<uint2*>(arg + o) = make_uint2(pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24),
+                                                      pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24));
+    }
+  }
+}
+
+// Backward by 2x2 input QUADS (H, W even): the quad (h0..h0+1, w0..w0+1), h0 / w0 even, is covered by exactly the four windows
+// (oh0 + a, ow0 + b), oh0 = h0/2, ow0 = w0/2, and the nine window taps that fall into the quad partition 0..8 —
+// window (0,0): taps 4,5,7,8 → pixels (0,0),(0,1),(1,0),(1,1);  (0,1): taps 3,6 → (0,1),(1,1);  (1,0): taps 1,2 → (1,0),(1,1);
+// (1,1): tap 0 → (1,1).  One thread: 4 x (arg 8 B + dy 16 B) in, 4 x 16 B of dx out, no branches on loaded data.
+__global__ void __launch_bounds__(256) psb_maxpool_bwd_quads(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ arg,
+                                                             __nv_bfloat16* __restrict__ dx, PoolGeom g, int lanes) {
+  const int tx = threadIdx.x % g.groups, ty = threadIdx.x / g.groups;
+  if (ty >= lanes) return;
+  const int hp = g.H >> 1, wq = g.W >> 1;
+  const int rows = g.N * hp;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / hp, oh0 = row - n * hp;
+    const size_t on = (size_t)n * g.OH * g.OW * g.C + tx * 8;
+    const size_t xbase = ((size_t)n * g.H + 2 * oh0) * g.W * g.C + tx * 8;
+    for (int qd = ty; qd < wq; qd += lanes) {
+      uint2 pr[4];
+      uint4 dv[4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int i = a * 2 + b;
+          pr[i] = make_uint2(0xffffffffu, 0xffffffffu);          // tap 255 matches nothing
+          dv[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (oh0 + a < g.OH && qd + b < g.OW) {
+            const size_t o = on + ((size_t)(oh0 + a) * g.OW + (qd + b)) * g.C;
+            pr[i] = *reinterpret_cast<const uint2*>(arg + o);
+            dv[i] = *reinterpret_cast<const uint4*>(dy + o);
+          }
+        }
+      float f[4][8], d[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack_bf16x8(dv[i], f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = ((j < 4 ? pr[i].x : pr[i].y) >> (8 * (j & 3))) & 0xffu;
+        d[0][j] = (t[0] == 4u ? f[0][j] : 0.f);
+        d[1][j] = (t[0] == 5u ? f[0][j] : 0.f) + (t[1] == 3u ? f[1][j] : 0.f);
+        d[2][j] = (t[0] == 7u ? f[0][j] : 0.f) + (t[2] == 1u ? f[2][j] : 0.f);
+        d[3][j] = (t[0] == 8u ? f[0][j] : 0.f) + (t[1] == 6u ? f[1][j] : 0.f) + (t[2] == 2u ? f[2][j] : 0.f) +
+                  (t[3] == 0u ? f[3][j] : 0.f);
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        *reinterpret_cast<uint4*>(dx + xbase + ((size_t)(p >> 1) * g.W + 2 * qd + (p & 1)) * g.C) =
+            make_uint4(pack_bf16x2(d[p][0], d[p][1]), pack_bf16x2(d[p][2], d[p][3]), pack_bf16x2(d[p][4], d[p][5]),
+                       pack_bf16x2(d[p][6], d[p][7]));
+    }
+  }
+}
+
 int pool_grid(long long total) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -113,6 +212,13 @@ void psb_maxpool3x3s2_forward(cudaStream_t s, const void* x, void* y, void* arg,
   psb_count_launch(1);
   PoolGeom g{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
   const long long total = (long long)N * g.OH * g.OW * g.groups;
+  if (g.groups <= 256 && 256 % g.groups == 0) {       // row-based kernel (channel groups tile the CTA)
+    const int lanes = 256 / g.groups, rows = N * g.OH, cap = pool_grid(total);
+    psb_maxpool_fwd_rows<<<rows < cap ? rows : cap, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                   reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<uint8_t*>(arg),
+                                                                   g, lanes);
+    return;
+  }
   psb_maxpool_fwd<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
                                                    reinterpret_cast<uint8_t*>(arg), g);
 }
@@ -121,6 +227,13 @@ void psb_maxpool3x3s2_backward(cudaStream_t s, const void* dy, const void* arg, 
   psb_count_launch(1);
   PoolGeom g{N, H, W, C, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1, C / 8};
   const long long total = (long long)N * H * W * g.groups;
+  if (H % 2 == 0 && W % 2 == 0 && g.groups <= 256 && 256 % g.groups == 0) {   // quad-based kernel
+    const int lanes = 256 / g.groups, rows = N * (H / 2), cap = pool_grid(total / 4);
+    psb_maxpool_bwd_quads<<<rows < cap ? rows : cap, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                                    reinterpret_cast<const uint8_t*>(arg),
+                                                                    reinterpret_cast<__nv_bfloat16*>(dx), g, lanes);
+    return;
+  }
   psb_maxpool_bwd<<<pool_grid(total), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const uint8_t*>(arg),
                                                    reinterpret_cast<__nv_bfloat16*>(dx), g);
 }

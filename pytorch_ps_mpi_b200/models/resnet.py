@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..ops.batchnorm import FusedBatchNormAct2d, _kernel_ok, fused_bn_relu_maxpool
+from ..ops.batchnorm import FusedBatchNormAct2d
 from ..ops.pooling import FusedMaxPool2d
 from ..ops.stem import STEM_K, STEM_STRIDES, stem_conv, stem_conv_fused, stem_fused_supported, stem_supported
 
@@ -21,10 +21,6 @@ from ..ops.stem import STEM_K, STEM_STRIDES, stem_conv, stem_conv_fused, stem_fu
 # statistics in its epilogue (csrc/kernels/stem_kernels.cu) instead of im2col + GEMM + statistics pass: 0.97 → 0.47 ms.
 # PSB200_STEM=im2col restores the round-1 path.
 _FUSED_STEM = os.environ.get("PSB200_STEM", "fused").lower() != "im2col"
-# Opt-in: BN1 + ReLU + max-pool in one pass each way (bn_kernels.cu).  Measured on B200 (bench/bnpool_check.py): forward
-# 0.47 → 0.37 ms but forward+backward 1.27 → 1.52 ms, so it stays off.
-_FUSED_BNPOOL = os.environ.get("PSB200_BNPOOL", "").lower() == "fused"
-
 
 def _conv3x3(i, o, stride=1):
     return nn.Conv2d(i, o, 3, stride, 1, bias=False)
@@ -138,11 +134,7 @@ class ResNet(nn.Module):
 
     def _tail(self, y, sums=None):
         """BN1 + ReLU + max-pool after the stem convolution."""
-        mp = self.maxpool
-        if (_FUSED_BNPOOL and self.training and self.bn1.relu and self.bn1.running_mean is not None
-                and (mp.kernel_size, mp.stride, mp.padding) == (3, 2, 1) and _kernel_ok(y, None, self.bn1.weight)):
-            return fused_bn_relu_maxpool(y, self.bn1, sums)
-        return mp(self.bn1(y, sums=sums) if sums is not None else self.bn1(y))
+        return self.maxpool(self.bn1(y, sums=sums) if sums is not None else self.bn1(y))
 
     def attach(self, optimizer) -> "ResNet":
         """Gate the stem kernel on the parameter server's broadcast: its weight load acquires ``PARAMS_READY`` itself and

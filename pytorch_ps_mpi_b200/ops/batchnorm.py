@@ -47,36 +47,6 @@ class _FusedBN(torch.autograd.Function):
         return dx, (dres if ctx.has_res else None), dgamma, dbeta, None, None, None, None, None, None, None
 
 
-class _FusedBNReLUPool(torch.autograd.Function):
-    """EXPERIMENTAL (``PSB200_BNPOOL=fused``): training BatchNorm + ReLU + 3x3/s2/p1 max-pool, one pass each way."""
-
-    @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, sums=None):
-        y, arg, mean, rstd, scale, shift = ext.cuda().bnpool_forward(x, gamma, beta, running_mean, running_var, eps, momentum, sums)
-        ctx.save_for_backward(x, arg, gamma, mean, rstd, scale, shift)
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        x, arg, gamma, mean, rstd, scale, shift = ctx.saved_tensors
-        if not dy.is_contiguous(memory_format=torch.channels_last):
-            dy = dy.contiguous(memory_format=torch.channels_last)
-        dx, dgamma, dbeta = ext.cuda().bnpool_backward(dy, arg, x, gamma, mean, rstd, scale, shift)
-        return dx, dgamma, dbeta, None, None, None, None, None
-
-
-def fused_bn_relu_maxpool(x: torch.Tensor, bn: "FusedBatchNormAct2d", sums: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``max_pool2d(relu(bn(x)), 3, 2, 1)`` in training mode without materialising the BN output (experimental)."""
-    assert bn.training and bn.relu and _kernel_ok(x, None, bn.weight)
-    if x.shape[2] % 2 or x.shape[3] % 2:       # the fused backward works on 2x2 input quads: odd sizes take the unfused pair
-        from .pooling import FusedMaxPool2d
-        return FusedMaxPool2d(3, 2, 1)(bn(x, sums=sums) if sums is not None else bn(x))
-    if bn.num_batches_tracked is not None:
-        bn._nbt_pending += 1
-    return _FusedBNReLUPool.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
-                                  bn.momentum if bn.momentum is not None else 0.1, sums)
-
-
 def _kernel_ok(x: torch.Tensor, res: Optional[torch.Tensor], weight) -> bool:
     return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and weight is not None
             and weight.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and x.shape[1] <= 2048

@@ -1,5 +1,5 @@
 """GPU tests of the fused ResNet stem (implicit-GEMM forward with BN statistics in the epilogue, implicit weight
-gradient), the fused BN + ReLU + max-pool pair and every epilogue of the cta_group::2 GEMM.
+gradient), and every epilogue of the cta_group::2 GEMM.
 
 First run on a B200 in round 2 (``scratch/round2_first_call.sh`` → 29 passed) and part of the default ``pytest -m gpu``
 run since.  Each compares the kernel with a plain PyTorch fp32 reference of the same op.
@@ -70,35 +70,7 @@ def test_fused_stem_autograd_matches_default_path():
     assert _rel(grads[1], grads[0]) < 1e-2 and _rel(grads[2], grads[0]) < 1e-2
 
 
-@pytest.mark.parametrize("shape", [(4, 64, 112, 112), (2, 64, 17, 23), (3, 128, 8, 8), (1, 8, 5, 4)])
-def test_fused_bn_relu_maxpool(shape):
-    from pytorch_ps_mpi_b200.ops.batchnorm import FusedBatchNormAct2d, fused_bn_relu_maxpool
-    from pytorch_ps_mpi_b200.ops.pooling import FusedMaxPool2d
-    n, c, h, w = shape
-    dev = torch.device("cuda", 0)
-    torch.manual_seed(0)
-    pool = FusedMaxPool2d(3, 2, 1)
-    bn_a = FusedBatchNormAct2d(c, relu=True).to(dev).bfloat16().train()
-    with torch.no_grad():
-        bn_a.weight.copy_(torch.randn(c).abs() + 0.5)
-        bn_a.bias.copy_(torch.randn(c) * 0.3)
-    bn_b = copy.deepcopy(bn_a)
-    x = _cl((torch.randn(n, c, h, w, device=dev) * 2 + 0.3).bfloat16())
-    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    ya, yb = pool(bn_a(xa)), fused_bn_relu_maxpool(xb, bn_b)
-    # same bf16 rounding point, but each path sums its own batch statistics with float atomics (order-dependent in the last
-    # bit): identical up to a rare 1-ulp flip of a bf16 output
-    assert float((ya.float() - yb.float()).abs().max()) <= 2.0 ** -7 * float(ya.float().abs().max())
-    assert float((ya != yb).float().mean()) < 1e-3
-    g = torch.randn_like(ya)
-    ya.backward(g)
-    yb.backward(g)
-    assert _rel(xb.grad, xa.grad) < 2e-2
-    assert _rel(bn_b.weight.grad, bn_a.weight.grad) < 2e-2 and _rel(bn_b.bias.grad, bn_a.bias.grad) < 2e-2
-    assert _rel(bn_b.running_var, bn_a.running_var) < 1e-5
-
-
-@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4])   # 0 auto (TMA store / staged), 1 staged, 2 eight warps, 3 TMA store, 4 round-1
+@pytest.mark.parametrize("epi", [0, 1, 3, 4])   # 0 auto (TMA store / staged), 1 staged, 3 TMA store, 4 round-1 row-strided stores
 @pytest.mark.parametrize("mnk", [(512, 256, 128), (1000, 328, 264), (4096, 3072, 768), (300, 64, 176), (515, 330, 72)])
 def test_gemm_epilogue_variants(epi, mnk):
     from pytorch_ps_mpi_b200.ops.linear import bcast_linear

@@ -37,6 +37,31 @@ def test_spawn_propagates_rank_failures():
     assert "rank 1 exploded" in str(e.value)
 
 
+def _boom_while_peer_waits(rank, size):
+    import time
+    if rank == 1:
+        raise ValueError("rank 1 exploded early")
+    time.sleep(600)                      # a peer that would sit in a barrier / device spin for its whole time-out
+
+
+def test_spawn_fails_fast_when_one_rank_dies():
+    """One deadline for the group and no waiting for healthy-but-stuck peers (a failing rank used to cost nprocs x timeout —
+    20 minutes of a 4-GPU box in round 2)."""
+    import time
+    t0 = time.time()
+    with pytest.raises(RuntimeError) as e:
+        spawn(_boom_while_peer_waits, 2, timeout=300)
+    assert "rank 1 exploded early" in str(e.value)
+    assert time.time() - t0 < 60
+
+
+def test_nvml_clock_sampler_degrades_without_gpu():
+    from pytorch_ps_mpi_b200.utils import NvmlClockSampler
+    with NvmlClockSampler(0) as c:
+        pass
+    assert set(c.summary()) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+
+
 def test_free_port_and_clock_sampler_without_gpu():
     assert 1024 < free_port() < 65536
     with ClockSampler(0) as c:       # no nvidia-smi / no GPU here: must degrade to an empty summary, not raise
