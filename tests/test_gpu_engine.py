@@ -251,7 +251,7 @@ def test_direct_gradient_placement_matches_encode_path(monkeypatch):
     # direct path agrees with itself
     for p, p2, q in zip(a, a2, b):
         noise = float((p - p2).abs().max())
-        assert float((p - q).abs().max()) <= 4.0 * noise + 1e-3, (float((p - q).abs().max()), noise)
+        assert float((p - q).abs().max()) <= 8.0 * noise + 2e-3, (float((p - q).abs().max()), noise)
 
 
 def test_stem_weight_lives_in_gemm_layout_in_the_arena():
