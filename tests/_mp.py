@@ -628,3 +628,32 @@ def shm_stress(rank, size):
         for k in range(5):
             tr.isend(0, bytes([rank, k]) * (1000 * k + 1), tag=9).Wait()
     tr.barrier()
+
+
+# --- the bench's same-invocation comparators (baseline/comparator.py) on CPU / gloo ---------------------------------------
+def comparator_host(rank, size):
+    """RefEquivalentSGD (the stock-tools re-creation of the reference's per-step algorithm that bench.py times next to the
+    product) must produce the summed-gradient SGD update on every rank — and must not hang: same collective sequence everywhere."""
+    ps, w = _world(rank, size)
+    from baseline.comparator import ComparatorSGD
+    from pytorch_ps_mpi_b200.models import mnist_mlp
+    torch.manual_seed(0)
+    model = mnist_mlp(hidden=32)
+    ref = [p.detach().clone() for p in model.parameters()]
+    bufs = [None] * len(ref)
+    hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-4)
+    opt = ComparatorSGD(model.named_parameters(), kind="host", **hyper)
+    for s in range(3):
+        x, y = _mlp_data(rank, s)
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(model(x), y).backward()
+        mine = [p.grad.detach().clone() for p in model.parameters()]
+        opt.step()
+        allg = w.all_gather_object(mine)
+        for i, q in enumerate(ref):
+            d = sum(allg[r][i] for r in range(size)) + hyper["weight_decay"] * q
+            bufs[i] = d.clone() if bufs[i] is None else bufs[i].mul_(hyper["momentum"]).add_(d)
+            q.add_(bufs[i], alpha=-hyper["lr"])
+    for p, q in zip(model.parameters(), ref):
+        assert torch.allclose(p.detach(), q, rtol=1e-5, atol=1e-6), float((p.detach() - q).abs().max())
+    opt.close()

@@ -51,3 +51,9 @@ def test_average_and_param_groups(transport):
 
 def test_async_consistent_reads():
     spawn(_mp.mlp_async_consistent, 3)
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_reference_equivalent_comparator(n):
+    """The comparator bench.py runs in the same invocation as the product arm: right numerics, no hang, on gloo."""
+    spawn(_mp.comparator_host, n, env={"PSB200_TRANSPORT": "gloo"}, timeout=180)
