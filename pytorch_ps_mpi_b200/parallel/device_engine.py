@@ -294,19 +294,7 @@ class DeviceEngine:
         backward keeps running on the later chunks (``/root/reference/ps.py:140-148,159-162``: one collective per
         parameter, consumed as each completes)."""
         L = self.layout
-        total = L.numel_padded * self.psz
-        target = max(self.chunk_bytes, TILE * self.psz, -(-total // 48))      # at most ~48 chunks
-        if not self.pipeline and self.mode != "async":
-            target = max(target, total)                                       # one chunk = the round-1 behaviour
-        chunks, cur, nbytes = [], [], 0
-        for sl in L.slots:
-            cur.append(sl)
-            nbytes += sl.ntiles * TILE * self.psz
-            if nbytes >= target:
-                chunks.append(cur)
-                cur, nbytes = [], 0
-        if cur:
-            chunks.append(cur)
+        chunks = L.plan_chunks(self.psz, self.chunk_bytes, single=(not self.pipeline and self.mode != "async"))
         self.chunks = chunks
         self.nchunks = len(chunks)
         self.chunk_tiles = [(c[0].first_tile, c[-1].first_tile + c[-1].ntiles) for c in chunks]

@@ -71,6 +71,27 @@ class FlatLayout:
         self.nparams = len(self.slots)
         self.ngroups = len(param_groups)
 
+    def plan_chunks(self, elem_bytes: int, chunk_bytes: int, single: bool = False, max_chunks: int = 48) -> List[List[ParamSlot]]:
+        """Static chunks of the update pipeline: contiguous runs of WHOLE parameters in arena (= backward) order, each holding at
+        least ``chunk_bytes`` of (tile-padded) parameter bytes — the last one takes the remainder — and at most ``max_chunks`` of
+        them.  They depend on the layout only, so every rank computes the same plan.  ``single``: one chunk (no pipeline)."""
+        total = self.numel_padded * elem_bytes
+        target = max(int(chunk_bytes), TILE * elem_bytes, -(-total // max_chunks))
+        if single:
+            target = max(target, total)
+        chunks: List[List[ParamSlot]] = []
+        cur: List[ParamSlot] = []
+        nbytes = 0
+        for sl in self.slots:
+            cur.append(sl)
+            nbytes += sl.ntiles * TILE * elem_bytes
+            if nbytes >= target:
+                chunks.append(cur)
+                cur, nbytes = [], 0
+        if cur:
+            chunks.append(cur)
+        return chunks
+
     def tile_table(self) -> torch.Tensor:
         """``[ntiles, 4]`` int32: (param, valid, group, first_tile) — ``TileInfo`` in common.cuh."""
         tab = torch.empty(self.ntiles, 4, dtype=torch.int32)

@@ -45,3 +45,44 @@ def test_device_spec_wire_sizes():
     tk32 = DeviceCodeSpec(KIND_TOPK, WIRE_F32, 0.5)
     assert tk32.bytes_per_tile(torch.float32) == 1024 * 8
     assert tile_k(0.1, 10) == 1 and tile_k(1.0, 7) == 7 and tile_k(0.001, 5) == 1
+
+
+def test_pipeline_chunk_plan():
+    """Chunks of the update pipeline: whole parameters, arena order, contiguous tile ranges, >= chunk_bytes each except the last,
+    capped in number, identical for identical layouts; ``single=True`` is the unpipelined plan."""
+    import torch
+    from pytorch_ps_mpi_b200 import models
+    from pytorch_ps_mpi_b200.codings import TILE
+    from pytorch_ps_mpi_b200.parallel.layout import FlatLayout
+    model = models.resnet18(num_classes=1000)
+    groups = [{"params": list(model.parameters())}]
+    L = FlatLayout(groups, {id(p): n for n, p in model.named_parameters()})
+    chunks = L.plan_chunks(2, 4 << 20)
+    assert [s.index for c in chunks for s in c] == list(range(L.nparams))           # a partition, in arena order
+    for c in chunks:
+        assert all(a.first_tile + a.ntiles == b.first_tile for a, b in zip(c, c[1:]))   # contiguous tiles
+    sizes = [sum(s.ntiles for s in c) * TILE * 2 for c in chunks]
+    assert all(sz >= (4 << 20) for sz in sizes[:-1]) and 2 <= len(chunks) <= 48
+    assert chunks[0][0].name.startswith("fc")                                          # backward order: the head comes first
+    assert len(L.plan_chunks(2, 4 << 20, single=True)) == 1
+    assert len(L.plan_chunks(2, 1)) <= 48                                               # tiny request: capped
+    again = FlatLayout(groups, {id(p): n for n, p in model.named_parameters()}).plan_chunks(2, 4 << 20)
+    assert [[s.name for s in c] for c in again] == [[s.name for s in c] for c in chunks]
+
+
+def test_custom_arena_placement_hint():
+    """``param.ps_arena_layout = (strides, span)``: the slot takes the span, an impossible hint is rejected."""
+    import pytest
+    import torch
+    from pytorch_ps_mpi_b200 import models
+    from pytorch_ps_mpi_b200.ops.stem import STEM_K, STEM_STRIDES
+    from pytorch_ps_mpi_b200.parallel.layout import FlatLayout
+    model = models.resnet18(num_classes=10)
+    groups = [{"params": list(model.parameters())}]
+    L = FlatLayout(groups, {id(p): n for n, p in model.named_parameters()})
+    slot = L.by_id[id(model.conv1.weight)]
+    assert slot.numel == 64 * STEM_K and slot.strides == STEM_STRIDES and slot.ntiles == -(-64 * STEM_K // 2048)
+    p = torch.nn.Parameter(torch.zeros(4, 4))
+    p.ps_arena_layout = ((8, 1), 16)                      # reaches element 3*8 + 3 = 27 >= 16
+    with pytest.raises(ValueError):
+        FlatLayout([{"params": [p]}], {id(p): "p"})
