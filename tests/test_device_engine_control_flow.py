@@ -230,3 +230,54 @@ def test_gradient_twice_before_step_is_rejected(fakes, monkeypatch):
     eng.on_grad(torch.randn_like(sl.param), sl.name, sl.param)
     with pytest.raises(RuntimeError):
         eng.on_grad(torch.randn_like(sl.param), sl.name, sl.param)
+
+
+def test_async_server_runs_ahead_and_harvests_in_order(fakes, monkeypatch):
+    """Device-resident AsySG-InCon server: select → update pairs are queued without looking at their result; results come back
+    through the pinned ring in order; a 'nothing selected' iteration rolls the predicted version / step count back; ps_done once
+    every worker posted DONE."""
+    script = [(0b0010, 1, 0), (0b0100, 1, 0), (0b0110, 2, 0b0010), (0, 0, 0b0110), (0, 0, 0b0110)]   # (mask, count, finished)
+    state = {"i": 0}
+
+    def select_ready(signal_local, consumed, cand_mask, quota, out, timeout_s, version=0, begin_targets=(), stream=0):
+        mask, cnt, fin = script[min(state["i"], len(script) - 1)]
+        state["i"] += 1
+        o = eng._select_out
+        o.zero_()
+        o[0], o[1], o[40], o[41] = mask, cnt, fin, version
+        for r in range(8):
+            if mask >> r & 1:
+                o[44 + r] = r                        # pretend staleness = rank
+        fakes.log.append(("select", dict(cand=cand_mask, quota=quota, version=version, begin=len(begin_targets))))
+
+    fakes.select_ready = select_ready
+    opt, eng, _ = _engine(monkeypatch, rank=0, size=3, mode="async")
+    opt.quota = 2
+    assert not eng.pipeline and eng.is_server
+    n = opt.serve()
+    assert n == 3                                    # three iterations applied something
+    assert eng.version == 3 and eng._async_applied == 3
+    assert eng._async_done_workers == {1, 2}
+    last = opt.timings[-1]
+    assert last["ps_done"] and last["updates_applied"] == 3 and last["contributors"] == [1, 2] and last["staleness"] == {1: 1, 2: 2}
+    sel = [e[1] for e in fakes.log if e[0] == "select"]
+    ups = [e[1] for e in fakes.log if e[0] == "update"]
+    assert len(sel) == len(ups) >= 4                 # every select is followed by its update launch, no host decision between
+    assert [s["version"] for s in sel[:3]] == [1, 2, 3]
+    assert sel[0]["cand"] == 0b110 and all(s["begin"] == 0 for s in sel)     # inconsistent reads: no sequence lock to open
+
+
+def test_async_worker_posts_gradient_with_its_parameter_version(fakes, monkeypatch):
+    calls = []
+    fakes.signal = lambda targets, slot, value, *a: calls.append((list(targets), slot, value, a))
+    opt, eng, _ = _engine(monkeypatch, rank=1, size=3, mode="async")
+    for step in (1, 2):
+        del fakes.log[:], calls[:]
+        _fire_all(eng)
+        assert [e[0] for e in fakes.log if e[0] == "update"] == []           # workers never launch updates
+        eng.step()
+        (targets, slot, value, extra), = calls
+        assert slot == FakeM.SIG_GRAD_READY + 1 and value == step and len(targets) == 1
+        assert extra[-1] == FakeM.SIG_GRAD_VERSION + 1                        # staleness accounting: posts the version it read
+        waits = [e[1] for e in fakes.log if e[0] == "wait"]
+        assert (len(waits) == 1 and waits[0]["slot0"] == FakeM.SIG_ACK and waits[0]["want"] == step - 1) if step > 1 else not waits
