@@ -1,0 +1,276 @@
+"""Run the REAL CUDA source of the parameter-server kernels (``csrc/kernels/ps_kernels.cu`` + the conversion helpers of
+``common.cuh``) on the CPU.
+
+One OS thread per CUDA thread (256 per CTA, CTAs one after another), ``__syncthreads`` = a pthread barrier, warp shuffles / ballots
+through a per-warp exchange buffer, atomics = GCC atomics, shared memory = function statics, system-scope loads / stores / fences
+= plain accesses (one process, one address space: "peer" arenas are just other buffers).  Only the PTX wrappers (``ld.relaxed.sys``,
+``st.release.sys``, ``multimem.*``, ``%globaltimer``) are replaced by hand-written equivalents; everything else — encode (cast /
+scale / radix-select top-k), the fused gather-decode-sum-SGD/Adam-publish kernel, the flag kernels — is compiled from the
+repository's ``.cu`` text with g++.  ``multimem`` (a property of the NVSwitch fabric) is not emulated.
+
+This is a numerics / indexing oracle that runs in every CPU round; it says nothing about timing or memory-model races (those are the
+GPU tests' and ``protocol_model.py``'s job)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import shutil
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KDIR = os.path.join(ROOT, "pytorch_ps_mpi_b200", "csrc", "kernels")
+CUDA_INC = "/usr/local/cuda/include"
+
+
+def cut_function(src: str, header_regex: str) -> str:
+    """The text of the first function whose header matches ``header_regex`` (from the match to its closing brace)."""
+    m = re.search(header_regex, src)
+    if m is None:
+        raise KeyError(header_regex)
+    depth, i = 0, src.index("{", m.start())
+    while True:
+        depth += src[i] == "{"
+        depth -= src[i] == "}"
+        i += 1
+        if depth == 0:
+            return src[m.start():i]
+
+
+SHIM_HEAD = r'''
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <pthread.h>
+#include <sched.h>
+#include <time.h>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#undef __device__
+#undef __global__
+#undef __forceinline__
+#undef __shared__
+#undef __launch_bounds__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __restrict__
+using std::min;
+using std::max;
+using std::isfinite;
+
+struct EmuIdx { unsigned x; };
+static thread_local EmuIdx threadIdx, blockIdx;
+static EmuIdx gridDim, blockDim;
+static pthread_barrier_t emu_cta_bar, emu_warp_bar[32];
+static uint64_t emu_xchg[32][32];
+static int emu_pred[1024];
+
+static inline void __syncthreads() { pthread_barrier_wait(&emu_cta_bar); }
+static inline int __syncthreads_and(int p) {
+  emu_pred[threadIdx.x] = p;
+  pthread_barrier_wait(&emu_cta_bar);
+  int r = 1;
+  for (unsigned i = 0; i < blockDim.x; ++i) r &= emu_pred[i] != 0;
+  pthread_barrier_wait(&emu_cta_bar);
+  return r;
+}
+static inline void __syncwarp() { pthread_barrier_wait(&emu_warp_bar[threadIdx.x >> 5]); }
+template <class T> static inline T emu_exchange(T v, int src_lane) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  uint64_t bits = 0; memcpy(&bits, &v, sizeof(T));
+  emu_xchg[w][l] = bits;
+  pthread_barrier_wait(&emu_warp_bar[w]);
+  T out = v;
+  if (src_lane >= 0 && src_lane < 32) memcpy(&out, &emu_xchg[w][src_lane], sizeof(T));
+  pthread_barrier_wait(&emu_warp_bar[w]);
+  return out;
+}
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int off) { const int l = threadIdx.x & 31; return emu_exchange(v, l >= off ? l - off : -1); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, (int)((threadIdx.x & 31) ^ m)); }
+static inline unsigned __ballot_sync(unsigned, int p) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  emu_xchg[w][l] = p != 0;
+  pthread_barrier_wait(&emu_warp_bar[w]);
+  unsigned r = 0;
+  const unsigned lanes = std::min(32u, blockDim.x - 32u * w);
+  for (unsigned i = 0; i < lanes; ++i) r |= (unsigned)(emu_xchg[w][i] != 0) << i;
+  pthread_barrier_wait(&emu_warp_bar[w]);
+  return r;
+}
+static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned) { sched_yield(); }
+static inline unsigned long long emu_now_ns() {       // stands in for %globaltimer
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec + 1ull;
+}
+template <class T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline float atomicAdd(float* p, float v) {
+  uint32_t* q = reinterpret_cast<uint32_t*>(p); uint32_t o = __atomic_load_n(q, __ATOMIC_SEQ_CST), n;
+  float f;
+  do { memcpy(&f, &o, 4); f += v; memcpy(&n, &f, 4); } while (!__atomic_compare_exchange_n(q, &o, n, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  memcpy(&f, &o, 4); return f;
+}
+template <class T> static inline T atomicMax(T* p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+template <class T> static inline T atomicMin(T* p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (o > v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+template <class T> static inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline int __float2int_rn(float a) { return (int)nearbyintf(a); }
+
+#include "common.cuh"      // constants, TileInfo, GroupHyper, wire_elem_bytes (host part of the real header)
+
+namespace psb {
+// ---- hand-written stand-ins for the PTX wrappers of common.cuh ----
+static inline uint64_t ld_acquire_sys(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline uint64_t ld_relaxed_sys_u64(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+static inline void st_release_sys(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline void st_relaxed_sys_f32(float* p, float v) { *p = v; }
+static inline uint4 ld_sys_v4(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
+static inline uint2 ld_sys_v2(const void* p) { uint2 v; memcpy(&v, p, 8); return v; }
+static inline float ld_sys_f32(const float* p) { return *p; }
+static inline uint4 ld_stream_v4(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
+static inline void st_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
+static inline void st_sys_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
+static inline void multimem_st_v4(void*, uint4) { fprintf(stderr, "multimem is not emulated\n"); abort(); }
+static inline uint4 multimem_ld_reduce_f32x4(const void*) { fprintf(stderr, "multimem is not emulated\n"); abort(); }
+static inline uint4 multimem_ld_reduce_bf16x8(const void*) { fprintf(stderr, "multimem is not emulated\n"); abort(); }
+static inline uint4 multimem_ld_reduce_f16x8(const void*) { fprintf(stderr, "multimem is not emulated\n"); abort(); }
+static inline bool spin_until_ge(const uint64_t* flag, uint64_t want, uint64_t* err_slot, unsigned long long) {
+  for (long spins = 0; spins < 200000000L; ++spins) {
+    if (ld_acquire_sys(flag) >= want) return true;
+    if (ld_relaxed_sys_u64(err_slot) != 0) return false;
+    if ((spins & 1023) == 1023) sched_yield();
+  }
+  st_release_sys(err_slot, 1ull);
+  return false;
+}
+'''
+
+CONVERSIONS = ["unpack_bf16x8", "unpack_f16x8", "unpack_fp8x8", "unpack_i8x8", "pack_bf16x2", "pack_f16x2_sat", "pack_f16x2",
+               "pack_fp8x4", "pack_i8x4", "load8_local", "pack8"]
+
+DRIVER = r'''
+// ---- CTA runner: 256 (or fewer) OS threads per CTA, CTAs one after another ----
+template <class F> static void emu_launch(int grid, int block, F body) {
+  gridDim.x = grid; blockDim.x = block;
+  pthread_barrier_init(&emu_cta_bar, nullptr, block);
+  const int warps = (block + 31) / 32;
+  for (int w = 0; w < warps; ++w) pthread_barrier_init(&emu_warp_bar[w], nullptr, std::min(32, block - 32 * w));
+  for (int b = 0; b < grid; ++b) {
+    std::vector<std::thread> th;
+    for (int t = 0; t < block; ++t) th.emplace_back([=] { blockIdx.x = b; threadIdx.x = t; body(); });
+    for (auto& x : th) x.join();
+  }
+  pthread_barrier_destroy(&emu_cta_bar);
+  for (int w = 0; w < warps; ++w) pthread_barrier_destroy(&emu_warp_bar[w]);
+}
+
+#define KW(K, W) if (kind == K && wire == W)
+extern "C" int emu_encode(int kind, int wire, int n, const void** src, const int* first_tile, const int* ntiles, const int* param,
+                          const void* tiles, void* wire_arena, float* scales, uint32_t* amax, float* residual, int bpt, int cap,
+                          double ratio, int grad_dt, uint64_t** sig_targets, int nsig, int sig_slot, uint64_t sig_value,
+                          unsigned* sig_counter) {
+  EncodeArgs a{};
+  a.batch.n = n; a.batch.cum[0] = 0;
+  for (int i = 0; i < n; ++i) { a.batch.src[i] = src[i]; a.batch.first_tile[i] = first_tile[i]; a.batch.param[i] = param[i]; a.batch.cum[i + 1] = a.batch.cum[i] + ntiles[i]; }
+  a.tiles = reinterpret_cast<const TileInfo*>(tiles); a.wire = wire_arena; a.scales = scales; a.amax_bits = amax; a.residual = residual;
+  a.bytes_per_tile = bpt; a.cap = cap; a.ratio = ratio; a.grad_dt = grad_dt;
+  a.nsig = nsig; for (int i = 0; i < nsig; ++i) a.sig_targets[i] = sig_targets[i];
+  a.sig_slot = sig_slot; a.sig_value = sig_value; a.sig_counter = sig_counter;
+  const int ctas = a.batch.cum[n];
+  if (kind == KIND_SCALED) emu_launch(ctas, PSB_THREADS, [&] { psb_absmax_kernel(a); });
+#define ENC(K, W) KW(K, W) { emu_launch(ctas, PSB_THREADS, [&] { psb_encode_kernel<K, W>(a); }); return 0; }
+  ENC(KIND_DENSE, WIRE_F32) ENC(KIND_DENSE, WIRE_BF16) ENC(KIND_DENSE, WIRE_F16) ENC(KIND_DENSE, WIRE_E4M3) ENC(KIND_DENSE, WIRE_E5M2)
+  ENC(KIND_SCALED, WIRE_I8) ENC(KIND_SCALED, WIRE_E4M3) ENC(KIND_SCALED, WIRE_F16) ENC(KIND_TOPK, WIRE_F32) ENC(KIND_TOPK, WIRE_BF16)
+  return 1;
+}
+
+extern "C" int emu_update(int kind, int wire, int opt, int world, int rank, void** wire_p, float** scales_p, void** param_dst,
+                          void* param_local, float* master, float* buf0, float* buf1, float* buf2, const void* tiles,
+                          const uint8_t* active, const float* param_hyper, uint64_t* signal_local, uint64_t** signal_peer,
+                          unsigned* done_counter, uint32_t* stats, const float* hyper /* ngroups x 11 */, int ngroups, int ntiles,
+                          int bpt, int cap, int param_dt, int bcast, uint32_t contrib, uint32_t wait_mask, float inv_count,
+                          uint64_t epoch, uint64_t wait_value, int tile_begin, int tile_end, int wait_grads, int signal_mode,
+                          uint32_t ack_mask, int grid) {
+  UpdateArgs a{};
+  for (int r = 0; r < world; ++r) { a.wire[r] = wire_p[r]; a.scales[r] = scales_p[r]; a.param_dst[r] = param_dst[r]; a.signal_peer[r] = signal_peer[r]; }
+  a.param_local = param_local; a.master = master; a.buf0 = buf0; a.buf1 = buf1; a.buf2 = buf2;
+  a.tiles = reinterpret_cast<const TileInfo*>(tiles); a.active = active; a.param_hyper = reinterpret_cast<const float2*>(param_hyper);
+  a.signal_local = signal_local; a.done_counter = done_counter; a.stats = stats;
+  for (int g = 0; g < ngroups; ++g) {
+    const float* h = hyper + 11 * g; GroupHyper& o = a.groups[g];
+    o.lr = h[0]; o.weight_decay = h[1]; o.momentum = h[2]; o.dampening = h[3]; o.beta1 = h[4]; o.beta2 = h[5]; o.eps = h[6];
+    o.step_size = h[7]; o.nesterov = (int)h[8]; o.amsgrad = (int)h[9]; o.first_step = (int)h[10]; o.pad = 0;
+  }
+  a.world = world; a.rank = rank; a.ntiles = ntiles; a.bytes_per_tile = bpt; a.cap = cap; a.param_dt = param_dt; a.bcast = bcast;
+  a.reduce = REDUCE_P2P; a.contrib_mask = contrib; a.wait_mask = wait_mask; a.inv_count = inv_count; a.epoch = epoch;
+  a.wait_value = wait_value; a.tile_begin = tile_begin; a.tile_end = tile_end; a.wait_grads = wait_grads; a.signal_mode = signal_mode;
+  a.ack_mask = ack_mask; a.ack_last = 1; a.timeout_ns = 2000000000ull;
+#define UPD(K, W) KW(K, W) { if (opt == OPT_SGD) emu_launch(grid, PSB_THREADS, [&] { psb_update_kernel<K, W, OPT_SGD>(a); }); \
+                             else emu_launch(grid, PSB_THREADS, [&] { psb_update_kernel<K, W, OPT_ADAM>(a); }); return 0; }
+  UPD(KIND_DENSE, WIRE_F32) UPD(KIND_DENSE, WIRE_BF16) UPD(KIND_DENSE, WIRE_F16) UPD(KIND_DENSE, WIRE_E4M3) UPD(KIND_DENSE, WIRE_E5M2)
+  UPD(KIND_SCALED, WIRE_I8) UPD(KIND_SCALED, WIRE_E4M3) UPD(KIND_SCALED, WIRE_F16) UPD(KIND_TOPK, WIRE_F32) UPD(KIND_TOPK, WIRE_BF16)
+  return 1;
+}
+
+extern "C" void emu_select(const uint64_t* signal_local, uint64_t* consumed, uint32_t cand_mask, int quota, uint64_t* out,
+                           uint64_t version) {
+  SelectArgs a{};
+  a.signal_local = signal_local; a.consumed = consumed; a.out = out; a.cand_mask = cand_mask; a.quota = quota; a.version = version;
+  a.timeout_ns = 50000000ull; a.nbegin = 0;
+  emu_launch(1, 32, [&] { psb_select_kernel(a); });
+}
+'''
+
+
+_LIB = None
+
+
+def build():
+    """Compile the emulator once per process; returns the ctypes library (or ``None`` without g++)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if shutil.which("g++") is None:
+        return None
+    common = open(os.path.join(KDIR, "common.cuh")).read()
+    ps = open(os.path.join(KDIR, "ps_kernels.cu")).read()
+    conv = "\n".join(cut_function(common, r"(template <int FP8KIND>[^\n]*\n)?__device__ __forceinline__ [^\n]*\b" + name + r"\(")
+                     for name in CONVERSIONS)
+    # the kernels: everything of ps_kernels.cu's anonymous namespace up to the launch helpers (which use <<< >>>)
+    body = ps[ps.index('#include "kernels.h"') + len('#include "kernels.h"'): ps.index("template <int KIND, int WIRE, int OPT>\nvoid launch_update_t")]
+    body = body.replace('asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));', "now = emu_now_ns();")
+    kernels_h = open(os.path.join(KDIR, "kernels.h")).read()
+    structs = kernels_h[kernels_h.index("#define PSB_ENCODE_MAX"): kernels_h.index("void psb_launch_absmax")]
+    d = tempfile.mkdtemp(prefix="psb_emu_")
+    src = SHIM_HEAD + conv + "\n}  // namespace psb\n" + structs + body + "\n}  // namespace (anonymous)\n" + DRIVER
+    # the anonymous namespace's kernels must be visible to the driver: open it as a named one instead
+    src = src.replace("namespace {\nusing namespace psb;", "namespace emu_ps {\nusing namespace psb;", 1)
+    src = src.replace("}  // namespace (anonymous)", "}  // namespace emu_ps\nusing namespace emu_ps;")
+    open(os.path.join(d, "emu.cpp"), "w").write(src)
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", CUDA_INC, "-I", KDIR, "-o", os.path.join(d, "emu.so"),
+           os.path.join(d, "emu.cpp")]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        raise RuntimeError("emulator build failed:\n" + p.stdout[-4000:])
+    _LIB = ctypes.CDLL(os.path.join(d, "emu.so"))
+    return _LIB
