@@ -14,6 +14,15 @@ import torch.nn.functional as F
 
 from tests import _cuda_emu
 
+
+@pytest.fixture(autouse=True)
+def _single_threaded_torch():
+    """The emulator runs one OS thread per CUDA thread; torch's OpenMP workers spin-waiting after each op would fight them."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
 EXTRA_SHIM = r'''
 static float emu_dyn_smem[65536];
 static inline int emu_cudaGetDevice(int* d) { *d = 0; return 0; }
@@ -71,7 +80,7 @@ def _p(t):
 
 
 @pytest.mark.parametrize("shape,relu,has_res", [((2, 16, 6, 5), True, True), ((3, 64, 9, 9), True, False), ((2, 8, 4, 4), False, True),
-                                                ((1, 512, 5, 5), True, False), ((40, 16, 12, 12), False, False)])
+                                                ((1, 512, 5, 5), True, False), ((12, 16, 12, 12), False, False)])
 def test_bn_forward_backward_emulated(lib, shape, relu, has_res):
     torch.manual_seed(0)
     N, C, H, W = shape

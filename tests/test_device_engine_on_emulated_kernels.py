@@ -13,6 +13,15 @@ from pytorch_ps_mpi_b200.parallel import device_engine as de
 from tests import _cuda_emu
 from tests.test_device_engine_control_flow import FakeArena, FakeEvent, FakeStream
 
+
+@pytest.fixture(autouse=True)
+def _single_threaded_torch():
+    """The emulator runs one OS thread per CUDA thread; torch's OpenMP workers spin-waiting after each op would fight them."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
 DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 

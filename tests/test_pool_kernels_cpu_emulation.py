@@ -14,6 +14,15 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+
+@pytest.fixture(autouse=True)
+def _single_threaded_torch():
+    """The emulator runs one OS thread per CUDA thread; torch's OpenMP workers spin-waiting after each op would fight them."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "pytorch_ps_mpi_b200", "csrc", "kernels", "pool_kernels.cu")
 

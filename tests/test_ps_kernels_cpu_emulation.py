@@ -15,6 +15,15 @@ from pytorch_ps_mpi_b200.codings import KIND_SCALED, TILE
 from pytorch_ps_mpi_b200.parallel.layout import FlatLayout
 from tests import _cuda_emu
 
+
+@pytest.fixture(autouse=True)
+def _single_threaded_torch():
+    """The emulator runs one OS thread per CUDA thread; torch's OpenMP workers spin-waiting after each op would fight them."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
 DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 SIG_PARAMS_READY, SIG_GRAD_READY, SIG_ERROR = 64, 0, 200
 c_void_pp = ctypes.POINTER(ctypes.c_void_p)
@@ -201,7 +210,7 @@ def test_sgd_momentum_steps(lib, hyper):
     ref = [torch.nn.Parameter(p.data.clone()) for p in V.params]
     opt = torch.optim.SGD(ref, lr=0.1, momentum=hyper.get("mom", 0), dampening=hyper.get("damp", 0),
                           weight_decay=hyper.get("wd", 0), nesterov=hyper.get("nesterov", False))
-    for step in range(3):
+    for step in range(2 if not FULL else 4):
         grads = [[torch.randn(s) for s in SHAPES] for _ in range(2)]
         for r in range(2):
             V.encode(r, grads[r])
@@ -221,7 +230,7 @@ def test_adam_steps(lib, amsgrad, dtype):
     ref = [torch.nn.Parameter(p.data.float().clone()) for p in V.params]
     o = ps.Adam([(f"p{i}", p) for i, p in enumerate(ref)], ref, lr=1e-2, betas=(0.9, 0.95), eps=1e-6,
                 weight_decay=1e-2, amsgrad=amsgrad, engine="host")
-    for step in range(3):
+    for step in range(2 if not FULL else 4):
         grads = [[torch.randn(s).to(dtype) for s in SHAPES] for _ in range(2)]
         for r in range(2):
             V.encode(r, grads[r])
