@@ -1,8 +1,9 @@
 """Run the REAL CUDA source of the parameter-server kernels (``csrc/kernels/ps_kernels.cu`` + the conversion helpers of
 ``common.cuh``) on the CPU.
 
-One OS thread per CUDA thread (256 per CTA, CTAs one after another), ``__syncthreads`` = a pthread barrier, warp shuffles / ballots
-through a per-warp exchange buffer, atomics = GCC atomics, shared memory = function statics, system-scope loads / stores / fences
+Every CUDA thread of a CTA is a user-level fiber (``ucontext``) on ONE OS thread, scheduled round-robin and switched at barriers
+(CTAs one after another): ``__syncthreads`` / warp barriers are generation counters, warp shuffles / ballots go through a per-warp
+exchange buffer, atomics are plain read-modify-writes (nothing runs concurrently), shared memory = function statics, system-scope loads / stores / fences
 = plain accesses (one process, one address space: "peer" arenas are just other buffers).  Only the PTX wrappers (``ld.relaxed.sys``,
 ``st.release.sys``, ``multimem.*``, ``%globaltimer``) are replaced by hand-written equivalents; everything else — encode (cast /
 scale / radix-select top-k), the fused gather-decode-sum-SGD/Adam-publish kernel, the flag kernels — is compiled from the
@@ -43,8 +44,7 @@ SHIM_HEAD = r'''
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
-#include <pthread.h>
-#include <sched.h>
+#include <ucontext.h>
 #include <time.h>
 #include <atomic>
 #include <cmath>
@@ -72,30 +72,60 @@ using std::max;
 using std::isfinite;
 
 struct EmuIdx { unsigned x; };
-static thread_local EmuIdx threadIdx, blockIdx;
-static EmuIdx gridDim, blockDim;
-static pthread_barrier_t emu_cta_bar, emu_warp_bar[32];
+static EmuIdx threadIdx, blockIdx, gridDim, blockDim;     // one OS thread: the scheduler sets threadIdx at every switch
+
+// ---- fibers: one per CUDA thread of the running CTA ----
+struct EmuFiber { ucontext_t ctx; bool done; };
+static EmuFiber emu_fib[1024];
+static char* emu_stacks = nullptr;
+static const size_t EMU_STACK = 96 * 1024;
+static ucontext_t emu_sched_ctx;
+static int emu_cur = 0, emu_live = 0, emu_warp_live[32];
+static int emu_bar_count = 0, emu_bar_gen = 0, emu_wbar_count[32], emu_wbar_gen[32];
+static void (*emu_body_call)(void*) = nullptr;
+static void* emu_body_obj = nullptr;
 static uint64_t emu_xchg[32][32];
 static int emu_pred[1024];
 
-static inline void __syncthreads() { pthread_barrier_wait(&emu_cta_bar); }
+static inline void emu_yield() { swapcontext(&emu_fib[emu_cur].ctx, &emu_sched_ctx); }
+static void emu_trampoline() {
+  emu_body_call(emu_body_obj);
+  const int w = emu_cur >> 5;
+  emu_fib[emu_cur].done = true;
+  --emu_live;
+  --emu_warp_live[w];
+  // like the hardware, an exited thread no longer counts at a barrier its siblings are waiting in
+  if (emu_live > 0 && emu_bar_count >= emu_live && emu_bar_count > 0) { emu_bar_count = 0; ++emu_bar_gen; }
+  if (emu_warp_live[w] > 0 && emu_wbar_count[w] >= emu_warp_live[w] && emu_wbar_count[w] > 0) { emu_wbar_count[w] = 0; ++emu_wbar_gen[w]; }
+  swapcontext(&emu_fib[emu_cur].ctx, &emu_sched_ctx);
+}
+static inline void __syncthreads() {
+  const int g = emu_bar_gen;
+  if (++emu_bar_count >= emu_live) { emu_bar_count = 0; ++emu_bar_gen; }
+  else while (emu_bar_gen == g) emu_yield();
+}
+static inline void emu_warp_barrier() {
+  const int w = threadIdx.x >> 5, g = emu_wbar_gen[w];
+  if (++emu_wbar_count[w] >= emu_warp_live[w]) { emu_wbar_count[w] = 0; ++emu_wbar_gen[w]; }
+  else while (emu_wbar_gen[w] == g) emu_yield();
+}
 static inline int __syncthreads_and(int p) {
   emu_pred[threadIdx.x] = p;
-  pthread_barrier_wait(&emu_cta_bar);
+  __syncthreads();
   int r = 1;
   for (unsigned i = 0; i < blockDim.x; ++i) r &= emu_pred[i] != 0;
-  pthread_barrier_wait(&emu_cta_bar);
+  __syncthreads();
   return r;
 }
-static inline void __syncwarp() { pthread_barrier_wait(&emu_warp_bar[threadIdx.x >> 5]); }
+static inline void __syncwarp() { emu_warp_barrier(); }
 template <class T> static inline T emu_exchange(T v, int src_lane) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   uint64_t bits = 0; memcpy(&bits, &v, sizeof(T));
   emu_xchg[w][l] = bits;
-  pthread_barrier_wait(&emu_warp_bar[w]);
+  emu_warp_barrier();
   T out = v;
   if (src_lane >= 0 && src_lane < 32) memcpy(&out, &emu_xchg[w][src_lane], sizeof(T));
-  pthread_barrier_wait(&emu_warp_bar[w]);
+  emu_warp_barrier();
   return out;
 }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int off) { const int l = threadIdx.x & 31; return emu_exchange(v, l >= off ? l - off : -1); }
@@ -103,11 +133,11 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { retur
 static inline unsigned __ballot_sync(unsigned, int p) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   emu_xchg[w][l] = p != 0;
-  pthread_barrier_wait(&emu_warp_bar[w]);
+  emu_warp_barrier();
   unsigned r = 0;
   const unsigned lanes = std::min(32u, blockDim.x - 32u * w);
   for (unsigned i = 0; i < lanes; ++i) r |= (unsigned)(emu_xchg[w][i] != 0) << i;
-  pthread_barrier_wait(&emu_warp_bar[w]);
+  emu_warp_barrier();
   return r;
 }
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
@@ -115,7 +145,7 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-static inline void __nanosleep(unsigned) { sched_yield(); }
+static inline void __nanosleep(unsigned) { emu_yield(); }
 static inline unsigned long long emu_now_ns() {       // stands in for %globaltimer
   timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
   return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec + 1ull;
@@ -158,7 +188,7 @@ static inline bool spin_until_ge(const uint64_t* flag, uint64_t want, uint64_t* 
   for (long spins = 0; spins < 200000000L; ++spins) {
     if (ld_acquire_sys(flag) >= want) return true;
     if (ld_relaxed_sys_u64(err_slot) != 0) return false;
-    if ((spins & 1023) == 1023) sched_yield();
+    if ((spins & 63) == 63) emu_yield();      // let the sibling threads of the CTA run
   }
   st_release_sys(err_slot, 1ull);
   return false;
@@ -169,19 +199,30 @@ CONVERSIONS = ["unpack_bf16x8", "unpack_f16x8", "unpack_fp8x8", "unpack_i8x8", "
                "pack_fp8x4", "pack_i8x4", "load8_local", "pack8"]
 
 DRIVER = r'''
-// ---- CTA runner: 256 (or fewer) OS threads per CTA, CTAs one after another ----
+// ---- CTA runner: the threads of a CTA are fibers scheduled round-robin on this OS thread; CTAs run one after another ----
+template <class F> static void emu_call_body(void* p) { (*static_cast<F*>(p))(); }
 template <class F> static void emu_launch(int grid, int block, F body) {
   gridDim.x = grid; blockDim.x = block;
-  pthread_barrier_init(&emu_cta_bar, nullptr, block);
+  if (emu_stacks == nullptr) emu_stacks = static_cast<char*>(malloc(EMU_STACK * 1024));
+  emu_body_call = &emu_call_body<F>;
+  emu_body_obj = &body;
   const int warps = (block + 31) / 32;
-  for (int w = 0; w < warps; ++w) pthread_barrier_init(&emu_warp_bar[w], nullptr, std::min(32, block - 32 * w));
   for (int b = 0; b < grid; ++b) {
-    std::vector<std::thread> th;
-    for (int t = 0; t < block; ++t) th.emplace_back([=] { blockIdx.x = b; threadIdx.x = t; body(); });
-    for (auto& x : th) x.join();
+    blockIdx.x = b;
+    emu_live = block; emu_bar_count = 0;
+    for (int w = 0; w < warps; ++w) { emu_warp_live[w] = std::min(32, block - 32 * w); emu_wbar_count[w] = 0; }
+    for (int t = 0; t < block; ++t) {
+      getcontext(&emu_fib[t].ctx);
+      emu_fib[t].ctx.uc_stack.ss_sp = emu_stacks + (size_t)t * EMU_STACK;
+      emu_fib[t].ctx.uc_stack.ss_size = EMU_STACK;
+      emu_fib[t].ctx.uc_link = nullptr;
+      emu_fib[t].done = false;
+      makecontext(&emu_fib[t].ctx, emu_trampoline, 0);
+    }
+    while (emu_live > 0)
+      for (int t = 0; t < block; ++t)
+        if (!emu_fib[t].done) { emu_cur = t; threadIdx.x = t; swapcontext(&emu_sched_ctx, &emu_fib[t].ctx); }
   }
-  pthread_barrier_destroy(&emu_cta_bar);
-  for (int w = 0; w < warps; ++w) pthread_barrier_destroy(&emu_warp_bar[w]);
 }
 
 #define KW(K, W) if (kind == K && wire == W)

@@ -123,10 +123,10 @@ def adam_h(lr, b1, b2, eps, wd, t, amsgrad=False):
     return [lr, wd, 0, 0, b1, b2, eps, lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t), 0, float(amsgrad), float(t == 1)]
 
 
-# one OS thread per CUDA thread is slow (a 256-thread CTA costs ~0.1-0.3 s when it shuffles): small arenas, a representative
-# subset of the coding x dtype x ranks matrix by default, the full matrix with PSB200_EMU_FULL=1
+# the emulator runs a CTA's threads as fibers on one OS thread (~10 ms per 256-thread CTA): small arenas keep the whole
+# coding x dtype x ranks matrix at a few seconds (PSB200_EMU_FULL=0 trims it to one case per coding)
 SHAPES = [(60, 41), (2100,), (64,), (3, 3, 16, 16), (TILE + 9,)]
-FULL = os.environ.get("PSB200_EMU_FULL") == "1"
+FULL = os.environ.get("PSB200_EMU_FULL", "1") == "1"
 CODES = {
     "identity": lambda: ps.Identity(), "cast_bf16": lambda: ps.Cast("bf16"), "cast_fp16": lambda: ps.Cast("fp16"),
     "cast_e4m3": lambda: ps.Cast("fp8_e4m3"), "cast_e5m2": lambda: ps.Cast("fp8_e5m2"),
