@@ -16,7 +16,7 @@ from tests.test_device_engine_control_flow import FakeArena, FakeEvent, FakeStre
 
 @pytest.fixture(autouse=True)
 def _single_threaded_torch():
-    """The emulator runs one OS thread per CUDA thread; torch's OpenMP workers spin-waiting after each op would fight them."""
+    """The emulated kernels run on the calling thread; keeping torch single-threaded makes the timings of these tests repeatable."""
     n = torch.get_num_threads()
     torch.set_num_threads(1)
     yield
