@@ -150,6 +150,8 @@ def main():
     w = ps.runtime.init()
     assert w.size == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={w.size}"
     device = w.device
+    # one process per GPU: run on the GPU's own socket, so the pinned input batches below are allocated NUMA-locally
+    numa = ps.runtime.bind_to_gpu_numa_node(device)
     torch.backends.cudnn.benchmark = True
     model, make_batch, loss_fn, cfg = build(args, device, ps)
     K, W = args.steps, max(args.warmup, 3)
@@ -419,7 +421,8 @@ def main():
                        "bcast": {0: "local", 1: "unicast-p2p", 2: "multimem.st"}.get(getattr(eng, "bcast", -1)),
                        "reduce": {0: "p2p rank-ordered", 1: "multimem.ld_reduce"}.get(getattr(eng, "reduce", -1)),
                        "update_pipeline_chunks": info["chunks"],
-                       "worker_wait_kernel": bool(eng is not None and not eng._gates)},
+                       "worker_wait_kernel": bool(eng is not None and not eng._gates),
+                       "numa_bind": numa},
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                        "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0),
                        "source": clocks.get("source")},

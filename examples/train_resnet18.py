@@ -14,6 +14,7 @@ from pytorch_ps_mpi_b200 import models   # noqa: E402
 from pytorch_ps_mpi_b200.ops.preprocess import normalize_nhwc   # noqa: E402
 
 w = ps.runtime.init()
+ps.runtime.bind_to_gpu_numa_node(w.device)      # run on the GPU's own socket (what `mpirun --bind-to numa` does)
 dev = w.device
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)

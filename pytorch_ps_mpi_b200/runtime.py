@@ -21,7 +21,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-__all__ = ["World", "init", "world", "rank", "size", "is_initialized", "shutdown", "COMM_WORLD"]
+__all__ = ["World", "init", "world", "rank", "size", "is_initialized", "shutdown", "COMM_WORLD", "bind_to_gpu_numa_node"]
 
 
 @dataclass
@@ -155,6 +155,61 @@ def tune_host_allocator() -> bool:
         ok = False
     _ALLOC_TUNED = ok
     return ok
+
+
+def bind_to_gpu_numa_node(device=None, min_cpus: int = 4, nvml=None) -> dict:
+    """Pin every thread of this process to the CPUs NVML reports as local to ``device``'s PCIe root (the socket / NUMA node
+    the GPU hangs off), so the launch path rings a local doorbell and pinned staging buffers allocated afterwards are
+    first-touched on the local node — what ``mpirun --bind-to numa`` does for the reference's ranks (``Makefile:2`` leaves
+    it to the MPI launcher).  One process per GPU on a two-socket box otherwise runs wherever the scheduler put it and
+    half of the ranks pull their input batches across the socket interconnect.
+
+    Never raises; returns ``{"bound": bool, "cpus": n, "why": ...}``.  Skipped when the allowed set would shrink below
+    ``min_cpus`` or ``PSB200_NUMA_BIND=0``."""
+    out = {"bound": False, "cpus": 0, "why": ""}
+    if os.environ.get("PSB200_NUMA_BIND", "1") == "0":
+        out["why"] = "disabled"
+        return out
+    try:
+        allowed = os.sched_getaffinity(0)
+        if nvml is None:
+            import pynvml as nvml
+            nvml.nvmlInit()
+        if device is None:
+            device = world().device
+        idx = device if isinstance(device, int) else (device.index or 0)
+        handle = None
+        if not isinstance(device, int) and torch.cuda.is_available():
+            pr = torch.cuda.get_device_properties(idx)
+            if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                try:                          # CUDA_VISIBLE_DEVICES renumbers CUDA devices, not NVML's
+                    handle = nvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+                except Exception:             # noqa: BLE001
+                    handle = None
+        if handle is None:
+            handle = nvml.nvmlDeviceGetHandleByIndex(idx)
+        words = nvml.nvmlDeviceGetCpuAffinity(handle, (max(allowed | {os.cpu_count() or 1}) + 64) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if int(word) >> b & 1}
+        want = allowed & local
+        out["cpus"] = len(want)
+        if len(want) < min_cpus:
+            out["why"] = f"only {len(want)} of the {len(allowed)} allowed CPUs are local to the GPU"
+            return out
+        if want == allowed:
+            out.update(bound=True, why="already local")
+            return out
+        tids = [int(t) for t in os.listdir("/proc/self/task")] if os.path.isdir("/proc/self/task") else [0]
+        for tid in tids:                      # threads that already exist (CUDA, gloo, NVML sampler) keep their own mask
+            try:
+                os.sched_setaffinity(tid, want)
+            except OSError:
+                pass
+        os.sched_setaffinity(0, want)         # and threads created from here on inherit this one
+        out.update(bound=True, why="ok")
+    except Exception as exc:      # noqa: BLE001 - an optimisation only: never take the job down
+        out["why"] = f"{type(exc).__name__}: {exc}"[:120]
+    return out
 
 
 def world() -> World:

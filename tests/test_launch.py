@@ -68,3 +68,50 @@ def test_free_port_and_clock_sampler_without_gpu():
         pass
     s = c.summary()
     assert set(s) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_numa_binding_in_a_child_process():
+    """``runtime.bind_to_gpu_numa_node``: intersect the allowed CPUs with NVML's GPU-local set, apply it to EVERY thread, refuse
+    sets that are too small, never raise (run in a child: it changes the process's CPU affinity)."""
+    code = textwrap.dedent("""
+        import os, threading, time
+        from pytorch_ps_mpi_b200 import runtime
+        allowed = sorted(os.sched_getaffinity(0))
+        half = allowed[: max(1, len(allowed) // 2)]
+
+        class Nvml:
+            def __init__(self, cpus): self.cpus = cpus
+            def nvmlDeviceGetHandleByIndex(self, i): return i
+            def nvmlDeviceGetCpuAffinity(self, h, n):
+                words = [0] * n
+                for c in self.cpus:
+                    if c // 64 < n: words[c // 64] |= 1 << (c % 64)
+                return words
+
+        stop = threading.Event()
+        seen = {}
+        def other():
+            while not stop.is_set(): time.sleep(0.01)
+            seen["mask"] = sorted(os.sched_getaffinity(0))
+        t = threading.Thread(target=other, daemon=True); t.start()
+        r0 = runtime.bind_to_gpu_numa_node(0, min_cpus=len(half) + 1, nvml=Nvml(half))      # too few: refused
+        assert not r0["bound"] and sorted(os.sched_getaffinity(0)) == allowed, r0
+        r1 = runtime.bind_to_gpu_numa_node(0, min_cpus=1, nvml=Nvml(half + [max(allowed) + 1]))   # CPUs we may not use are ignored
+        assert r1["bound"] and r1["cpus"] == len(half) and sorted(os.sched_getaffinity(0)) == half, r1
+        stop.set(); t.join()
+        assert seen["mask"] == half, seen            # the thread that already existed was moved too
+        r2 = runtime.bind_to_gpu_numa_node(0, min_cpus=1, nvml=Nvml(half))
+        assert r2["bound"] and r2["why"] == "already local", r2
+        class Broken:
+            def nvmlDeviceGetHandleByIndex(self, i): raise RuntimeError("no driver")
+        r3 = runtime.bind_to_gpu_numa_node(0, nvml=Broken())
+        assert not r3["bound"] and "no driver" in r3["why"], r3
+        os.environ["PSB200_NUMA_BIND"] = "0"
+        assert runtime.bind_to_gpu_numa_node(0, nvml=Nvml(half))["why"] == "disabled"
+        print("numa-ok")
+    """)
+    if len(os.sched_getaffinity(0)) < 2:
+        pytest.skip("one CPU")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and "numa-ok" in out.stdout, out.stderr[-2000:]
