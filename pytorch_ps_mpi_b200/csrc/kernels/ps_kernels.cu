@@ -651,6 +651,7 @@ __global__ void psb_signal_kernel(const __grid_constant__ SignalArgs a) {
     if (a.version_local != nullptr && a.targets[t] != nullptr) st_release_sys(a.targets[t] + a.version_slot, seen);
     if (a.targets[t] != nullptr) st_release_sys(a.targets[t] + a.slot, a.value);
   }
+  __syncwarp();      // every lane has read `seen` before lane 0 replaces it (several targets: one lane each)
   if (a.version_local != nullptr && t == 0)
     st_release_sys(a.version_local + SIG_SEEN_VERSION, ld_acquire_sys(a.version_local + SIG_VERSION));
 }

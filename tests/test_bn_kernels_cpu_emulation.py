@@ -4,7 +4,6 @@ the CPU emulator, against ``F.batch_norm`` + autograd in fp32.  ``kernel<<<grid,
 emulator's CTA runner, so the real grid-size logic (``grid_for`` / ``REDUCE_MIN_ITERS``) is what runs."""
 import ctypes
 import os
-import re
 import subprocess
 import tempfile
 
@@ -25,9 +24,6 @@ def _single_threaded_torch():
 
 EXTRA_SHIM = r'''
 static float emu_dyn_smem[65536];
-static inline int emu_cudaGetDevice(int* d) { *d = 0; return 0; }
-static inline int emu_cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return 0; }
-static inline int emu_cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 static inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
 void psb_count_launch(int) {}
 '''
@@ -56,14 +52,12 @@ def lib():
     body = body.replace("extern __shared__ float smem[];", "float* smem = emu_dyn_smem;")
     for fn in ("cudaGetDevice", "cudaDeviceGetAttribute", "cudaMemsetAsync"):
         body = body.replace(fn + "(", "emu_" + fn + "(")
-    body, n = re.subn(r"(\w+(?:<[^<>;]*>)?)<<<([^;]*?),\s*([^,;]*?),\s*([^,;]*?),\s*s>>>\((.*?)\)(\s*;|\s*\n)",
-                      lambda m: f"emu_launch({m.group(2)}, {m.group(3)}, [&] {{ {m.group(1)}({m.group(5)}); }}){m.group(6)}", body,
-                      flags=re.S)
+    body, n = _cuda_emu.rewrite_launches(body)
     assert n >= 8 and "<<<" not in body, n
     common = open(os.path.join(_cuda_emu.KDIR, "common.cuh")).read()
     conv = "\n".join(_cuda_emu.cut_function(common, r"(template <int FP8KIND>[^\n]*\n)?__device__ __forceinline__ [^\n]*\b" + name + r"\(")
                      for name in _cuda_emu.CONVERSIONS)
-    runner = _cuda_emu.DRIVER[: _cuda_emu.DRIVER.index("#define KW(K, W)")]
+    runner = _cuda_emu.CUDA_RT_SHIM + _cuda_emu.RUNNER
     d = tempfile.mkdtemp(prefix="psb_emu_bn_")
     full = _cuda_emu.SHIM_HEAD + conv + "\n}  // namespace psb\n" + EXTRA_SHIM + runner + body.replace("namespace {\nusing namespace psb;", "using namespace psb;", 1).replace("}  // namespace\n", "", 1) + DRIVER
     open(os.path.join(d, "emu.cpp"), "w").write(full)

@@ -26,6 +26,7 @@ def _single_threaded_torch():
 
 DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 SIG_PARAMS_READY, SIG_GRAD_READY, SIG_ERROR = 64, 0, 200
+SIG_CONSUMED, SIG_VERSION, SIG_STAGE_BEGIN, SIG_SEEN_VERSION, SIG_ACK, SIG_GRAD_VERSION = 128, 201, 202, 203, 256, 320
 c_void_pp = ctypes.POINTER(ctypes.c_void_p)
 
 
@@ -296,19 +297,81 @@ def test_fused_flag_raise_and_wait(lib):
     assert torch.allclose(V.param_values()[0], w - 2.0)
 
 
+def _select(lib, sig, consumed, cand, quota, out, version, begin=(), timeout_s=0.05):
+    arr = (ctypes.c_void_p * max(len(begin), 1))(*[b.data_ptr() for b in begin])
+    lib.emu_select(_ptr(sig), _ptr(consumed), ctypes.c_uint32(cand), quota, _ptr(out), ctypes.c_uint64(version), arr, len(begin),
+                   ctypes.c_double(timeout_s))
+
+
 def test_async_select_kernel(lib):
-    """``psb_select_kernel``: quota gradients from ANY source with rotating priority, finished workers reported, staleness recorded."""
+    """``psb_select_kernel``: quota gradients from ANY source with rotating priority, finished workers reported, staleness
+    recorded; with ``consistent=True`` targets it opens the sequence lock (STAGE_BEGIN = version) on every rank iff it selected."""
     sig = torch.zeros(512, dtype=torch.int64)
+    peer = torch.zeros(512, dtype=torch.int64)
     consumed = torch.zeros(64, dtype=torch.int64)
     out = torch.zeros(64, dtype=torch.int64)
     sig[SIG_GRAD_READY + 1], sig[SIG_GRAD_READY + 2], sig[SIG_GRAD_READY + 3] = 1, 1, 1 << 62      # rank 3 posted DONE
     sig[320 + 1], sig[320 + 2] = 4, 2                          # SIG_GRAD_VERSION: the versions their gradients were computed on
-    lib.emu_select(_ptr(sig), _ptr(consumed), ctypes.c_uint32(0b1110), 1, _ptr(out), ctypes.c_uint64(6))
+    _select(lib, sig, consumed, 0b1110, 1, out, 6, begin=(sig, peer))
     first = int(out[0])
     assert first in (0b0010, 0b0100) and int(out[1]) == 1 and int(out[40]) == 0b1000 and int(out[41]) == 6
+    assert int(sig[SIG_STAGE_BEGIN]) == 6 and int(peer[SIG_STAGE_BEGIN]) == 6
     r = 1 if first == 0b0010 else 2
     assert int(out[44 + r]) == 5 - int(sig[320 + r]) and int(consumed[r]) == 1
-    lib.emu_select(_ptr(sig), _ptr(consumed), ctypes.c_uint32(0b1110), 1, _ptr(out), ctypes.c_uint64(7))
+    _select(lib, sig, consumed, 0b1110, 1, out, 7)
     assert int(out[0]) == (0b0110 ^ first)                    # rotating priority: the other worker is served next
-    lib.emu_select(_ptr(sig), _ptr(consumed), ctypes.c_uint32(0b1110), 2, _ptr(out), ctypes.c_uint64(8))
+    _select(lib, sig, consumed, 0b1110, 2, out, 8, begin=(sig, peer))
     assert int(out[0]) == 0 and int(out[1]) == 0              # nothing new within the (emulated, short) time-out → no selection
+    assert int(peer[SIG_STAGE_BEGIN]) == 6                    # ... and the sequence lock stays closed
+
+
+def test_signal_and_wait_kernels(lib):
+    """``psb_signal_kernel`` (flag + optional extra slot + the staleness version hand-off) and ``psb_wait_kernel`` (masked wait;
+    a time-out poisons SIG_ERROR and makes every later wait return at once — what ``DeviceEngine._poll_error`` surfaces)."""
+    import time
+    mine, a, b = (torch.zeros(512, dtype=torch.int64) for _ in range(3))
+    mine[SIG_VERSION], mine[SIG_SEEN_VERSION] = 9, 7          # latest published version / the one my last forward started on
+    tg = (ctypes.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+    lib.emu_signal(tg, 2, SIG_GRAD_READY + 3, ctypes.c_uint64(5), _ptr(a), SIG_ACK + 3, ctypes.c_uint64(11), _ptr(mine),
+                   SIG_GRAD_VERSION + 3)
+    for t in (a, b):
+        assert int(t[SIG_GRAD_READY + 3]) == 5 and int(t[SIG_ACK + 3]) == 11 and int(t[SIG_GRAD_VERSION + 3]) == 7
+    assert int(mine[SIG_SEEN_VERSION]) == 9                   # re-sampled for the NEXT gradient
+    # wait: ranks 1 and 3 of the mask must reach 5; rank 3 has, rank 1 has not
+    t0 = time.time()
+    lib.emu_wait(_ptr(a), SIG_GRAD_READY, ctypes.c_uint32(0b1000), ctypes.c_uint64(5), ctypes.c_double(5.0))
+    assert time.time() - t0 < 1.0 and int(a[SIG_ERROR]) == 0
+    lib.emu_wait(_ptr(a), SIG_GRAD_READY, ctypes.c_uint32(0b1010), ctypes.c_uint64(5), ctypes.c_double(0.05))
+    assert int(a[SIG_ERROR]) != 0                             # timed out on rank 1's flag
+    t0 = time.time()
+    lib.emu_wait(_ptr(a), SIG_GRAD_READY, ctypes.c_uint32(0b0010), ctypes.c_uint64(5), ctypes.c_double(30.0))
+    assert time.time() - t0 < 1.0                             # poisoned: no second 30 s spin
+
+
+def test_snapshot_kernels_sequence_lock(lib):
+    """``psb_snapshot_fetch`` / ``psb_snapshot_commit`` (``consistent=True``): adopt staging → live only for a COMPLETE version
+    (BEGIN == VERSION), newer than the adopted one; anything else leaves the live parameters untouched."""
+    n = 256 * 40 + 16                                          # several CTAs, a ragged tail (16-byte vectors)
+    sig = torch.zeros(512, dtype=torch.int64)
+    stage = torch.arange(n, dtype=torch.float32)
+    shadow, live = torch.zeros(n), torch.full((n,), -1.0)
+    scratch = torch.tensor([0, -1, 0, 0, 0, 0], dtype=torch.int64)
+
+    def snap(attempts=1):
+        lib.emu_snapshot(_ptr(sig), _ptr(stage), _ptr(shadow), _ptr(live), ctypes.c_size_t(n * 4), _ptr(scratch), attempts)
+
+    snap()                                                     # version 0: nothing published yet
+    assert float(live[0]) == -1.0 and int(scratch[5]) == 0
+    sig[SIG_STAGE_BEGIN], sig[SIG_VERSION] = 3, 2              # publication of version 3 in progress
+    snap()
+    assert float(live[5]) == -1.0 and int(scratch[5]) == 0 and int(scratch[4]) == 0
+    assert scratch[:4].tolist() == [0, -1, 0, 0]               # the last CTA re-armed the voting words
+    sig[SIG_VERSION] = 3                                       # complete
+    snap(attempts=2)                                           # second attempt: already adopted → vetoed, live stays on v3
+    assert torch.equal(live, stage) and int(scratch[5]) == 3
+    stage += 1.0
+    snap()                                                     # same version again: not re-copied
+    assert float(live[1]) == 1.0
+    sig[SIG_STAGE_BEGIN], sig[SIG_VERSION] = 4, 4
+    snap()
+    assert torch.equal(live, stage) and int(scratch[5]) == 4
