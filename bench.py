@@ -368,6 +368,24 @@ def main():
 
     if eng is not None:
         eng.check()
+    # driver-visible correctness bit at every N: after the last broadcast every rank must hold bit-identical parameters
+    # (workers adopt the server's update through multimem.st / peer stores; nothing else ever synchronises them)
+    check = None
+    if eng is not None and args.mode != "async":
+        try:                                          # local part: no collectives inside the try
+            eng.ensure_params()                       # gated runs queue no wait kernel: acquire the last PARAMS_READY here
+            torch.cuda.synchronize(device)
+            flat = eng.param_arena.view(torch.int16 if eng.param_arena.element_size() == 2 else torch.int32).to(torch.int64)
+            digest = [int(flat.sum().item()), int((flat * 31 % 1000003).sum().item()),
+                      bool(torch.isfinite(eng.param_arena.float()).all().item())]
+            del flat
+        except Exception as exc:    # noqa: BLE001 - a diagnostic must never take the headline down
+            digest = f"{type(exc).__name__}: {exc}"[:200]
+        every = w.all_gather_object(digest)
+        bad = [d for d in every if isinstance(d, str)]
+        check = {"error": bad[0]} if bad else {
+            "params_bit_identical_across_ranks": all(d[:2] == every[0][:2] for d in every),
+            "params_finite": all(d[2] for d in every), "ranks": len(every)}
     if args.profile and getattr(opt, "timings", None):
         keys = ("dev_gather_update_bcast_time", "dev_update_pipeline_time", "dev_step_tail_time", "code_wait", "isend_time",
                 "optim_step_time", "comm_wait")
@@ -426,7 +444,7 @@ def main():
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                        "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0),
                        "source": clocks.get("source")},
-            "e2e": e2e, "gpu_launches": launches,
+            "e2e": e2e, "gpu_launches": launches, "check": check,
             "vs_comparator": vs_comp or None, "comparators": comparators or None,
         }
         print(json.dumps(out))
