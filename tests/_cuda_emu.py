@@ -260,6 +260,12 @@ extern "C" int emu_encode(int kind, int wire, int n, const void** src, const int
   return 0;
 }
 
+// async-only arguments of the next emu_update call (consumed by it): version published, device-side selection, averaging
+static uint64_t emu_x_version = 0; static const uint64_t* emu_x_select = nullptr; static int emu_x_avg = 0;
+static double emu_x_timeout = 2.0;
+extern "C" void emu_update_extra(uint64_t version, const uint64_t* select_out, int average_dynamic, double timeout_s) {
+  emu_x_version = version; emu_x_select = select_out; emu_x_avg = average_dynamic; emu_x_timeout = timeout_s;
+}
 extern "C" int emu_update(int kind, int wire, int opt, int world, int rank, void** wire_p, float** scales_p, void** param_dst,
                           void* param_local, float* master, float* buf0, float* buf1, float* buf2, const void* tiles,
                           const uint8_t* active, const float* param_hyper, uint64_t* signal_local, uint64_t** signal_peer,
@@ -280,7 +286,9 @@ extern "C" int emu_update(int kind, int wire, int opt, int world, int rank, void
   a.world = world; a.rank = rank; a.ntiles = ntiles; a.bytes_per_tile = bpt; a.cap = cap; a.param_dt = param_dt; a.bcast = bcast;
   a.reduce = REDUCE_P2P; a.contrib_mask = contrib; a.wait_mask = wait_mask; a.inv_count = inv_count; a.epoch = epoch;
   a.wait_value = wait_value; a.tile_begin = tile_begin; a.tile_end = tile_end; a.wait_grads = wait_grads; a.signal_mode = signal_mode;
-  a.ack_mask = ack_mask; a.ack_last = 1; a.timeout_ns = 2000000000ull;
+  a.ack_mask = ack_mask; a.ack_last = 1; a.timeout_ns = (unsigned long long)(emu_x_timeout * 1e9);
+  a.version = emu_x_version; a.select_out = emu_x_select; a.average_dynamic = emu_x_avg;
+  emu_x_version = 0; emu_x_select = nullptr; emu_x_avg = 0; emu_x_timeout = 2.0;
   psb_launch_update(nullptr, kind, wire, opt, a, grid);
   return 0;
 }

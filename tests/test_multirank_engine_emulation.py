@@ -1,0 +1,456 @@
+"""N ranks of the REAL device engine driving the REAL kernel source — on the CPU, in one process.
+
+Every rank is a Python thread with its own model, ``ps.SGD`` / ``ps.Adam`` and :class:`DeviceEngine`; the "symmetric arenas" are
+plain host buffers every thread can address (one address space = NVLink peer mappings), the extension module is replaced by a
+shim that executes the repository's ``ps_kernels.cu`` through the CPU emulator (``tests/_cuda_emu.py``, real launchers
+included), and a rank's launches run synchronously in program order — i.e. one in-order stream per rank.  A launch that would
+spin on a flag (``psb_wait_kernel``, ``psb_select_kernel``) first polls the flag words from Python so that the other ranks' threads
+keep running, then executes the real kernel.
+
+What this pins, in every CPU round: the flag protocol as the engine really drives it (progress values per chunk and step, slots,
+masks, PARAMS_READY / CONSUMED / ACK / DONE), the chunk pipeline across ranks, inactive parameters, the async server loop with
+device-side selection, staleness and the consistent-read sequence lock — against a single-process fp32 oracle for the synchronous
+modes and against the protocol's invariants for AsySG-InCon.  The same scenarios run on hardware in ``test_gpu_engine.py``."""
+import contextlib
+import ctypes
+import threading
+import time
+from functools import partial
+
+import pytest
+import torch
+
+import pytorch_ps_mpi_b200 as ps
+from pytorch_ps_mpi_b200 import runtime
+from pytorch_ps_mpi_b200.parallel import device_engine as de
+from tests import _cuda_emu
+from tests.test_device_engine_control_flow import FakeEvent, FakeStream
+
+DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+DONE = 1 << 62
+_tls = threading.local()
+
+
+@pytest.fixture(autouse=True)
+def _single_threaded_torch():
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
+
+def _p(x):
+    return ctypes.c_void_p(int(x))
+
+
+def _words(ptr, n=512):
+    return (ctypes.c_uint64 * n).from_address(int(ptr))
+
+
+class Cluster:
+    def __init__(self, lib, n):
+        self.lib, self.n = lib, n
+        self.lock = threading.Lock()                  # one emulated kernel at a time (the emulator is single-threaded)
+        self.bar = threading.Barrier(n)
+        self.box = [None] * n
+        self.failed = None
+
+    def fail(self, exc):
+        if self.failed is None:
+            self.failed = exc
+        self.bar.abort()
+
+    def poll(self, cond, what, timeout=60.0):
+        """Block THIS rank (not the others) until ``cond()``; a stuck protocol fails the test instead of hanging it."""
+        t0 = time.time()
+        while not cond():
+            if self.failed is not None:
+                raise RuntimeError("another rank failed")
+            if time.time() - t0 > timeout:
+                raise TimeoutError(f"stuck waiting for {what}")
+            time.sleep(0.0005)
+
+
+class World:
+    backend = "emulated"
+
+    def __init__(self, cluster, rank):
+        self.c, self.rank, self.size, self.local_rank = cluster, rank, cluster.n, rank
+        self.device = torch.device("cpu")
+        self.job_id = "emu"
+
+    def barrier(self):
+        if self.size > 1:
+            self.c.bar.wait(timeout=120)
+
+    def all_gather_object(self, obj):
+        if self.size == 1:
+            return [obj]
+        self.c.box[self.rank] = obj
+        self.barrier()
+        out = list(self.c.box)
+        self.barrier()
+        return out
+
+    def broadcast_object(self, obj, src=0):
+        return self.all_gather_object(obj)[src]
+
+
+class SharedArena:
+    """``SymmetricArena`` over host memory: every rank's block is addressable by every thread."""
+
+    def __init__(self, nbytes, device, world):
+        self.buf = torch.zeros(nbytes + 64, dtype=torch.uint8)
+        self.nbytes, self.rank, self.size = nbytes, world.rank, world.size
+        self.bufs = world.all_gather_object(self.buf)
+        self.ptrs = [b.data_ptr() for b in self.bufs]
+        self.mc_ptr, self.provider = 0, "host-emulated"
+
+    local_ptr = property(lambda self: self.ptrs[self.rank])
+    has_multicast = property(lambda self: False)
+
+    def tensor(self, offset, nbytes, dtype, rank=None):
+        b = self.bufs[self.rank if rank is None else rank]
+        return b[offset: offset + nbytes].view(dtype)
+
+    def close(self):
+        pass
+
+
+class Plan:
+    def __init__(self, m):
+        self.m = m
+        self.kind = self.wire = self.opt = self.grid = 0
+        self.window_bytes = 128 << 20
+        self.rank_ptrs = {}
+
+    def set_rank_ptrs(self, r, wire_p, scales_p, param_p, signal_p):
+        self.rank_ptrs[r] = (wire_p, scales_p, param_p, signal_p)
+
+    def configure(self, world, rank, ntiles, bpt, cap, param_dt, bcast, reduce, param_mc, wire_mc, param_local, master, buf0, buf1,
+                  buf2, tiles, signal_local, done_counter, stats):
+        assert reduce == 0 and param_mc == 0
+        self.c = dict(world=world, rank=rank, ntiles=ntiles, bpt=bpt, cap=cap, param_dt=param_dt, bcast=bcast,
+                      param_local=param_local, master=master, buf0=buf0, buf1=buf1, buf2=buf2, tiles=tiles,
+                      signal_local=signal_local, done_counter=done_counter, stats=stats)
+
+    def launch(self, epoch, groups, contrib_mask, inv_count, wait_grads, signal_mode, ack_mask=0, version=0, select_out=0,
+               average_dynamic=0, active_ptr=0, timeout_s=30.0, wait_mask=0xffffffff, stream=0, tile_begin=0, tile_end=-1,
+               wait_value=0, param_hyper=0):
+        c, lib = self.c, self.m.lib
+        assert wait_grads == 0          # the engine always waits with the one-warp kernel
+        if tile_end < 0:
+            tile_begin, tile_end, wait_value = 0, c["ntiles"], epoch
+        n = c["world"]
+        arr = lambda xs: (ctypes.c_void_p * len(xs))(*xs)      # noqa: E731
+        flat = [float(x) for g in groups for x in g]
+        w, s, p, sig = (arr([self.rank_ptrs[r][i] for r in range(n)]) for i in range(4))
+        with self.m.cluster.lock:
+            lib.emu_update_extra(ctypes.c_uint64(version), _p(select_out), average_dynamic, ctypes.c_double(2.0))
+            rc = lib.emu_update(self.kind, self.wire, self.opt, n, c["rank"], w, s, p, _p(c["param_local"]), _p(c["master"]),
+                                _p(c["buf0"]), _p(c["buf1"]), _p(c["buf2"]), _p(c["tiles"]), _p(active_ptr), _p(param_hyper),
+                                _p(c["signal_local"]), sig, _p(c["done_counter"]), _p(c["stats"]),
+                                (ctypes.c_float * len(flat))(*flat), len(groups), c["ntiles"], c["bpt"], c["cap"], c["param_dt"],
+                                c["bcast"], ctypes.c_uint32(contrib_mask), ctypes.c_uint32(wait_mask), ctypes.c_float(inv_count),
+                                ctypes.c_uint64(epoch), ctypes.c_uint64(wait_value), tile_begin, tile_end, 0, signal_mode,
+                                ctypes.c_uint32(ack_mask), min(3, tile_end - tile_begin))
+        assert rc == 0
+        self.m.log.append(("update", tile_begin, tile_end, signal_mode))
+
+
+class M:
+    """The extension module as the engine sees it, executing on the emulator."""
+    TILE, SIGNAL_SLOTS, MAX_RANKS, MAX_GROUPS = 2048, 512, 16, 16
+    SIG_GRAD_READY, SIG_PARAMS_READY, SIG_CONSUMED, SIG_ERROR, SIG_VERSION = 0, 64, 128, 200, 201
+    SIG_ACK, SIG_GRAD_VERSION, SIG_STAGE_BEGIN, SIG_SEEN_VERSION = 256, 320, 202, 203
+
+    def __init__(self, cluster):
+        self.cluster, self.lib, self.log = cluster, cluster.lib, []
+
+    def UpdatePlan(self):
+        return Plan(self)
+
+    def update_max_grid(self, *a):
+        return 444
+
+    def launch_count(self):
+        return 0
+
+    def encode(self, kind, wire, grads, first_tile, ntiles, param_idx, tiles_ptr, wire_ptr, scales_ptr, amax_ptr, residual_ptr,
+               bpt, cap, ratio, sig_targets, sig_slot, sig_value, sig_counter, stream):
+        n = len(grads)
+        assert 0 < n <= 64
+        ia = lambda xs: (ctypes.c_int * n)(*xs)      # noqa: E731
+        tg = (ctypes.c_void_p * max(len(sig_targets), 1))(*sig_targets)
+        with self.cluster.lock:
+            rc = self.lib.emu_encode(kind, wire, n, (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads]), ia(first_tile),
+                                     ia(ntiles), ia(param_idx), _p(tiles_ptr), _p(wire_ptr), _p(scales_ptr), _p(amax_ptr),
+                                     _p(residual_ptr), bpt, cap, ctypes.c_double(ratio), DT[grads[0].dtype], tg, len(sig_targets),
+                                     sig_slot, ctypes.c_uint64(sig_value), _p(sig_counter))
+        assert rc == 0
+        self.log.append(("encode", list(first_tile), sig_value if sig_targets else None))
+
+    def signal(self, targets, slot, value, extra_slot=-1, extra_value=0, stream=0, version_local=0, version_slot=0):
+        tg = (ctypes.c_void_p * len(targets))(*targets)
+        with self.cluster.lock:
+            self.lib.emu_signal(tg, len(targets), slot, ctypes.c_uint64(value), _p(1 if extra_slot >= 0 else 0),
+                                max(extra_slot, 0), ctypes.c_uint64(extra_value), _p(version_local), version_slot)
+        self.log.append(("signal", slot, value))
+
+    def wait_flags(self, signal_local, slot0, mask, want, timeout_s, stream=0):
+        sig = _words(signal_local)
+        self.cluster.poll(lambda: sig[self.SIG_ERROR] != 0 or all(sig[slot0 + r] >= want for r in range(32) if mask >> r & 1),
+                          f"slot {slot0} mask {mask:#x} >= {want}")
+        with self.cluster.lock:
+            self.lib.emu_wait(_p(signal_local), slot0, ctypes.c_uint32(mask), ctypes.c_uint64(want), ctypes.c_double(1.0))
+        assert sig[self.SIG_ERROR] == 0, "device wait timed out"
+        self.log.append(("wait", slot0, mask, want))
+
+    def select_ready(self, signal_local, consumed, cand_mask, quota, out, timeout_s, version=0, begin_targets=(), stream=0):
+        sig, cons = _words(signal_local), _words(consumed, 64)
+
+        def ready():
+            fin = [r for r in range(32) if cand_mask >> r & 1 and sig[r] >= DONE]
+            rdy = [r for r in range(32) if cand_mask >> r & 1 and r not in fin and sig[r] > cons[r]]
+            need = min(quota, bin(cand_mask).count("1") - len(fin))
+            return need == 0 or len(rdy) >= need
+        self.cluster.poll(ready, "quota gradients")
+        bt = (ctypes.c_void_p * max(len(begin_targets), 1))(*begin_targets)
+        with self.cluster.lock:
+            self.lib.emu_select(_p(signal_local), _p(consumed), ctypes.c_uint32(cand_mask), quota, _p(out), ctypes.c_uint64(version),
+                                bt, len(begin_targets), ctypes.c_double(1.0))
+
+    def snapshot(self, signal_local, stage, shadow, params, nbytes, scratch, attempts=2, stream=0):
+        with self.cluster.lock:
+            self.lib.emu_snapshot(_p(signal_local), _p(stage), _p(shadow), _p(params), ctypes.c_size_t(nbytes), _p(scratch), attempts)
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    lib = _cuda_emu.build()
+    if lib is None:
+        pytest.skip("no g++")
+    _tls.world, _tls.m = World(Cluster(lib, 1), 0), None      # the test's own thread: a single-process world (oracles)
+    monkeypatch.setattr(runtime, "world", lambda: _tls.world)
+    monkeypatch.setattr(de.ext, "cuda", lambda: _tls.m)
+    monkeypatch.setattr(de, "SymmetricArena", SharedArena)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setenv("PSB200_CHUNK_BYTES", str(2048 * 4))              # one tile per chunk: a real pipeline on a tiny model
+    return lib
+
+
+def run_ranks(lib, n, fn):
+    """Run ``fn(rank, world)`` on n threads; returns their results, re-raises the first failure."""
+    cluster = Cluster(lib, n)
+    out, errs = [None] * n, []
+
+    def main(r):
+        _tls.world, _tls.m = World(cluster, r), M(cluster)
+        try:
+            out[r] = fn(r, _tls.world)
+        except BaseException as exc:       # noqa: BLE001
+            errs.append((r, exc))
+            cluster.fail(exc)
+
+    ts = [threading.Thread(target=main, args=(r,), daemon=True) for r in range(n)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in ts), "a rank thread is stuck"
+    real = [e for e in errs if not isinstance(e[1], (threading.BrokenBarrierError, RuntimeError)) or "another rank" not in str(e[1])]
+    if errs:
+        raise (real or errs)[0][1]
+    return out
+
+
+_rng_lock = threading.Lock()
+
+
+def _model(dtype=torch.float32):
+    with _rng_lock:                       # the global RNG is shared by the rank threads: seed + init must not interleave
+        torch.manual_seed(0)
+        return _build(dtype)
+
+
+def _build(dtype):
+    return torch.nn.Sequential(torch.nn.Linear(20, 30), torch.nn.Tanh(), torch.nn.Linear(30, 24), torch.nn.Tanh(),
+                               torch.nn.Linear(24, 10)).to(dtype)
+
+
+def _data(rank, step, dtype=torch.float32):
+    g = torch.Generator().manual_seed(1000 * rank + step)
+    return torch.randn(8, 20, generator=g).to(dtype), torch.randint(0, 10, (8,), generator=g)
+
+
+def _loss(model, x, y, skip_head):
+    h = model[:-1](x)
+    out = h[:, :10] if skip_head else model[-1](h)
+    return torch.nn.functional.cross_entropy(out.float(), y)
+
+
+def _attach(opt, **kw):
+    for h in opt._hooks:
+        h.remove()
+    opt._engine = de.DeviceEngine(opt, **kw)
+    opt._hooks = [p.register_hook(partial(opt._engine.on_grad, name=n, param=p)) for n, p in opt._named.items()]
+
+
+def _oracle(n, steps, optim, hyper, average, skip_until):
+    """Single process: every rank's gradient on the SAME parameters, summed in rank order, then one ``torch.optim.SGD`` step or
+    the reference's Adam rule (``ps.Adam.optim_step`` = ``/root/reference/ps.py:217-261``; parameters without a gradient are
+    skipped and keep their own step count, ``ps.py:178-179``)."""
+    model = _model()
+    if optim == "sgd":
+        opt = torch.optim.SGD(model.parameters(), **hyper)
+    else:
+        opt = ps.Adam(model.named_parameters(), model.parameters(), engine="host", **hyper)
+        for h in opt._hooks:
+            h.remove()
+    for s in range(steps):
+        tot = None
+        for r in range(n):
+            model.zero_grad(set_to_none=True)
+            _loss(model, *_data(r, s), skip_head=s < skip_until).backward()
+            gs = [None if p.grad is None else p.grad.clone() for p in model.parameters()]
+            tot = gs if tot is None else [a if b is None else a + b for a, b in zip(tot, gs)]
+        tot = [None if g is None else (g / n if average else g) for g in tot]
+        if optim == "sgd":
+            for p, g in zip(model.parameters(), tot):
+                p.grad = g
+            opt.step()
+        else:
+            with torch.no_grad():
+                for p, g in zip(model.parameters(), tot):
+                    if g is not None:
+                        opt.optim_step(p, g, betas=(0.9, 0.999), eps=1e-8, lr=hyper["lr"], weight_decay=hyper["weight_decay"])
+    if optim != "sgd":
+        opt.close()
+    return [p.detach().clone() for p in model.parameters()]
+
+
+@pytest.mark.parametrize("n,mode,optim,average,skip_until", [
+    (2, "ps", "sgd", False, 0), (3, "ps", "sgd", True, 0), (3, "allgather", "sgd", False, 0), (2, "ps", "adam", True, 0),
+    (2, "ps", "sgd", False, 2), (2, "allgather", "adam", False, 2)])
+def test_sync_modes_match_single_process_oracle(emu, n, mode, optim, average, skip_until):
+    """PS / all-gather at 2-3 ranks, 4 steps, per-chunk pipeline (one tile per chunk), optionally with a parameter (the head) that
+    gets no gradient on ANY rank for the first steps: every rank ends on the oracle's parameters."""
+    hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-3, dampening=0.2) if optim == "sgd" else dict(lr=1e-2, weight_decay=1e-2)
+    steps = 4
+
+    def rank_main(rank, w):
+        model = _model()
+        cls = ps.SGD if optim == "sgd" else ps.Adam
+        opt = cls(model.named_parameters(), model.parameters(), engine="host", mode=mode, average=average, **hyper)
+        assert opt.rank == rank and opt.size == n
+        _attach(opt)
+        eng = opt._engine
+        assert eng.nchunks >= 3 and eng.pipeline and eng.is_server == (mode == "allgather" or rank == 0)
+        for s in range(steps):
+            if mode == "ps" and rank != 0 and s > 0:
+                assert _words(eng.arena.local_ptr)[M.SIG_PARAMS_READY] == s         # the forward below reads published weights
+            opt.zero_grad(set_to_none=True)
+            _loss(model, *_data(rank, s), skip_head=s < skip_until).backward()
+            opt.step()
+        eng.check()
+        w.barrier()
+        mine = [p.detach().clone() for p in model.parameters()]
+        sig = list(_words(eng.arena.local_ptr))
+        log = list(_tls.m.log)
+        opt.close()
+        return mine, sig, log, eng.nchunks
+
+    res = run_ranks(emu, n, rank_main)
+    want = _oracle(n, steps, optim, hyper, average, skip_until)
+    for mine, _, _, _ in res:
+        for a, b in zip(mine, want):
+            assert torch.allclose(a, b, rtol=3e-5, atol=3e-6), float((a - b).abs().max())
+    for r, (mine, sig, log, nchunks) in enumerate(res):
+        for a, b in zip(mine, res[0][0]):
+            assert torch.equal(a, b)                                   # ranks bit-identical
+        assert sig[M.SIG_ERROR] == 0
+        if mode == "ps":
+            assert sig[M.SIG_PARAMS_READY] == steps
+            if r == 0:
+                assert all(sig[M.SIG_GRAD_READY + q] == steps * nchunks for q in range(1, n))       # monotone progress values
+        else:
+            assert all(sig[M.SIG_CONSUMED + q] == steps for q in range(n) if q != r)
+            assert all(sig[M.SIG_GRAD_READY + q] == steps * nchunks for q in range(n) if q != r)
+        ups = [e for e in log if e[0] == "update"]
+        if mode == "allgather" or r == 0:
+            assert len(ups) == steps * nchunks and [u[3] for u in ups].count(0) == steps * (nchunks - 1)
+        else:
+            assert not ups                                             # workers never run the update kernel in PS mode
+
+
+def test_async_server_with_device_selection(emu):
+    """AsySG-InCon at 3 ranks (server + 2 workers), quota 1: every gradient is applied exactly once, acknowledged, its staleness
+    recorded; after the drain every rank holds the server's final parameters."""
+    nsteps, n = 3, 3
+
+    def rank_main(rank, w):
+        model = _model()
+        opt = ps.SGD(model.named_parameters(), model.parameters(), engine="host", mode="async", quota=1, lr=0.05, average=True)
+        _attach(opt)
+        eng = opt._engine
+        seen = []
+        if rank == 0:
+            applied = opt.serve()
+            assert applied == nsteps * (n - 1), applied
+            seen = dict(eng._async_last)
+        else:
+            for s in range(nsteps):
+                opt.zero_grad(set_to_none=True)
+                _loss(model, *_data(rank, s), skip_head=False).backward()
+                _, data = opt.step()
+                time.sleep(0.002 * rank)
+        opt.close()                                # workers: wait for the last ACK, then post DONE
+        sig = list(_words(eng.arena.local_ptr))
+        return [p.detach().clone() for p in model.parameters()], sig, seen
+
+    res = run_ranks(emu, n, rank_main)
+    before = [p.detach() for p in _model().parameters()]
+    assert not torch.equal(res[0][0][0], before[0])
+    assert all(torch.isfinite(p).all() for p in res[0][0])
+    srv = res[0][1]
+    for r in (1, 2):
+        assert res[r][1][M.SIG_ACK] == nsteps                      # every gradient of every worker was acknowledged
+        assert srv[M.SIG_GRAD_READY + r] == DONE                   # ... and the worker said goodbye
+    last = res[0][2]
+    assert last["updates_applied"] == nsteps * (n - 1) and last["param_version"] == nsteps * (n - 1)
+    assert all(v >= 0 for v in last["staleness"].values()) and set(last["staleness"]) == set(last["contributors"])
+
+
+def test_async_consistent_reads(emu):
+    """``consistent=True``: workers adopt whole versions through the device-side sequence lock; versions never go backwards and
+    every rank leaves with the server's final parameters."""
+    nsteps, n = 3, 2
+
+    def rank_main(rank, w):
+        model = _model()
+        opt = ps.SGD(model.named_parameters(), model.parameters(), engine="host", mode="async", quota=1, lr=0.05, consistent=True)
+        _attach(opt)
+        eng = opt._engine
+        assert eng.consistent
+        seen = []
+        if rank == 0:
+            assert opt.serve() == nsteps * (n - 1)
+        else:
+            for s in range(nsteps):
+                opt.zero_grad(set_to_none=True)
+                _loss(model, *_data(rank, s), skip_head=False).backward()
+                _, data = opt.step()
+                seen.append(data["param_version"])
+        opt.close()
+        return [p.detach().clone() for p in model.parameters()], seen, eng._snap_version
+
+    res = run_ranks(emu, n, rank_main)
+    assert res[1][1] == sorted(res[1][1])
+    assert res[1][2] == nsteps * (n - 1) and res[0][2] == nsteps * (n - 1)          # the final snapshot is the last version
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
