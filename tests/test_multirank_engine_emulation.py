@@ -199,11 +199,15 @@ class M:
 
     def wait_flags(self, signal_local, slot0, mask, want, timeout_s, stream=0):
         sig = _words(signal_local)
-        self.cluster.poll(lambda: sig[self.SIG_ERROR] != 0 or all(sig[slot0 + r] >= want for r in range(32) if mask >> r & 1),
-                          f"slot {slot0} mask {mask:#x} >= {want}")
-        with self.cluster.lock:
-            self.lib.emu_wait(_p(signal_local), slot0, ctypes.c_uint32(mask), ctypes.c_uint64(want), ctypes.c_double(1.0))
-        assert sig[self.SIG_ERROR] == 0, "device wait timed out"
+        try:
+            self.cluster.poll(lambda: sig[self.SIG_ERROR] != 0 or all(sig[slot0 + r] >= want for r in range(32) if mask >> r & 1),
+                              f"slot {slot0} mask {mask:#x} >= {want}", timeout=min(timeout_s, 60.0))
+        except TimeoutError:
+            if timeout_s >= 60.0:
+                raise                       # a stuck protocol, not a scenario with a deliberately short device time-out
+        with self.cluster.lock:             # the real kernel: returns at once, or times out and poisons SIG_ERROR
+            self.lib.emu_wait(_p(signal_local), slot0, ctypes.c_uint32(mask), ctypes.c_uint64(want), ctypes.c_double(0.01))
+        assert sig[self.SIG_ERROR] == 0 or timeout_s < 60.0, "device wait timed out"
         self.log.append(("wait", slot0, mask, want))
 
     def select_ready(self, signal_local, consumed, cand_mask, quota, out, timeout_s, version=0, begin_targets=(), stream=0):
@@ -454,3 +458,98 @@ def test_async_consistent_reads(emu):
     assert res[1][2] == nsteps * (n - 1) and res[0][2] == nsteps * (n - 1)          # the final snapshot is the last version
     for a, b in zip(res[0][0], res[1][0]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,mode,optim,coding,dtype", [
+    (2, "ps", "sgd", "topk", torch.float32), (2, "allgather", "sgd", "scale", torch.float32), (3, "ps", "adam", "cast", torch.float32),
+    (2, "ps", "sgd", "identity", torch.bfloat16), (2, "allgather", "adam", "topk", torch.bfloat16)])
+def test_codings_and_bf16_masters_multirank(emu, n, mode, optim, coding, dtype):
+    """Coded wires (block-wise top-k, abs-max int8, bf16 cast) and bf16 parameters with fp32 masters across ranks: each step all
+    ranks' ACTUAL gradients are gathered, ``decode(encode(.))`` applied per rank, summed in fp32 in rank order and fed to the
+    reference optimizer math on fp32 shadows (the oracle of ``tests/_mp.py::gpu_train``); the engine's masters must match, the
+    published parameters must be the rounded masters, and all ranks must be bit-identical."""
+    factory = {"identity": ps.Identity, "cast": lambda: ps.Cast("bf16"), "scale": lambda: ps.Scale("int8"),
+               "topk": lambda: ps.TopK(ratio=0.25)}[coding]
+    hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-4) if optim == "sgd" else dict(lr=1e-2, eps=1e-8)
+    steps = 3
+
+    def rank_main(rank, w):
+        model = _model(dtype)
+        shadow = [torch.nn.Parameter(p.detach().float().clone()) for p in model.parameters()]
+        cls = ps.SGD if optim == "sgd" else ps.Adam
+        oracle = cls([(f"p{i}", q) for i, q in enumerate(shadow)], shadow, engine="host", use_mpi=False, **hyper)
+        for h in oracle._hooks:
+            h.remove()
+        groups = oracle._group_of()
+        opt = cls(model.named_parameters(), model.parameters(), engine="host", mode=mode, code=factory(), **hyper)
+        _attach(opt)
+        eng = opt._engine
+        assert (eng.master is not None) == (dtype != torch.float32 and eng.is_server)
+        for s in range(steps):
+            opt.zero_grad(set_to_none=True)
+            x, y = _data(rank, s, dtype)
+            _loss(model, x, y, skip_head=False).backward()
+            mine = [p.grad.detach().clone() for p in model.parameters()]
+            opt.step()
+            allg = w.all_gather_object(mine)
+            with torch.no_grad():
+                for i, q in enumerate(shadow):
+                    total = torch.zeros_like(q)
+                    for r in range(n):
+                        code = factory()
+                        total += code.decode(code.encode(allg[r][i], name=f"p{i}")).reshape(q.shape).float()
+                    oracle.optim_step(q, total, **oracle._hyper(groups[id(q)]))
+        eng.check()
+        w.barrier()
+        got = [(opt.state[p]["master_param"] if eng.master is not None else p).detach().float().clone() for p in model.parameters()]
+        pub = [p.detach().clone() for p in model.parameters()]
+        opt.close()
+        oracle.close()
+        return got, pub, [q.detach().clone() for q in shadow], eng.is_server
+
+    res = run_ranks(emu, n, rank_main)
+    for got, pub, shadow, is_server in res:
+        for a, b in zip(pub, res[0][1]):
+            assert torch.equal(a, b)                                   # ranks bit-identical
+        if is_server:
+            for g, q, p in zip(got, shadow, pub):
+                assert torch.allclose(g, q, rtol=2e-4, atol=2e-5), (coding, float((g - q).abs().max()))
+                if dtype != torch.float32:
+                    assert torch.equal(g.to(dtype), p)                 # published parameter == the rounded master
+
+
+def test_stalled_peer_is_detected_and_nothing_is_applied(emu, monkeypatch):
+    """Failure detection: a worker that stops sending gradients makes the server's bounded device wait time out — the
+    error slot is poisoned, the update kernel of that step returns without touching parameters or raising PARAMS_READY,
+    ``check()`` raises, and ``recover()`` (collective) clears the slot."""
+    monkeypatch.setenv("PSB200_DEVICE_TIMEOUT", "0.3")
+
+    def rank_main(rank, w):
+        model = _model()
+        opt = ps.SGD(model.named_parameters(), model.parameters(), engine="host", mode="ps", lr=0.05)
+        _attach(opt)
+        eng = opt._engine
+        for s in range(2):
+            if rank == 1 and s == 1:
+                break                                                  # the stalled peer: no backward, no step
+            opt.zero_grad(set_to_none=True)
+            _loss(model, *_data(rank, s), skip_head=False).backward()
+            if rank == 0 and s == 1:
+                before = [p.detach().clone() for p in model.parameters()]
+            opt.step()
+        raised = False
+        if rank == 0:
+            assert all(torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))     # nothing was applied
+            assert _words(eng.arena.local_ptr)[M.SIG_PARAMS_READY] == 1
+            try:
+                eng.check()
+            except RuntimeError as exc:
+                raised = "timed out" in str(exc)
+        w.barrier()
+        eng.recover()
+        err = _words(eng.arena.local_ptr)[M.SIG_ERROR]
+        opt.close()
+        return raised, err
+
+    res = run_ranks(emu, 2, rank_main)
+    assert res[0] == (True, 0) and res[1] == (False, 0)
