@@ -553,3 +553,93 @@ def test_stalled_peer_is_detected_and_nothing_is_applied(emu, monkeypatch):
 
     res = run_ranks(emu, 2, rank_main)
     assert res[0] == (True, 0) and res[1] == (False, 0)
+
+
+class _DirectLinear(torch.autograd.Function):
+    """A producer we own: writes dW / db straight into the views handed out by ``param.ps_grad_out()`` (what the fused BN backward,
+    the stem wgrad and ``BcastLinear`` do on the GPU) and returns those views as the gradients."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.params = (w, b)
+        return torch.addmm(b, x, w.t())
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        wp, bp = ctx.params
+        gw = getattr(wp, "ps_grad_out", lambda: None)()
+        gb = getattr(bp, "ps_grad_out", lambda: None)()
+        gx = gy @ w
+        gw = torch.mm(gy.t(), x, out=gw) if gw is not None else gy.t() @ x
+        if gb is not None:
+            torch.sum(gy, 0, out=gb)
+        else:
+            gb = gy.sum(0)
+        return gx, gw, gb
+
+
+class _DirectNet(torch.nn.Module):
+    def __init__(self, base, direct_layers):
+        super().__init__()
+        self.base, self.direct_layers = base, direct_layers
+
+    def forward(self, x):
+        for i, m in enumerate(self.base):
+            x = _DirectLinear.apply(x, m.weight, m.bias) if i in self.direct_layers else m(x)
+        return x
+
+
+@pytest.mark.parametrize("option", ["unpipelined", "gate", "direct", "direct+inactive"])
+def test_engine_options_multirank(emu, monkeypatch, option):
+    """The same 3-rank PS-SGD run through the engine's other paths: one fused launch per step (``pipeline=False``), a registered
+    gate (workers queue no wait kernel; the consumer acquires ``gate()``'s flag itself), and direct gradient placement (producers
+    write into the wire arena, mixed with encoded gradients inside a chunk; with a frozen-for-a-while parameter on top)."""
+    n, steps = 3, 4
+    hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-3)
+    skip_until = 2 if option == "direct+inactive" else 0
+
+    def rank_main(rank, w):
+        base = _model()
+        model = _DirectNet(base, {0, 4} if option.startswith("direct") else set())
+        opt = ps.SGD(base.named_parameters(), base.parameters(), engine="host", mode="ps", pipeline=option != "unpipelined", **hyper)
+        _attach(opt)
+        eng = opt._engine
+        assert eng.nchunks == (1 if option == "unpipelined" else 6)          # six parameters, one tile each
+        if option == "gate":
+            eng.register_gate(object())
+        for s in range(steps):
+            if option == "gate":
+                flag_ptr, epoch = eng.gate()              # what the first forward GEMM's TMA producer acquires on the GPU
+                assert (flag_ptr == 0) == (rank == 0 or s == 0) and epoch == (0 if rank == 0 else s)
+                if flag_ptr:
+                    _tls.m.cluster.poll(lambda: _words(flag_ptr, 1)[0] >= epoch, "gated PARAMS_READY")
+            opt.zero_grad(set_to_none=True)
+            x, y = _data(rank, s)
+            h = model(x) if s >= skip_until else _DirectNet(base[:-1], {0})(x)[:, :10]
+            torch.nn.functional.cross_entropy(h, y).backward()
+            opt.step()
+        if option == "gate":
+            eng.ensure_params()                          # nothing consumed the last broadcast through a gate: plain wait
+        eng.check()
+        w.barrier()
+        mine = [p.detach().clone() for p in base.parameters()]
+        waits = [e for e in _tls.m.log if e[0] == "wait" and e[1] == M.SIG_PARAMS_READY]
+        direct = eng.direct_grads
+        opt.close()
+        return mine, len(waits), direct
+
+    res = run_ranks(emu, n, rank_main)
+    want = _oracle(n, steps, "sgd", hyper, False, skip_until)
+    for r, (mine, waits, direct) in enumerate(res):
+        for a, b in zip(mine, want):
+            assert torch.allclose(a, b, rtol=3e-5, atol=3e-6), (option, r, float((a - b).abs().max()))
+        if option == "gate":
+            assert waits == (0 if r == 0 else 1)                       # only the final ensure_params()
+        elif r > 0:
+            assert waits == steps
+        if option == "direct":
+            assert direct == 4 * steps                                 # two layers x (weight, bias) per step, no encode pass
+        if option == "direct+inactive":
+            assert direct == 2 * skip_until + 4 * (steps - skip_until)
