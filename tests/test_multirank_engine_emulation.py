@@ -643,3 +643,53 @@ def test_engine_options_multirank(emu, monkeypatch, option):
             assert direct == 4 * steps                                 # two layers x (weight, bias) per step, no encode pass
         if option == "direct+inactive":
             assert direct == 2 * skip_until + 4 * (steps - skip_until)
+
+
+@pytest.mark.parametrize("optim", ["sgd", "adam"])
+def test_checkpoint_resume_multirank(emu, optim):
+    """``state_dict()`` / ``load_state_dict()`` through the device engine at 2 ranks, bf16 parameters with fp32 masters, a
+    parameter whose first gradient arrives late (its own step count must survive the round trip): 2 steps + save + load into
+    fresh objects + 2 steps == 4 straight steps, bit for bit."""
+    import copy
+    hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-4, dampening=0.1) if optim == "sgd" else dict(lr=1e-2, weight_decay=1e-2)
+
+    def rank_main(rank, w):
+        def make():
+            m = _model(torch.bfloat16)
+            cls = ps.SGD if optim == "sgd" else ps.Adam
+            o = cls(m.named_parameters(), m.parameters(), engine="host", mode="ps", **hyper)
+            _attach(o)
+            return m, o
+
+        def run(m, o, steps, start=0):
+            for s in range(start, start + steps):
+                o.zero_grad(set_to_none=True)
+                x, y = _data(rank, s, torch.bfloat16)
+                _loss(m, x, y, skip_head=s < 1).backward()          # the head sits out step 0
+                o.step()
+
+        m1, o1 = make()
+        run(m1, o1, 4)
+        want = [p.detach().clone() for p in m1.parameters()]
+        m2, o2 = make()
+        run(m2, o2, 2)
+        sd_model = {k: v.clone() for k, v in m2.state_dict().items()}
+        sd_opt = copy.deepcopy(o2.state_dict())
+        if rank == 0:
+            st = list(sd_opt["state"].values())
+            assert all("master_param" in s for s in st) and sorted(int(s["step"]) for s in st) == [1, 1, 2, 2, 2, 2]
+        m3, o3 = make()
+        with torch.no_grad():
+            for k, v in m3.state_dict().items():
+                v.copy_(sd_model[k])
+        o3.load_state_dict(sd_opt)
+        run(m3, o3, 2, start=2)
+        got = [p.detach().clone() for p in m3.parameters()]
+        w.barrier()
+        for o in (o1, o2, o3):
+            o.close()
+        return got, want
+
+    for got, want in run_ranks(emu, 2, rank_main):
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), float((a.float() - b.float()).abs().max())
