@@ -728,13 +728,65 @@ class DeviceEngine:
                 self._err_event.record(self.comm_stream)
 
     def recover(self):
-        """Explicit recovery after a surfaced time-out: every rank clears its error slot (collective)."""
+        """Collective recovery after a surfaced time-out: bring every rank back to a common, clean protocol state so that
+        training can continue (the reference has no failure handling at all; a dead rank hangs ``mpirun`` for good).
+
+        A timed-out step leaves the ranks' epoch clocks and progress flags misaligned (the stalled rank never posted its
+        chunks; chunks gathered before the stall may already have been applied and published).  So: quiesce, clear every
+        rank's signal pad and error slot, restart the epoch / chunk clocks at zero, re-adopt rank 0's parameters (and, in
+        ``allgather`` mode where optimizer state is replicated, rank 0's state and step counts — through the slow object
+        path: this is a rare event), and re-open.  Optimizer step counts keep counting the failed step."""
         torch.cuda.synchronize(self.device)
-        self.signal[self.m.SIG_ERROR] = 0
+        self.world.barrier()                  # every rank is here: nobody launches into the old epoch any more
+        with torch.no_grad():
+            self.signal.zero_()               # peers only ever store flags into this pad, and all of them are quiescent
+            self.counters.zero_()
+            self._consumed.zero_()
+            self._select_out.zero_()
         self._err_host.zero_()
         self._err_event = None
+        self._epoch = 0
+        self._fired = set()
+        self._keep, self._keep_prev = [], []
+        self._prev_done = None
+        self._raw_bytes = 0
+        self._first_flush_done = False
+        self._step_hyp = None
+        self._next_chunk = 0
+        self._chunk_left = [len(c) for c in self.chunks]
+        for it in self._chunk_items:
+            it.clear()
+        self._gate_epoch = -1
+        self.version = 0
+        self._async_pending, self._async_done_workers = [], set()
+        self._snap_version = 0
+        if self._snap_shadow is not None:
+            self._snap_scratch.copy_(torch.tensor([0, -1, 0, 0, 0, 0], dtype=torch.int64))
+            self._snap_event = None
         torch.cuda.synchronize(self.device)
-        self.world.barrier()
+        self.world.barrier()                  # all pads are clean before anybody reads a peer's memory
+        if self.size > 1:
+            L = self.layout
+            nbytes = L.numel_padded * self.psz
+            with torch.no_grad():
+                src = self.arena.tensor(self.off_stage if self.consistent else self.off_param, nbytes, self.dtype, rank=0)
+                if self.rank != 0 or self.consistent:
+                    self.param_arena.copy_(src)
+                if self.consistent and self.rank != 0:
+                    self.stage_arena.copy_(src)
+                if self.mode == "allgather":
+                    bufs = [b for b in (self.master, self.buf0, self.buf1, self.buf2) if b is not None]
+                    state = self.world.broadcast_object(
+                        ([b.cpu() for b in bufs], self._group_steps, self._param_steps, self._uniform_steps)
+                        if self.rank == 0 else None, src=0)
+                    if self.rank != 0:
+                        for b, v in zip(bufs, state[0]):
+                            b.copy_(v)
+                        self._group_steps, self._param_steps = list(state[1]), list(state[2])
+                        self._uniform_steps = bool(state[3])
+                        self._hyper_cache = None
+            torch.cuda.synchronize(self.device)
+            self.world.barrier()
 
     def resync_master(self):
         """Re-seed the fp32 master weights from the (bf16/fp16) parameters — call after changing parameters in place

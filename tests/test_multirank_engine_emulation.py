@@ -518,41 +518,68 @@ def test_codings_and_bf16_masters_multirank(emu, n, mode, optim, coding, dtype):
                     assert torch.equal(g.to(dtype), p)                 # published parameter == the rounded master
 
 
-def test_stalled_peer_is_detected_and_nothing_is_applied(emu, monkeypatch):
-    """Failure detection: a worker that stops sending gradients makes the server's bounded device wait time out — the
-    error slot is poisoned, the update kernel of that step returns without touching parameters or raising PARAMS_READY,
-    ``check()`` raises, and ``recover()`` (collective) clears the slot."""
+@pytest.mark.parametrize("mode", ["ps", "allgather"])
+def test_stalled_peer_is_detected_then_recovered(emu, monkeypatch, mode):
+    """Failure detection and recovery: a rank that sits a step out makes its peers' bounded device waits time out —
+    the error slot is poisoned, the update kernels of that step return without touching parameters or raising their flags,
+    ``check()`` raises; ``recover()`` (collective) realigns clocks, flags, parameters (and replicated state), after which
+    training continues and ends exactly where a run WITHOUT the failed step ends."""
     monkeypatch.setenv("PSB200_DEVICE_TIMEOUT", "0.3")
+    hyper = dict(lr=0.05, momentum=0.9)
+    order = [0, 1, 2, 3]                                                # data steps; rank 1 stalls at step 1
 
     def rank_main(rank, w):
         model = _model()
-        opt = ps.SGD(model.named_parameters(), model.parameters(), engine="host", mode="ps", lr=0.05)
+        opt = ps.SGD(model.named_parameters(), model.parameters(), engine="host", mode=mode, **hyper)
         _attach(opt)
         eng = opt._engine
-        for s in range(2):
-            if rank == 1 and s == 1:
-                break                                                  # the stalled peer: no backward, no step
+        raised = None
+        for s in order:
+            if s == 1:
+                before = [p.detach().clone() for p in model.parameters()]
+                if rank == 0:
+                    opt.zero_grad(set_to_none=True)
+                    _loss(model, *_data(rank, s), skip_head=False).backward()
+                    opt.step()                                         # rank 1 never posts: every wait of this step times out
+                    assert all(torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))     # nothing applied
+                    if mode == "ps":
+                        assert _words(eng.arena.local_ptr)[M.SIG_PARAMS_READY] == 1
+                    try:
+                        eng.check()
+                        raised = False
+                    except RuntimeError as exc:
+                        raised = "timed out" in str(exc)
+                w.barrier()
+                eng.recover()
+                assert _words(eng.arena.local_ptr)[M.SIG_ERROR] == 0 and eng._epoch == 0
+                continue
             opt.zero_grad(set_to_none=True)
             _loss(model, *_data(rank, s), skip_head=False).backward()
-            if rank == 0 and s == 1:
-                before = [p.detach().clone() for p in model.parameters()]
             opt.step()
-        raised = False
-        if rank == 0:
-            assert all(torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))     # nothing was applied
-            assert _words(eng.arena.local_ptr)[M.SIG_PARAMS_READY] == 1
-            try:
-                eng.check()
-            except RuntimeError as exc:
-                raised = "timed out" in str(exc)
+        eng.check()
         w.barrier()
-        eng.recover()
-        err = _words(eng.arena.local_ptr)[M.SIG_ERROR]
+        mine = [p.detach().clone() for p in model.parameters()]
         opt.close()
-        return raised, err
+        return raised, mine
 
     res = run_ranks(emu, 2, rank_main)
-    assert res[0] == (True, 0) and res[1] == (False, 0)
+    assert res[0][0] is True and res[1][0] is None
+    # oracle: steps 0, 2, 3 of both ranks (the failed step contributed nothing)
+    model = _model()
+    o = torch.optim.SGD(model.parameters(), **hyper)
+    for s in (0, 2, 3):
+        tot = None
+        for r in range(2):
+            model.zero_grad(set_to_none=True)
+            _loss(model, *_data(r, s), skip_head=False).backward()
+            gs = [p.grad.clone() for p in model.parameters()]
+            tot = gs if tot is None else [a + b for a, b in zip(tot, gs)]
+        for p, g in zip(model.parameters(), tot):
+            p.grad = g
+        o.step()
+    for _, mine in res:
+        for a, b in zip(mine, model.parameters()):
+            assert torch.allclose(a, b.detach(), rtol=3e-5, atol=3e-6), float((a - b.detach()).abs().max())
 
 
 class _DirectLinear(torch.autograd.Function):
