@@ -7,7 +7,9 @@ exchange buffer, atomics are plain read-modify-writes (nothing runs concurrently
 = plain accesses (one process, one address space: "peer" arenas are just other buffers).  Only the PTX wrappers (``ld.relaxed.sys``,
 ``st.release.sys``, ``multimem.*``, ``%globaltimer``) are replaced by hand-written equivalents; everything else — encode (cast /
 scale / radix-select top-k), the fused gather-decode-sum-SGD/Adam-publish kernel, the flag kernels — is compiled from the
-repository's ``.cu`` text with g++.  ``multimem`` (a property of the NVSwitch fabric) is not emulated.
+repository's ``.cu`` text with g++.  ``multimem.st`` / ``multimem.ld_reduce`` (NVLS) act on registered multicast windows: a
+multicast address is an offset applied to every rank's buffer (store = replicate; load-reduce = fp32 sum over the ranks, rounded
+once to the wire type).
 
 This is a numerics / indexing oracle that runs in every CPU round; it says nothing about timing or memory-model races (those are the
 GPU tests' and ``protocol_model.py``'s job)."""
@@ -180,20 +182,56 @@ static inline float ld_sys_f32(const float* p) { return *p; }
 static inline uint4 ld_stream_v4(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
 static inline void st_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
 static inline void st_sys_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
-static inline void multimem_st_v4(void*, uint4) { fprintf(stderr, "multimem is not emulated\n"); abort(); }
-static inline uint4 multimem_ld_reduce_f32x4(const void*) { fprintf(stderr, "multimem is not emulated\n"); abort(); }
-static inline uint4 multimem_ld_reduce_bf16x8(const void*) { fprintf(stderr, "multimem is not emulated\n"); abort(); }
-static inline uint4 multimem_ld_reduce_f16x8(const void*) { fprintf(stderr, "multimem is not emulated\n"); abort(); }
-static inline bool spin_until_ge(const uint64_t* flag, uint64_t want, uint64_t* err_slot, unsigned long long) {
-  for (long spins = 0; spins < 200000000L; ++spins) {
-    if (ld_acquire_sys(flag) >= want) return true;
-    if (ld_relaxed_sys_u64(err_slot) != 0) return false;
-    if ((spins & 63) == 63) emu_yield();      // let the sibling threads of the CTA run
-  }
-  st_release_sys(err_slot, 1ull);
-  return false;
+// ---- multicast windows (NVLS): a multicast address is an offset into a window bound to every rank's buffer ----
+struct EmuMcWindow { const uint8_t* mc; size_t nbytes; int n; uint8_t* base[16]; };
+static EmuMcWindow emu_mc[8];
+static int emu_mc_n = 0;
+static inline const EmuMcWindow& emu_mc_find(const void* p, size_t* off) {
+  const uint8_t* q = static_cast<const uint8_t*>(p);
+  for (int i = 0; i < emu_mc_n; ++i)
+    if (q >= emu_mc[i].mc && q + 16 <= emu_mc[i].mc + emu_mc[i].nbytes) { *off = q - emu_mc[i].mc; return emu_mc[i]; }
+  fprintf(stderr, "multimem access outside every registered multicast window\n");
+  abort();
 }
+static inline void multimem_st_v4(void* mc, uint4 v) {            // multimem.st: the switch replicates the store
+  size_t off;
+  const EmuMcWindow& w = emu_mc_find(mc, &off);
+  for (int r = 0; r < w.n; ++r) memcpy(w.base[r] + off, &v, 16);
+}
+static inline uint4 multimem_ld_reduce_f32x4(const void* mc) {    // multimem.ld_reduce.add.f32: one load per rank, summed
+  size_t off;
+  const EmuMcWindow& w = emu_mc_find(mc, &off);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < w.n; ++r) { float t[4]; memcpy(t, w.base[r] + off, 16); for (int j = 0; j < 4; ++j) acc[j] += t[j]; }
+  uint4 v; memcpy(&v, acc, 16); return v;
+}
+static inline uint4 emu_mc_reduce_16bit(const void* mc, bool bf) {   // .acc::f32: fp32 accumulation, ONE rounding to the wire type
+  size_t off;
+  const EmuMcWindow& w = emu_mc_find(mc, &off);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < w.n; ++r) {
+    uint16_t t[8]; memcpy(t, w.base[r] + off, 16);
+    for (int j = 0; j < 8; ++j) {
+      if (bf) { uint32_t u = (uint32_t)t[j] << 16; float f; memcpy(&f, &u, 4); acc[j] += f; }
+      else { __half h; memcpy(&h, &t[j], 2); acc[j] += __half2float(h); }
+    }
+  }
+  uint16_t o[8];
+  for (int j = 0; j < 8; ++j) {
+    if (bf) { __nv_bfloat16 b = __float2bfloat16_rn(acc[j]); memcpy(&o[j], &b, 2); }
+    else { __half h = __float2half_rn(acc[j]); memcpy(&o[j], &h, 2); }
+  }
+  uint4 v; memcpy(&v, o, 16); return v;
+}
+static inline uint4 multimem_ld_reduce_bf16x8(const void* mc) { return emu_mc_reduce_16bit(mc, true); }
+static inline uint4 multimem_ld_reduce_f16x8(const void* mc) { return emu_mc_reduce_16bit(mc, false); }
 '''
+
+def real_spin(common: str) -> str:
+    """The repository's bounded spin (``common.cuh::spin_until_ge``: time-out → error slot), reading the emulated clock."""
+    return cut_function(common, r"__device__ __forceinline__ bool spin_until_ge\(").replace(
+        'asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));', "now = emu_now_ns();")
+
 
 CONVERSIONS = ["unpack_bf16x8", "unpack_f16x8", "unpack_fp8x8", "unpack_i8x8", "pack_bf16x2", "pack_f16x2_sat", "pack_f16x2",
                "pack_fp8x4", "pack_i8x4", "load8_local", "pack8"]
@@ -266,6 +304,19 @@ static double emu_x_timeout = 2.0;
 extern "C" void emu_update_extra(uint64_t version, const uint64_t* select_out, int average_dynamic, double timeout_s) {
   emu_x_version = version; emu_x_select = select_out; emu_x_avg = average_dynamic; emu_x_timeout = timeout_s;
 }
+// multicast (NVLS) arguments of the next emu_update call + the window registry
+static void* emu_x_param_mc = nullptr; static const void* emu_x_wire_mc = nullptr; static int emu_x_reduce = 0;
+extern "C" void emu_update_mc(void* param_mc, const void* wire_mc, int reduce) {
+  emu_x_param_mc = param_mc; emu_x_wire_mc = wire_mc; emu_x_reduce = reduce;
+}
+extern "C" int emu_mc_register(const void* mc, size_t nbytes, int n, void** bases) {
+  if (psb::emu_mc_n >= 8 || n > 16) return -1;
+  psb::EmuMcWindow& w = psb::emu_mc[psb::emu_mc_n];
+  w.mc = static_cast<const uint8_t*>(mc); w.nbytes = nbytes; w.n = n;
+  for (int r = 0; r < n; ++r) w.base[r] = static_cast<uint8_t*>(bases[r]);
+  return psb::emu_mc_n++;
+}
+extern "C" void emu_mc_clear() { psb::emu_mc_n = 0; }
 extern "C" int emu_update(int kind, int wire, int opt, int world, int rank, void** wire_p, float** scales_p, void** param_dst,
                           void* param_local, float* master, float* buf0, float* buf1, float* buf2, const void* tiles,
                           const uint8_t* active, const float* param_hyper, uint64_t* signal_local, uint64_t** signal_peer,
@@ -284,7 +335,9 @@ extern "C" int emu_update(int kind, int wire, int opt, int world, int rank, void
     o.step_size = h[7]; o.nesterov = (int)h[8]; o.amsgrad = (int)h[9]; o.first_step = (int)h[10]; o.pad = 0;
   }
   a.world = world; a.rank = rank; a.ntiles = ntiles; a.bytes_per_tile = bpt; a.cap = cap; a.param_dt = param_dt; a.bcast = bcast;
-  a.reduce = REDUCE_P2P; a.contrib_mask = contrib; a.wait_mask = wait_mask; a.inv_count = inv_count; a.epoch = epoch;
+  a.reduce = emu_x_reduce; a.param_mc = emu_x_param_mc; a.wire_mc = emu_x_wire_mc;
+  emu_x_reduce = REDUCE_P2P; emu_x_param_mc = nullptr; emu_x_wire_mc = nullptr;
+  a.contrib_mask = contrib; a.wait_mask = wait_mask; a.inv_count = inv_count; a.epoch = epoch;
   a.wait_value = wait_value; a.tile_begin = tile_begin; a.tile_end = tile_end; a.wait_grads = wait_grads; a.signal_mode = signal_mode;
   a.ack_mask = ack_mask; a.ack_last = 1; a.timeout_ns = (unsigned long long)(emu_x_timeout * 1e9);
   a.version = emu_x_version; a.select_out = emu_x_select; a.average_dynamic = emu_x_avg;
@@ -329,6 +382,7 @@ def build():
     ps = open(os.path.join(KDIR, "ps_kernels.cu")).read()
     conv = "\n".join(cut_function(common, r"(template <int FP8KIND>[^\n]*\n)?__device__ __forceinline__ [^\n]*\b" + name + r"\(")
                      for name in CONVERSIONS)
+    conv += "\n" + real_spin(common)
     # ps_kernels.cu from its first kernel to the end: the anonymous namespace with the kernels AND the launchers behind it
     # (dispatch tables, grids), their <<< >>> launches rewritten to the fiber runner
     body = ps[ps.index('#include "kernels.h"') + len('#include "kernels.h"'):]

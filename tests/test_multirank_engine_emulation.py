@@ -54,6 +54,7 @@ class Cluster:
         self.bar = threading.Barrier(n)
         self.box = [None] * n
         self.failed = None
+        self.multicast = False
 
     def fail(self, exc):
         if self.failed is None:
@@ -105,9 +106,20 @@ class SharedArena:
         self.bufs = world.all_gather_object(self.buf)
         self.ptrs = [b.data_ptr() for b in self.bufs]
         self.mc_ptr, self.provider = 0, "host-emulated"
+        c = world.c
+        if c.multicast and world.size > 1:
+            # NVLS: a multicast window bound to every rank's block (symm_mem.cpp::mc_create / mc_bind_and_map); the window's
+            # address range is a dummy allocation that is never dereferenced
+            self.mc_buf = world.broadcast_object(torch.zeros(nbytes + 64, dtype=torch.uint8) if world.rank == 0 else None, src=0)
+            if world.rank == 0:
+                with c.lock:
+                    assert c.lib.emu_mc_register(_p(self.mc_buf.data_ptr()), ctypes.c_size_t(nbytes), world.size,
+                                                 (ctypes.c_void_p * world.size)(*self.ptrs)) >= 0
+            world.barrier()
+            self.mc_ptr = self.mc_buf.data_ptr()
 
     local_ptr = property(lambda self: self.ptrs[self.rank])
-    has_multicast = property(lambda self: False)
+    has_multicast = property(lambda self: self.mc_ptr != 0)
 
     def tensor(self, offset, nbytes, dtype, rank=None):
         b = self.bufs[self.rank if rank is None else rank]
@@ -129,7 +141,7 @@ class Plan:
 
     def configure(self, world, rank, ntiles, bpt, cap, param_dt, bcast, reduce, param_mc, wire_mc, param_local, master, buf0, buf1,
                   buf2, tiles, signal_local, done_counter, stats):
-        assert reduce == 0 and param_mc == 0
+        self.mc = (param_mc, wire_mc, reduce)
         self.c = dict(world=world, rank=rank, ntiles=ntiles, bpt=bpt, cap=cap, param_dt=param_dt, bcast=bcast,
                       param_local=param_local, master=master, buf0=buf0, buf1=buf1, buf2=buf2, tiles=tiles,
                       signal_local=signal_local, done_counter=done_counter, stats=stats)
@@ -147,6 +159,7 @@ class Plan:
         w, s, p, sig = (arr([self.rank_ptrs[r][i] for r in range(n)]) for i in range(4))
         with self.m.cluster.lock:
             lib.emu_update_extra(ctypes.c_uint64(version), _p(select_out), average_dynamic, ctypes.c_double(2.0))
+            lib.emu_update_mc(_p(self.mc[0]), _p(self.mc[1]), self.mc[2])
             rc = lib.emu_update(self.kind, self.wire, self.opt, n, c["rank"], w, s, p, _p(c["param_local"]), _p(c["master"]),
                                 _p(c["buf0"]), _p(c["buf1"]), _p(c["buf2"]), _p(c["tiles"]), _p(active_ptr), _p(param_hyper),
                                 _p(c["signal_local"]), sig, _p(c["done_counter"]), _p(c["stats"]),
@@ -248,9 +261,11 @@ def emu(monkeypatch):
     return lib
 
 
-def run_ranks(lib, n, fn):
+def run_ranks(lib, n, fn, multicast=False):
     """Run ``fn(rank, world)`` on n threads; returns their results, re-raises the first failure."""
     cluster = Cluster(lib, n)
+    cluster.multicast = multicast
+    lib.emu_mc_clear()
     out, errs = [None] * n, []
 
     def main(r):
@@ -720,3 +735,59 @@ def test_checkpoint_resume_multirank(emu, optim):
     for got, want in run_ranks(emu, 2, rank_main):
         for a, b in zip(got, want):
             assert torch.equal(a, b), float((a.float() - b.float()).abs().max())
+
+
+@pytest.mark.parametrize("n,optim,dtype,reduce", [(4, "sgd", torch.bfloat16, "auto"), (4, "adam", torch.float32, "auto"),
+                                                  (2, "sgd", torch.bfloat16, "nvls"), (3, "sgd", torch.float32, "auto")])
+def test_switch_reduction_and_multicast_publish_multirank(emu, n, optim, dtype, reduce):
+    """With multicast memory the engine publishes through ``multimem.st`` and — at N >= 4 (or when forced) — reduces through
+    ``multimem.ld_reduce``: same grad-gather oracle as the GPU suite, with its tolerance for the switch's single rounding of the
+    16-bit sums (``tests/_mp.py::gpu_train``)."""
+    hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-4) if optim == "sgd" else dict(lr=1e-2, eps=1e-8)
+    steps = 3
+
+    def rank_main(rank, w):
+        model = _model(dtype)
+        shadow = [torch.nn.Parameter(p.detach().float().clone()) for p in model.parameters()]
+        cls = ps.SGD if optim == "sgd" else ps.Adam
+        oracle = cls([(f"p{i}", q) for i, q in enumerate(shadow)], shadow, engine="host", use_mpi=False, **hyper)
+        for h in oracle._hooks:
+            h.remove()
+        groups = oracle._group_of()
+        opt = cls(model.named_parameters(), model.parameters(), engine="host", mode="ps", **hyper)
+        _attach(opt, reduce=reduce)
+        eng = opt._engine
+        assert eng.arena.has_multicast and eng.bcast == 2
+        assert eng.reduce == (1 if (n >= 4 or reduce == "nvls") else 0)
+        sum_mag = 0.0
+        for s in range(steps):
+            opt.zero_grad(set_to_none=True)
+            x, y = _data(rank, s, dtype)
+            _loss(model, x, y, skip_head=False).backward()
+            mine = [p.grad.detach().clone() for p in model.parameters()]
+            opt.step()
+            allg = w.all_gather_object(mine)
+            with torch.no_grad():
+                for i, q in enumerate(shadow):
+                    total = sum(allg[r][i].float() for r in range(n))
+                    sum_mag = max(sum_mag, float(total.abs().max()))
+                    oracle.optim_step(q, total, **oracle._hyper(groups[id(q)]))
+        eng.check()
+        w.barrier()
+        got = [(opt.state[p]["master_param"] if eng.master is not None else p).detach().float().clone() for p in model.parameters()]
+        pub = [p.detach().clone() for p in model.parameters()]
+        nvls = eng.reduce == 1
+        opt.close()
+        oracle.close()
+        return got, pub, [q.detach().clone() for q in shadow], eng.is_server, sum_mag, nvls
+
+    res = run_ranks(emu, n, rank_main, multicast=True)
+    for got, pub, shadow, is_server, sum_mag, nvls in res:
+        for a, b in zip(pub, res[0][1]):
+            assert torch.equal(a, b)                                   # multimem.st: every rank bit-identical
+        if is_server:
+            lossy = nvls and dtype != torch.float32
+            atol = 2e-5 + (steps * hyper["lr"] * sum_mag * 2.0 ** -8 if lossy else 0.0)
+            for g, q in zip(got, shadow):
+                assert torch.allclose(g, q, rtol=2e-4, atol=atol), float((g - q).abs().max())
+    emu.emu_mc_clear()

@@ -92,10 +92,20 @@ class VirtualCPU:
                                  ctypes.c_void_p(self.counters.data_ptr() + 8))
         assert rc == 0
 
+    def bind_multicast(self):
+        """NVLS: one multicast window over the ranks' wire arenas, one over their parameter arenas (``symm_mem.cpp::mc_*``)."""
+        self.lib.emu_mc_clear()
+        self.mc_wire, self.mc_param = torch.zeros_like(self.wires[0]), torch.zeros_like(self.param_arenas[0])   # address space only
+        for mc, bufs in ((self.mc_wire, self.wires), (self.mc_param, self.param_arenas)):
+            assert self.lib.emu_mc_register(_ptr(mc), ctypes.c_size_t(mc.numel() * mc.element_size()), self.n,
+                                            _arr([b.data_ptr() for b in bufs])) >= 0
+
     def update(self, epoch, hypers, wait=False, mask=None, inv=1.0, lo=0, hi=None, signal_mode=1, active=None, param_hyper=None,
-               wait_value=None, grid=None):
+               wait_value=None, grid=None, nvls=False):
         nt = self.L.ntiles
         hi = nt if hi is None else hi
+        if nvls:          # bcast = multimem.st, reduce = multimem.ld_reduce
+            self.lib.emu_update_mc(_ptr(self.mc_param), _ptr(self.mc_wire), 1)
         flat = [float(x) for h in hypers for x in h]
         hy = (ctypes.c_float * len(flat))(*flat)
         grid = grid or min(hi - lo, 6)                      # few CTAs: every CTA walks several tiles (grid-stride loop)
@@ -105,7 +115,7 @@ class VirtualCPU:
                                  _ptr(self.buf0), _ptr(self.buf1), _ptr(self.buf2), _ptr(self.tiles), _ptr(active),
                                  _ptr(param_hyper), _ptr(self.signals[0]), _arr([s.data_ptr() for s in self.signals]),
                                  _ptr(self.counters), ctypes.c_void_p(self.counters.data_ptr() + 4), hy, len(hypers), nt, self.bpt,
-                                 self.cap, DT[self.dtype], 1, ctypes.c_uint32((1 << self.n) - 1 if mask is None else mask),
+                                 self.cap, DT[self.dtype], 2 if nvls else 1, ctypes.c_uint32((1 << self.n) - 1 if mask is None else mask),
                                  ctypes.c_uint32(((1 << self.n) - 1) & ~1), ctypes.c_float(inv), ctypes.c_uint64(epoch),
                                  ctypes.c_uint64(epoch if wait_value is None else wait_value), lo, hi, 1 if wait else 0,
                                  signal_mode, ctypes.c_uint32(0), grid)
@@ -375,3 +385,50 @@ def test_snapshot_kernels_sequence_lock(lib):
     sig[SIG_STAGE_BEGIN], sig[SIG_VERSION] = 4, 4
     snap()
     assert torch.equal(live, stage) and int(scratch[5]) == 4
+
+
+@pytest.mark.parametrize("dtype,optim,ranks", [(torch.float32, "sgd", 4), (torch.bfloat16, "sgd", 5), (torch.float16, "adam", 4),
+                                                (torch.bfloat16, "adam", 8)])
+def test_nvls_reduce_and_multicast_publish(lib, dtype, optim, ranks):
+    """The switch path (default at N >= 4): ``multimem.ld_reduce`` over the wire arenas (NVLS_U tiles in flight per thread, chunk
+    ranges, inactive parameters) and ``multimem.st`` publication — against the fp32 sum of the ranks' wire values (16-bit wires:
+    fp32 accumulation rounded ONCE to the wire type, as the switch does) and against the P2P path on the same inputs."""
+    shapes = [(TILE * 9 + 5,), (60, 41), (TILE,), (300,)]          # 13 tiles: more than NVLS_U x grid for small grids
+    torch.manual_seed(3)
+    V = VirtualCPU(lib, shapes, dtype, ps.Identity(), ranks, optim=optim)
+    torch.manual_seed(3)
+    P = VirtualCPU(lib, shapes, dtype, ps.Identity(), ranks, optim=optim)
+    V.bind_multicast()
+    grads = [[torch.randn(s).to(dtype) for s in shapes] for _ in range(ranks)]
+    for r in range(ranks):
+        V.encode(r, grads[r])
+        P.encode(r, grads[r])
+    h = [sgd_h(lr=0.1, mom=0.9)] if optim == "sgd" else [adam_h(1e-2, 0.9, 0.999, 1e-8, 0.0, 1)]
+    active = torch.ones(len(shapes), dtype=torch.uint8)
+    active[V.L.by_id[id(V.params[2])].index] = 0                   # one parameter (registration index 2) sits the step out
+    nt = V.L.ntiles
+    V.update(1, h, lo=0, hi=5, signal_mode=0, active=active, nvls=True, grid=2)      # two chunks, ragged against NVLS_U * grid
+    V.update(1, h, lo=5, hi=nt, signal_mode=1, active=active, nvls=True, grid=3)
+    P.update(1, h, active=active)
+    assert int(V.signals[0][SIG_ERROR]) == 0 and all(int(s[SIG_PARAMS_READY]) == 1 for s in V.signals)
+    for r in range(1, ranks):
+        assert torch.equal(V.param_arenas[r], V.param_arenas[0])   # multimem.st reached every rank
+    for i, (a, b) in enumerate(zip(V.param_values(), P.param_values())):
+        if i == 2:
+            assert torch.equal(a, V.params[2].data)                # inactive: untouched
+            continue
+        # fp32 wire: only the summation order differs; 16-bit wires: the switch rounds the fp32 sum once, P2P never rounds it
+        tol = 1e-5 if dtype == torch.float32 else 0.1 * 2.0 ** -7 * float(ranks) ** 0.5 * 4
+        assert torch.allclose(a.float(), b.float(), rtol=2e-2 if dtype != torch.float32 else 1e-5, atol=tol), \
+            (i, float((a.float() - b.float()).abs().max()))
+    if optim == "sgd":                                             # exact model of the switch: sum in fp32, round once, then SGD
+        tot = [sum(g[i].float() for g in grads) for i in range(len(shapes))]
+        if dtype != torch.float32:
+            tot = [t.to(dtype).float() for t in tot]
+        for i, (a, t, p) in enumerate(zip(V.param_values(), tot, V.params)):
+            if i != 2:
+                want = (p.data.float() - 0.1 * t)
+                sl = V.L.by_id[id(p)]
+                got = V.master[sl.offset: sl.offset + sl.numel].view(p.shape) if V.master is not None else a.float()
+                assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), (i, float((got - want).abs().max()))
+    lib.emu_mc_clear()
