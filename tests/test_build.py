@@ -55,9 +55,26 @@ def test_sass_of_the_fused_stem_and_gemm_epilogues():
     g = _sass(gexp)
     for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTMASTG.2D", "LDTM"):
         assert mnemonic in g, f"{mnemonic} missing from bcast_gemm_exp SASS"
-    for log in ("stem_kernels.nvcc.log", "bcast_gemm2.nvcc.log", "bn_kernels.nvcc.log"):
+    for log in ("stem_kernels.nvcc.log", "bcast_gemm2.nvcc.log", "bcast_gemm.nvcc.log", "bn_kernels.nvcc.log", "pool_kernels.nvcc.log"):
         p = ext.OBJ / log
         if p.exists():
             for line in p.read_text().splitlines():
                 if "spill" in line:
                     assert "0 bytes spill stores, 0 bytes spill loads" in line, f"{log}: {line.strip()}"
+
+
+def test_ps_kernels_spill_budget():
+    """``ps_kernels.cu`` at ``__launch_bounds__(256, 3)`` (85 registers): nothing spills except the fp32-wire Adam instantiation
+    of the update kernel (four fp32 state vectors + two 16-byte gathers per rank in flight), and that one stays under 128 bytes."""
+    p = ext.OBJ / "ps_kernels.nvcc.log"
+    if not p.exists():
+        pytest.skip("build log not present (built elsewhere)")
+    entry, seen = None, 0
+    for line in p.read_text().splitlines():
+        if "Compiling entry function" in line:
+            entry = line.split("'")[1]
+        if "spill" in line and "0 bytes spill stores, 0 bytes spill loads" not in line:
+            seen += 1
+            assert "psb_update_kernelILi0ELi0ELi1E" in entry, f"{entry}: {line.strip()}"
+            assert int(line.split("bytes stack frame,")[1].split("bytes spill stores")[0]) <= 128, line
+    assert seen <= 1
