@@ -78,3 +78,16 @@ def test_ps_kernels_spill_budget():
             assert "psb_update_kernelILi0ELi0ELi1E" in entry, f"{entry}: {line.strip()}"
             assert int(line.split("bytes stack frame,")[1].split("bytes spill stores")[0]) <= 128, line
     assert seen <= 1
+
+
+def test_built_extensions_are_not_older_than_their_sources():
+    """The in-tree ``.so`` files travel to the GPU box as they are: a kernel edited after the last build would be tested (and
+    benchmarked) in its OLD form there.  ``make build`` / ``__graft_entry__.build()`` refreshes them."""
+    if not ext.CUDA_SO.exists() or not ext.HOST_SO.exists():
+        pytest.skip("extensions not built yet (run __graft_entry__.build())")
+    native = ext.cuda_sources() + list((ext.CSRC / "kernels").glob("*.cuh")) + list((ext.CSRC / "kernels").glob("*.h")) + \
+        list((ext.CSRC / "runtime").glob("*.h")) + [ext.CSRC / "runtime" / "symm_mem.cpp", ext.CSRC / "bindings.cpp",
+                                                     ext.CSRC / "gemm_bindings.cpp"]
+    stale = [p.name for p in native if p.stat().st_mtime > ext.CUDA_SO.stat().st_mtime]
+    assert not stale, f"{ext.CUDA_SO.name} is older than {stale}: rebuild"
+    assert (ext.CSRC / "runtime" / "host_ext.cpp").stat().st_mtime <= ext.HOST_SO.stat().st_mtime, "host extension is stale"
