@@ -219,7 +219,7 @@ at::Tensor normalize_pad8(const at::Tensor& x, std::vector<double> mean, std::ve
 }
 
 // bf16 NHWC [N,3,H,W] (channels_last) → patch matrix [N*OH*OW, 176] for the 7x7/s2/p3 stem
-// EXPERIMENTAL: training BatchNorm forward whose Σx / Σx² were produced by the fused stem kernel; returns (y, mean, rstd)
+// training BatchNorm forward whose Σx / Σx² were produced by the fused stem kernel; returns (y, mean, rstd)
 std::vector<at::Tensor> bn_forward_presummed(const at::Tensor& x, c10::optional<at::Tensor> res, const at::Tensor& gamma,
                                              const at::Tensor& beta, at::Tensor running_mean, at::Tensor running_var, double eps,
                                              double momentum, bool relu, const at::Tensor& sums) {

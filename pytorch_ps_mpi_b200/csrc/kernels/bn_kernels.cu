@@ -342,7 +342,7 @@ void psb_bn_forward(cudaStream_t s, const void* x, const void* res, const void* 
 }
 
 // Training forward whose per-channel sums were produced elsewhere (the fused stem kernel's epilogue, stem_kernels.cu):
-// finalize + apply only — the statistics pass over x is skipped.  EXPERIMENTAL (PSB200_STEM=fused).
+// finalize + apply only — the statistics pass over x is skipped (the fused stem, default).
 void psb_bn_forward_presummed(cudaStream_t s, const void* x, const void* res, const void* gamma, const void* beta, void* y,
                               const float* sums /*2C, filled by the producer*/, float* mean, float* rstd, float* scale,
                               float* shift, float* running_mean, float* running_var, long long pixels, int C, float eps,

@@ -90,7 +90,7 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
                 sums: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """``sums`` (experimental): fp32 ``[2C]`` = Σx | Σx² over N·H·W already computed by the producer of ``x``."""
+        """``sums``: fp32 ``[2C]`` = Σx | Σx² over N·H·W already computed by the producer of ``x``."""
         if _kernel_ok(x, residual, self.weight) and (self.training or self.running_mean is not None):
             if self.training and self.num_batches_tracked is not None:
                 if self.momentum is None:

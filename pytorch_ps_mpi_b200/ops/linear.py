@@ -54,8 +54,9 @@ def bcast_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
                  w_ptr: int = 0, flag_ptr: int = 0, epoch: int = 0, variant: int = 0) -> torch.Tensor:
     """``act(x @ weight.T + bias)`` on tcgen05 (bf16 in, fp32 accumulate, bf16 out).
 
-    ``variant``: 0 = auto (2-CTA ``cta_group::2`` 256x256 tiles when M >= 256), 1 = 1-CTA, 2 = 2-CTA.  Bits 4-7 / 8-11
-    select the experimental epilogues / diagnostic modes of ``csrc/kernels/bcast_gemm_exp.cu`` (``bench/gemm_variants.py``)."""
+    ``variant``: 0 = auto (2-CTA ``cta_group::2`` 256x256 tiles when M >= 256), 1 = 1-CTA, 2 = 2-CTA.  Bits 4-7 select the
+    2-CTA kernel's epilogue (``csrc/kernels/bcast_gemm2.cu``: 0 = auto → TMA store, 1 = staged full-line stores, 3 = TMA store,
+    4 = the round-1 row-strided stores kept for A/B; ``bench/gemm_variants.py``)."""
     if not (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
             and weight.shape[1] % 8 == 0):
         y = F.linear(x, weight, bias)          # shapes/dtypes the kernel does not cover

@@ -731,7 +731,7 @@ def build_async(n: int, epochs: int, quota: int = 1, consistent: bool = False, d
 
 
 def build_stem_pipeline(n: int = 1, epochs: int = 4, drop: Optional[str] = None) -> Model:
-    """Intra-CTA pipeline of the experimental fused stem kernel (``csrc/kernels/stem_kernels.cu::psb_stem_fwd_kernel``):
+    """Intra-CTA pipeline of the fused stem kernel (``csrc/kernels/stem_kernels.cu::psb_stem_fwd_kernel``):
     builder warps, the MMA warp, the epilogue warps, the cp.async patch loads and the bulk stores, over ``epochs``
     tiles.  mbarrier phase waits are modelled as counts (``wait(parity)`` at tile ``i`` of a double-buffered resource
     == "at least ``i // 2`` completions", exact because nothing can run two phases ahead — which the search confirms by
