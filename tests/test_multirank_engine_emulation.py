@@ -55,6 +55,12 @@ class Cluster:
         self.box = [None] * n
         self.failed = None
         self.multicast = False
+        self.jitter_s = 0.0                            # > 0: every launch is preceded by a random pause (schedule fuzzing)
+
+    def jitter(self):
+        if self.jitter_s:
+            import random
+            time.sleep(random.random() * self.jitter_s)
 
     def fail(self, exc):
         if self.failed is None:
@@ -149,6 +155,7 @@ class Plan:
     def launch(self, epoch, groups, contrib_mask, inv_count, wait_grads, signal_mode, ack_mask=0, version=0, select_out=0,
                average_dynamic=0, active_ptr=0, timeout_s=30.0, wait_mask=0xffffffff, stream=0, tile_begin=0, tile_end=-1,
                wait_value=0, param_hyper=0):
+        self.m.cluster.jitter()
         c, lib = self.c, self.m.lib
         assert wait_grads == 0          # the engine always waits with the one-warp kernel
         if tile_end < 0:
@@ -191,6 +198,7 @@ class M:
 
     def encode(self, kind, wire, grads, first_tile, ntiles, param_idx, tiles_ptr, wire_ptr, scales_ptr, amax_ptr, residual_ptr,
                bpt, cap, ratio, sig_targets, sig_slot, sig_value, sig_counter, stream):
+        self.cluster.jitter()
         n = len(grads)
         assert 0 < n <= 64
         ia = lambda xs: (ctypes.c_int * n)(*xs)      # noqa: E731
@@ -204,6 +212,7 @@ class M:
         self.log.append(("encode", list(first_tile), sig_value if sig_targets else None))
 
     def signal(self, targets, slot, value, extra_slot=-1, extra_value=0, stream=0, version_local=0, version_slot=0):
+        self.cluster.jitter()
         tg = (ctypes.c_void_p * len(targets))(*targets)
         with self.cluster.lock:
             self.lib.emu_signal(tg, len(targets), slot, ctypes.c_uint64(value), _p(1 if extra_slot >= 0 else 0),
@@ -211,6 +220,7 @@ class M:
         self.log.append(("signal", slot, value))
 
     def wait_flags(self, signal_local, slot0, mask, want, timeout_s, stream=0):
+        self.cluster.jitter()
         sig = _words(signal_local)
         try:
             self.cluster.poll(lambda: sig[self.SIG_ERROR] != 0 or all(sig[slot0 + r] >= want for r in range(32) if mask >> r & 1),
@@ -224,6 +234,7 @@ class M:
         self.log.append(("wait", slot0, mask, want))
 
     def select_ready(self, signal_local, consumed, cand_mask, quota, out, timeout_s, version=0, begin_targets=(), stream=0):
+        self.cluster.jitter()
         sig, cons = _words(signal_local), _words(consumed, 64)
 
         def ready():
@@ -261,10 +272,10 @@ def emu(monkeypatch):
     return lib
 
 
-def run_ranks(lib, n, fn, multicast=False):
+def run_ranks(lib, n, fn, multicast=False, jitter_s=0.0):
     """Run ``fn(rank, world)`` on n threads; returns their results, re-raises the first failure."""
     cluster = Cluster(lib, n)
-    cluster.multicast = multicast
+    cluster.multicast, cluster.jitter_s = multicast, jitter_s
     lib.emu_mc_clear()
     out, errs = [None] * n, []
 
@@ -790,4 +801,44 @@ def test_switch_reduction_and_multicast_publish_multirank(emu, n, optim, dtype, 
             atol = 2e-5 + (steps * hyper["lr"] * sum_mag * 2.0 ** -8 if lossy else 0.0)
             for g, q in zip(got, shadow):
                 assert torch.allclose(g, q, rtol=2e-4, atol=atol), float((g - q).abs().max())
+    emu.emu_mc_clear()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_schedules_keep_the_oracle(emu, seed):
+    """Schedule fuzzing: random world size / mode / optimizer / averaging / inactive steps, and a random pause in front of EVERY
+    launch of every rank (so chunk k of one rank meets chunk k+2 of another, servers run ahead of workers and vice versa).
+    Whatever the interleaving, every rank must end on the single-process oracle's parameters."""
+    import random
+    rnd = random.Random(seed)
+    n = rnd.choice([2, 3, 4])
+    mode = rnd.choice(["ps", "ps", "allgather"])
+    optim = rnd.choice(["sgd", "adam"])
+    average = rnd.random() < 0.5
+    skip_until = rnd.choice([0, 0, 1, 2])
+    multicast = rnd.random() < 0.5
+    steps = 4
+    hyper = dict(lr=0.05, momentum=0.9, weight_decay=1e-3) if optim == "sgd" else dict(lr=1e-2, weight_decay=1e-2)
+
+    def rank_main(rank, w):
+        model = _model()
+        cls = ps.SGD if optim == "sgd" else ps.Adam
+        opt = cls(model.named_parameters(), model.parameters(), engine="host", mode=mode, average=average, **hyper)
+        _attach(opt)
+        for s in range(steps):
+            opt.zero_grad(set_to_none=True)
+            _loss(model, *_data(rank, s), skip_head=s < skip_until).backward()
+            opt.step()
+            time.sleep(random.random() * 0.003)
+        opt._engine.check()
+        w.barrier()
+        mine = [p.detach().clone() for p in model.parameters()]
+        opt.close()
+        return mine
+
+    res = run_ranks(emu, n, rank_main, multicast=multicast, jitter_s=0.002)
+    want = _oracle(n, steps, optim, hyper, average, skip_until)
+    for mine in res:
+        for a, b in zip(mine, want):
+            assert torch.allclose(a, b, rtol=5e-5, atol=5e-6), (seed, n, mode, optim, multicast, float((a - b).abs().max()))
     emu.emu_mc_clear()
