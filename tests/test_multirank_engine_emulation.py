@@ -247,6 +247,8 @@ class M:
         with self.cluster.lock:
             self.lib.emu_select(_p(signal_local), _p(consumed), ctypes.c_uint32(cand_mask), quota, _p(out), ctypes.c_uint64(version),
                                 bt, len(begin_targets), ctypes.c_double(1.0))
+        o = _words(out, 64)
+        self.log.append(("select", int(o[0]), int(o[1]), [int(o[2 + r]) for r in range(16)]))
 
     def snapshot(self, signal_local, stage, shadow, params, nbytes, scratch, attempts=2, stream=0):
         with self.cluster.lock:
@@ -842,3 +844,50 @@ def test_randomised_schedules_keep_the_oracle(emu, seed):
         for a, b in zip(mine, want):
             assert torch.allclose(a, b, rtol=5e-5, atol=5e-6), (seed, n, mode, optim, multicast, float((a - b).abs().max()))
     emu.emu_mc_clear()
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_randomised_async_applies_every_gradient_exactly_once(emu, seed):
+    """AsySG-InCon under schedule fuzzing: random worker count, quota, consistent reads, per-worker step counts and pauses.
+    Invariants of the protocol: every posted gradient (worker r, epoch e) is selected by exactly one update, in epoch order per
+    worker; every worker is acknowledged up to its last gradient; after the drain all ranks hold the server's parameters."""
+    import random
+    rnd = random.Random(100 + seed)
+    n = rnd.choice([2, 3, 4])
+    quota = rnd.randint(1, n - 1)
+    consistent = rnd.random() < 0.5
+    nsteps = [0] + [rnd.randint(1, 4) for _ in range(n - 1)]
+
+    def rank_main(rank, w):
+        model = _model()
+        opt = ps.SGD(model.named_parameters(), model.parameters(), engine="host", mode="async", quota=quota, lr=0.05,
+                     average=True, consistent=consistent)
+        _attach(opt)
+        eng = opt._engine
+        if rank == 0:
+            opt.serve()
+        else:
+            for s in range(nsteps[rank]):
+                opt.zero_grad(set_to_none=True)
+                _loss(model, *_data(rank, s), skip_head=False).backward()
+                opt.step()
+                time.sleep(random.random() * 0.004)
+        log = list(_tls.m.log)
+        opt.close()
+        sig = list(_words(eng.arena.local_ptr))
+        return [p.detach().clone() for p in model.parameters()], sig, log
+
+    res = run_ranks(emu, n, rank_main, jitter_s=0.002)
+    taken = {r: [] for r in range(1, n)}
+    for kind, mask, cnt, epochs in (e for e in res[0][2] if e[0] == "select"):
+        assert bin(mask).count("1") == cnt <= quota
+        for r in range(1, n):
+            if mask >> r & 1:
+                taken[r].append(epochs[r])
+    for r in range(1, n):
+        assert taken[r] == list(range(1, nsteps[r] + 1)), (seed, r, taken[r], nsteps[r])     # exactly once, in order
+        assert res[r][1][M.SIG_ACK] == nsteps[r]
+    for mine, _, _ in res[1:]:
+        for a, b in zip(mine, res[0][0]):
+            assert torch.equal(a, b)
+    assert all(torch.isfinite(p).all() for p in res[0][0])
