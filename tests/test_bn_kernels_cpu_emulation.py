@@ -34,6 +34,12 @@ extern "C" void emu_bn_forward(const void* x, const void* res, const void* gamma
   psb_bn_forward(0, x, res, gamma, beta, y, scratch, scratch + 2 * C, scratch + 3 * C, scratch + 4 * C, scratch + 5 * C, rm, rv, pixels, C,
                  eps, mom, relu, 1, mask);
 }
+extern "C" void emu_bn_forward_presummed(const void* x, const void* gamma, const void* beta, void* y, const float* sums,
+                                         float* scratch /*4C*/, float* rm, float* rv, long long pixels, int C, float eps, float mom,
+                                         int relu, void* mask) {
+  psb_bn_forward_presummed(0, x, nullptr, gamma, beta, y, sums, scratch, scratch + C, scratch + 2 * C, scratch + 3 * C, rm, rv, pixels, C,
+                           eps, mom, relu, mask);
+}
 extern "C" void emu_bn_backward(const void* dy, const void* x, const void* y, const void* gamma, const float* mean, const float* rstd,
                                 float* scratch /*5C*/, void* dx, void* dres, void* dgamma, void* dbeta, long long pixels, int C, int relu,
                                 const void* mask) {
@@ -120,3 +126,27 @@ def test_bn_forward_backward_emulated(lib, shape, relu, has_res):
     scale = max(1.0, float(gf.grad.abs().max()))
     assert torch.allclose(dgamma.float() / scale, gf.grad / scale, rtol=2e-2, atol=2e-2)
     assert torch.allclose(dbeta.float() / scale, bf.grad / scale, rtol=2e-2, atol=2e-2)
+
+
+def test_bn_forward_with_sums_from_the_producer(lib):
+    """``psb_bn_forward_presummed`` (the default ResNet stem: Σy / Σy² come out of the stem kernel's epilogue, so BatchNorm
+    skips its statistics pass): same output, mask and running statistics as the full forward."""
+    torch.manual_seed(1)
+    N, H, W, C = 3, 6, 10, 64
+    pixels = N * H * W
+    x = (torch.randn(N, H, W, C) * 2.0 - 0.5).bfloat16()
+    gamma, beta = (torch.rand(C) + 0.5).bfloat16(), (torch.randn(C) * 0.3).bfloat16()
+    xf = x.float().reshape(-1, C)
+    sums = torch.cat([xf.sum(0), (xf * xf).sum(0)]).contiguous()               # what the producer's epilogue accumulates (fp32)
+    rm, rv, y = torch.zeros(C), torch.ones(C), torch.empty_like(x)
+    scratch = torch.zeros(4 * C)
+    mask = torch.zeros(pixels * (C // 8), dtype=torch.uint8)
+    lib.emu_bn_forward_presummed(_p(x), _p(gamma), _p(beta), _p(y), _p(sums), _p(scratch), _p(rm), _p(rv), ctypes.c_longlong(pixels), C,
+                                 ctypes.c_float(1e-5), ctypes.c_float(0.1), 1, _p(mask))
+    orm, orv = torch.zeros(C), torch.ones(C)
+    want = F.relu(F.batch_norm(x.float().permute(0, 3, 1, 2), orm, orv, gamma.float(), beta.float(), True, 0.1, 1e-5)).permute(0, 2, 3, 1)
+    assert torch.allclose(y.float(), want, rtol=2e-2, atol=2e-2)
+    assert torch.allclose(rm, orm, rtol=1e-4, atol=1e-5) and torch.allclose(rv, orv, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(scratch[:C], xf.mean(0), rtol=1e-5, atol=1e-6)         # mean
+    bits = ((mask.view(pixels, C // 8, 1) >> torch.arange(8, dtype=torch.uint8)) & 1).view(N, H, W, C)
+    assert torch.equal(bits.bool(), y.float() > 0)

@@ -31,6 +31,7 @@ extern "C" void emu_pool_bwd(const void* dy, const void* arg, void* dx, int N, i
 extern "C" void emu_norm8(const void* x, void* y, const float* m, const float* s, int N, long long HW) { psb_normalize_pad8_launch(0, x, y, m, s, N, HW); }
 extern "C" void emu_norm3(const void* x, void* y, const float* m, const float* s, int N, long long HW) { psb_normalize_nhwc3_launch(0, x, y, m, s, N, HW); }
 extern "C" void emu_im2col(const void* x, void* a, int N, int H, int W) { psb_im2col_stem_launch(0, x, a, N, H, W); }
+extern "C" void emu_stem_finalize(const float* partial, int grid, void* out) { psb_stem_wgrad_finalize_launch(0, partial, grid, out); }
 '''
 
 
@@ -42,8 +43,13 @@ def lib():
     body = src[src.index('#include "kernels.h"') + len('#include "kernels.h"'):]
     for fn in ("cudaGetDevice", "cudaDeviceGetAttribute"):
         body = body.replace(fn + "(", "emu_" + fn + "(")
+    # + the one plain-CUDA kernel of stem_kernels.cu (everything else there is tcgen05 / TMA): Σ partials → bf16 [64,176]
+    stem = open(os.path.join(_cuda_emu.KDIR, "stem_kernels.cu")).read()
+    body += "\nnamespace { constexpr int SK = 176;\n" + _cuda_emu.cut_function(
+        stem, r"__global__ void __launch_bounds__\(256\) psb_stem_wgrad_finalize_kernel\(") + "\n}\n" + _cuda_emu.cut_function(
+        stem, r"void psb_stem_wgrad_finalize_launch\(")
     body, n = _cuda_emu.rewrite_launches(body)
-    assert n == 7 and "<<<" not in body, n
+    assert n == 8 and "<<<" not in body, n
     common = open(os.path.join(_cuda_emu.KDIR, "common.cuh")).read()
     conv = "\n".join(_cuda_emu.cut_function(common, r"(template <int FP8KIND>[^\n]*\n)?__device__ __forceinline__ [^\n]*\b" + name + r"\(")
                      for name in _cuda_emu.CONVERSIONS)
@@ -116,3 +122,17 @@ def test_stem_im2col_matches_unfold(lib, shape):
     cols = cols.view(N, 3, 7, 7, OH * OW).permute(0, 4, 2, 3, 1).reshape(N * OH * OW, 7, 21)
     want = F.pad(F.pad(cols, (0, 3)).reshape(-1, 168), (0, 8)).bfloat16()
     assert torch.equal(a, want)
+
+
+@pytest.mark.parametrize("grid", [1, 5, 148])
+def test_stem_wgrad_finalize_sums_partials_in_order(lib, grid):
+    """``psb_stem_wgrad_finalize_kernel``: dW2d[co][k] = Σ_cta partial[cta][k][co] in CTA order (deterministic), cast to bf16 — the
+    [64,176] GEMM-layout gradient the engine receives straight in the wire arena."""
+    g = torch.Generator().manual_seed(grid)
+    partial = torch.randn(grid, 176, 64, generator=g)
+    out = torch.full((64, 176), float("nan"), dtype=torch.bfloat16)
+    lib.emu_stem_finalize(_p(partial), grid, _p(out))
+    acc = torch.zeros(176, 64)
+    for c in range(grid):                                                   # the kernel's summation order
+        acc += partial[c]
+    assert torch.equal(out, acc.t().bfloat16())
