@@ -371,13 +371,8 @@ extern "C" void emu_snapshot(const uint64_t* signal_local, const void* stage, vo
 _LIB = None
 
 
-def build():
-    """Compile the emulator once per process; returns the ctypes library (or ``None`` without g++)."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    if shutil.which("g++") is None:
-        return None
+def kernel_source() -> str:
+    """The emulated translation unit of ``ps_kernels.cu``: shim + conversions + the file's own text (kernels AND launchers)."""
     common = open(os.path.join(KDIR, "common.cuh")).read()
     ps = open(os.path.join(KDIR, "ps_kernels.cu")).read()
     conv = "\n".join(cut_function(common, r"(template <int FP8KIND>[^\n]*\n)?__device__ __forceinline__ [^\n]*\b" + name + r"\(")
@@ -393,10 +388,19 @@ def build():
     assert nlaunch >= 8 and "<<<" not in body, nlaunch
     kernels_h = open(os.path.join(KDIR, "kernels.h")).read()
     structs = kernels_h[kernels_h.index("#define PSB_ENCODE_MAX"): kernels_h.index("void psb_launch_absmax")]
-    d = tempfile.mkdtemp(prefix="psb_emu_")
-    src = SHIM_HEAD + conv + "\n}  // namespace psb\n" + CUDA_RT_SHIM + RUNNER + structs + body + DRIVER
     # the anonymous namespace's kernels stay private to the launchers, exactly as in the real translation unit
-    open(os.path.join(d, "emu.cpp"), "w").write(src)
+    return SHIM_HEAD + conv + "\n}  // namespace psb\n" + CUDA_RT_SHIM + RUNNER + structs + body + DRIVER
+
+
+def build():
+    """Compile the emulator once per process; returns the ctypes library (or ``None`` without g++)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if shutil.which("g++") is None:
+        return None
+    d = tempfile.mkdtemp(prefix="psb_emu_")
+    open(os.path.join(d, "emu.cpp"), "w").write(kernel_source())
     cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", CUDA_INC, "-I", KDIR, "-o", os.path.join(d, "emu.so"),
            os.path.join(d, "emu.cpp")]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -404,3 +408,87 @@ def build():
         raise RuntimeError("emulator build failed:\n" + p.stdout[-4000:])
     _LIB = ctypes.CDLL(os.path.join(d, "emu.so"))
     return _LIB
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The REAL Python bindings (csrc/bindings.cpp: UpdatePlan with its window loop, encode batching, signal / wait / select /
+# snapshot marshalling) linked against the emulated kernels: an importable stand-in for ``_psb200_cuda``.
+# ---------------------------------------------------------------------------------------------------------------------
+_EXT = None
+
+
+def bindings_source() -> str:
+    src = open(os.path.join(ROOT, "pytorch_ps_mpi_b200", "csrc", "bindings.cpp")).read()
+
+    def drop(text, what):
+        assert what in text, what
+        return text.replace(what, "")
+
+    for inc in ("#include <ATen/cuda/CUDAContext.h>\n", "#include <c10/cuda/CUDAGuard.h>\n", "#include <c10/cuda/CUDAStream.h>\n",
+                '#include "symm_mem.h"\n', "void bind_gemm(py::module_& m);   // gemm_bindings.cpp\n", "  bind_gemm(m);\n"):
+        src = drop(src, inc)
+    # no CUDA runtime underneath: launches cannot fail, there is one "stream", 148 "SMs"
+    src = src.replace('#include "kernels.h"\n', '#include "kernels.h"\n#define cudaGetLastError() cudaSuccess\n'
+                      '#define cudaGetDevice(p) (*(p) = 0)\n#define cudaDeviceGetAttribute(p, a, d) (*(p) = 148)\n', 1)
+    src = drop(src, "c10::cuda::getCurrentCUDAStream().stream()").replace("cudaStream_t cur_stream() { return ; }",
+                                                                          "cudaStream_t cur_stream() { return nullptr; }")
+    assert "cur_stream() { return nullptr; }" in src
+    src = src.replace("at::kCUDA", "at::kCPU")
+    src = drop(src, "!g.is_cuda() || ")                      # host tensors stand in for device tensors
+    a = src.index("  py::class_<psb::SymmBlock")
+    b = src.index(';', src.index('.def("ptr", &psb::SymmBlock::ptr)')) + 1
+    return src[:a] + src[b:]                                 # the VMM runtime (driver API) is not part of the emulation
+
+
+def build_extension():
+    """Compile ``bindings.cpp`` (transformed as above) + the emulated kernels into ``_psb200_emu``; returns the imported module
+    (or ``None`` without g++).  Cached in the temp directory by source hash: torch's headers take about a minute to compile."""
+    global _EXT
+    if _EXT is not None:
+        return _EXT
+    if shutil.which("g++") is None:
+        return None
+    import hashlib
+    import importlib.machinery
+    import importlib.util
+    import sysconfig
+
+    import pybind11
+    import torch
+    from torch.utils import cpp_extension as ce
+    ksrc, bsrc = kernel_source(), bindings_source()
+    tag = hashlib.sha1((ksrc + bsrc + torch.__version__).encode()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), f"psb_emu_ext_{tag}")
+    so = os.path.join(d, "_psb200_emu.so")
+    if not os.path.exists(so):
+        os.makedirs(d, exist_ok=True)
+        open(os.path.join(d, "emu_kernels.cpp"), "w").write(ksrc)
+        open(os.path.join(d, "bindings_emu.cpp"), "w").write(bsrc)
+        abi = getattr(torch._C, "_GLIBCXX_USE_CXX11_ABI", True)
+        inc = ["-I" + KDIR, "-I" + CUDA_INC, "-I" + sysconfig.get_paths()["include"], "-I" + pybind11.get_include()]
+        inc += ["-I" + p for p in ce.include_paths()]
+        jobs = [["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-w", *inc, "-c", os.path.join(d, "emu_kernels.cpp"), "-o",
+                 os.path.join(d, "emu_kernels.o")],
+                ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={int(abi)}",
+                 "-DTORCH_EXTENSION_NAME=_psb200_emu", "-DTORCH_API_INCLUDE_EXTENSION_H", *inc, "-c",
+                 os.path.join(d, "bindings_emu.cpp"), "-o", os.path.join(d, "bindings_emu.o")]]
+        procs = [subprocess.Popen(j, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for j in jobs]
+        for pr in procs:
+            out, _ = pr.communicate()
+            if pr.returncode != 0:
+                raise RuntimeError("emulated extension build failed:\n" + out[-4000:])
+        libdirs = ce.library_paths()
+        link = ["g++", "-shared", "-o", so + ".tmp", os.path.join(d, "bindings_emu.o"), os.path.join(d, "emu_kernels.o"),
+                *["-L" + x for x in libdirs], *["-Wl,-rpath," + x for x in libdirs], "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+                "-pthread"]
+        p = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("emulated extension link failed:\n" + p.stdout[-4000:])
+        os.replace(so + ".tmp", so)
+    loader = importlib.machinery.ExtensionFileLoader("_psb200_emu", so)
+    spec = importlib.util.spec_from_file_location("_psb200_emu", so, loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    mod.emu = ctypes.CDLL(so)              # the emulator's own entry points (multicast windows) of the SAME library
+    _EXT = mod
+    return mod

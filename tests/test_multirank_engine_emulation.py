@@ -29,6 +29,7 @@ from tests.test_device_engine_control_flow import FakeEvent, FakeStream
 DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 DONE = 1 << 62
 _tls = threading.local()
+_EXT = None          # set by the fixture: None = Python shim over ctypes, else the real bindings module
 
 
 @pytest.fixture(autouse=True)
@@ -255,9 +256,89 @@ class M:
             self.lib.emu_snapshot(_p(signal_local), _p(stage), _p(shadow), _p(params), ctypes.c_size_t(nbytes), _p(scratch), attempts)
 
 
-@pytest.fixture
-def emu(monkeypatch):
-    lib = _cuda_emu.build()
+class PlanProxy:
+    """The REAL ``UpdatePlan`` of ``csrc/bindings.cpp`` (argument marshalling, window loop), with a launch log."""
+
+    def __init__(self, m):
+        object.__setattr__(self, "_m", m)
+        object.__setattr__(self, "_p", m.x.UpdatePlan())
+        # 8 KB windows instead of 128 MB: every multi-tile launch walks the window loop (only the first window waits, only the
+        # last one raises PARAMS_READY / CONSUMED / ACK) — on hardware that loop only runs for >= 128 MB chunks
+        self._p.window_bytes = 8192
+
+    def __setattr__(self, k, v):
+        setattr(self._p, k, v)
+
+    def __getattr__(self, k):
+        return getattr(self._p, k)
+
+    def launch(self, *a, **k):
+        self._m.cluster.jitter()
+        self._p.launch(*a, **k)
+        self._m.log.append(("update", k.get("tile_begin", 0), k.get("tile_end", -1), a[5]))
+
+
+class RealM:
+    """``_psb200_emu``: the repository's real pybind11 bindings linked against the emulated kernels
+    (``_cuda_emu.build_extension``).  Calls hold the GIL, which serialises the (single-threaded) emulator; launches that would
+    spin on a flag are preceded by the same Python-side poll as in :class:`M`."""
+
+    def __init__(self, cluster, ext):
+        self.cluster, self.x, self.log = cluster, ext, []
+
+    def __getattr__(self, k):
+        return getattr(self.x, k)
+
+    def UpdatePlan(self):
+        return PlanProxy(self)
+
+    def encode(self, *a, **k):
+        self.cluster.jitter()
+        self.x.encode(*a, **k)
+        self.log.append(("encode", list(a[3]), a[16] if a[14] else None))
+
+    def signal(self, *a, **k):
+        self.cluster.jitter()
+        self.x.signal(*a, **k)
+        self.log.append(("signal", a[1], a[2]))
+
+    def wait_flags(self, signal_local, slot0, mask, want, timeout_s, stream=0):
+        self.cluster.jitter()
+        sig = _words(signal_local)
+        try:
+            self.cluster.poll(lambda: sig[M.SIG_ERROR] != 0 or all(sig[slot0 + r] >= want for r in range(32) if mask >> r & 1),
+                              f"slot {slot0} mask {mask:#x} >= {want}", timeout=min(timeout_s, 60.0))
+        except TimeoutError:
+            if timeout_s >= 60.0:
+                raise
+        self.x.wait_flags(signal_local, slot0, mask, want, 0.01, stream)
+        assert sig[M.SIG_ERROR] == 0 or timeout_s < 60.0, "device wait timed out"
+        self.log.append(("wait", slot0, mask, want))
+
+    def select_ready(self, signal_local, consumed, cand_mask, quota, out, timeout_s, version=0, begin_targets=(), stream=0):
+        self.cluster.jitter()
+        sig, cons = _words(signal_local), _words(consumed, 64)
+
+        def ready():
+            fin = [r for r in range(32) if cand_mask >> r & 1 and sig[r] >= DONE]
+            rdy = [r for r in range(32) if cand_mask >> r & 1 and r not in fin and sig[r] > cons[r]]
+            need = min(quota, bin(cand_mask).count("1") - len(fin))
+            return need == 0 or len(rdy) >= need
+        self.cluster.poll(ready, "quota gradients")
+        self.x.select_ready(signal_local, consumed, cand_mask, quota, out, 1.0, version, list(begin_targets), stream)
+        o = _words(out, 64)
+        self.log.append(("select", int(o[0]), int(o[1]), [int(o[2 + r]) for r in range(16)]))
+
+
+@pytest.fixture(params=["shim", "bindings"])
+def emu(monkeypatch, request):
+    global _EXT
+    if request.param == "bindings":
+        # the extension module as built from csrc/bindings.cpp; its library also carries the emulator's own entry points
+        _EXT = _cuda_emu.build_extension()
+        lib = None if _EXT is None else _EXT.emu
+    else:
+        _EXT, lib = None, _cuda_emu.build()
     if lib is None:
         pytest.skip("no g++")
     _tls.world, _tls.m = World(Cluster(lib, 1), 0), None      # the test's own thread: a single-process world (oracles)
@@ -282,7 +363,7 @@ def run_ranks(lib, n, fn, multicast=False, jitter_s=0.0):
     out, errs = [None] * n, []
 
     def main(r):
-        _tls.world, _tls.m = World(cluster, r), M(cluster)
+        _tls.world, _tls.m = World(cluster, r), (M(cluster) if _EXT is None else RealM(cluster, _EXT))
         try:
             out[r] = fn(r, _tls.world)
         except BaseException as exc:       # noqa: BLE001
