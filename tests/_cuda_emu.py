@@ -392,6 +392,60 @@ def kernel_source() -> str:
     return SHIM_HEAD + conv + "\n}  // namespace psb\n" + CUDA_RT_SHIM + RUNNER + structs + body + DRIVER
 
 
+def _conversions() -> str:
+    common = open(os.path.join(KDIR, "common.cuh")).read()
+    return "\n".join(cut_function(common, r"(template <int FP8KIND>[^\n]*\n)?__device__ __forceinline__ [^\n]*\b" + name + r"\(")
+                     for name in CONVERSIONS)
+
+
+def _count_launch(define: bool) -> str:
+    return "void psb_count_launch(int) {}\n" if define else "void psb_count_launch(int);\n"
+
+
+def bn_source(define_count_launch: bool = True) -> str:
+    """The emulated translation unit of ``bn_kernels.cu`` (kernels + launchers, dynamic shared memory as a static buffer)."""
+    src = open(os.path.join(KDIR, "bn_kernels.cu")).read()
+    body = src[src.index('#include "kernels.h"') + len('#include "kernels.h"'):]
+    body = body.replace("extern __shared__ float smem[];", "float* smem = emu_dyn_smem;")
+    for fn in ("cudaGetDevice", "cudaDeviceGetAttribute", "cudaMemsetAsync"):
+        body = body.replace(fn + "(", "emu_" + fn + "(")
+    body, n = rewrite_launches(body)
+    assert n >= 8 and "<<<" not in body, n
+    body = body.replace("namespace {\nusing namespace psb;", "namespace emu_bn {\nusing namespace psb;", 1).replace(
+        "}  // namespace\n", "}  // namespace emu_bn\nusing namespace emu_bn;\n", 1)
+    extra = "static float emu_dyn_smem[65536];\nstatic inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }\n"
+    return SHIM_HEAD + _conversions() + "\n}  // namespace psb\n" + extra + _count_launch(define_count_launch) + CUDA_RT_SHIM + \
+        RUNNER + body
+
+
+def pool_source(define_count_launch: bool = True) -> str:
+    """``pool_kernels.cu`` (max-pool, input normalisers, stem im2col: kernels + launchers) plus the one plain-CUDA kernel of
+    ``stem_kernels.cu`` (Σ of the weight-gradient partials; everything else there is tcgen05 / TMA)."""
+    src = open(os.path.join(KDIR, "pool_kernels.cu")).read()
+    body = src[src.index('#include "kernels.h"') + len('#include "kernels.h"'):]
+    for fn in ("cudaGetDevice", "cudaDeviceGetAttribute"):
+        body = body.replace(fn + "(", "emu_" + fn + "(")
+    stem = open(os.path.join(KDIR, "stem_kernels.cu")).read()
+    body += "\nnamespace { constexpr int SK = 176;\n" + cut_function(
+        stem, r"__global__ void __launch_bounds__\(256\) psb_stem_wgrad_finalize_kernel\(") + "\n}\n" + cut_function(
+        stem, r"void psb_stem_wgrad_finalize_launch\(")
+    body, n = rewrite_launches(body)
+    assert n == 8 and "<<<" not in body, n
+    return SHIM_HEAD + _conversions() + "\n}  // namespace psb\n" + CUDA_RT_SHIM + RUNNER + _count_launch(define_count_launch) + body
+
+
+def compile_shared(source: str, prefix: str):
+    """g++ one emulated translation unit (+ its extern "C" driver) into a ctypes library."""
+    d = tempfile.mkdtemp(prefix=prefix)
+    open(os.path.join(d, "emu.cpp"), "w").write(source)
+    p = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", CUDA_INC, "-I", KDIR,
+                        "-o", os.path.join(d, "emu.so"), os.path.join(d, "emu.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True)
+    if p.returncode != 0:
+        raise RuntimeError("emulator build failed:\n" + p.stdout[-4000:])
+    return ctypes.CDLL(os.path.join(d, "emu.so"))
+
+
 def build():
     """Compile the emulator once per process; returns the ctypes library (or ``None`` without g++)."""
     global _LIB

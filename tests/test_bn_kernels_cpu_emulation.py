@@ -22,12 +22,6 @@ def _single_threaded_torch():
     yield
     torch.set_num_threads(n)
 
-EXTRA_SHIM = r'''
-static float emu_dyn_smem[65536];
-static inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
-void psb_count_launch(int) {}
-'''
-
 DRIVER = r'''
 extern "C" void emu_bn_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, float* scratch /*6C*/,
                                float* rm, float* rv, long long pixels, int C, float eps, float mom, int relu, void* mask) {
@@ -53,26 +47,7 @@ def lib():
     import shutil
     if shutil.which("g++") is None:
         pytest.skip("no g++")
-    src = open(os.path.join(_cuda_emu.KDIR, "bn_kernels.cu")).read()
-    body = src[src.index('#include "kernels.h"') + len('#include "kernels.h"'):]
-    body = body.replace("extern __shared__ float smem[];", "float* smem = emu_dyn_smem;")
-    for fn in ("cudaGetDevice", "cudaDeviceGetAttribute", "cudaMemsetAsync"):
-        body = body.replace(fn + "(", "emu_" + fn + "(")
-    body, n = _cuda_emu.rewrite_launches(body)
-    assert n >= 8 and "<<<" not in body, n
-    common = open(os.path.join(_cuda_emu.KDIR, "common.cuh")).read()
-    conv = "\n".join(_cuda_emu.cut_function(common, r"(template <int FP8KIND>[^\n]*\n)?__device__ __forceinline__ [^\n]*\b" + name + r"\(")
-                     for name in _cuda_emu.CONVERSIONS)
-    runner = _cuda_emu.CUDA_RT_SHIM + _cuda_emu.RUNNER
-    d = tempfile.mkdtemp(prefix="psb_emu_bn_")
-    full = _cuda_emu.SHIM_HEAD + conv + "\n}  // namespace psb\n" + EXTRA_SHIM + runner + body.replace("namespace {\nusing namespace psb;", "using namespace psb;", 1).replace("}  // namespace\n", "", 1) + DRIVER
-    open(os.path.join(d, "emu.cpp"), "w").write(full)
-    p = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", _cuda_emu.CUDA_INC, "-I", _cuda_emu.KDIR,
-                        "-o", os.path.join(d, "emu.so"), os.path.join(d, "emu.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       text=True)
-    if p.returncode != 0:
-        raise RuntimeError("emulator build failed:\n" + p.stdout[-3000:])
-    return ctypes.CDLL(os.path.join(d, "emu.so"))
+    return _cuda_emu.compile_shared(_cuda_emu.bn_source() + DRIVER, "psb_emu_bn_")
 
 
 def _p(t):

@@ -23,8 +23,6 @@ def _single_threaded_torch():
     torch.set_num_threads(n)
 
 
-PRELUDE = "void psb_count_launch(int) {}\n"
-
 DRIVER = r'''
 extern "C" void emu_pool_fwd(const void* x, void* y, void* arg, int N, int H, int W, int C) { psb_maxpool3x3s2_forward(0, x, y, arg, N, H, W, C); }
 extern "C" void emu_pool_bwd(const void* dy, const void* arg, void* dx, int N, int H, int W, int C) { psb_maxpool3x3s2_backward(0, dy, arg, dx, N, H, W, C); }
@@ -39,29 +37,7 @@ extern "C" void emu_stem_finalize(const float* partial, int grid, void* out) { p
 def lib():
     if shutil.which("g++") is None:
         pytest.skip("no g++")
-    src = open(os.path.join(_cuda_emu.KDIR, "pool_kernels.cu")).read()
-    body = src[src.index('#include "kernels.h"') + len('#include "kernels.h"'):]
-    for fn in ("cudaGetDevice", "cudaDeviceGetAttribute"):
-        body = body.replace(fn + "(", "emu_" + fn + "(")
-    # + the one plain-CUDA kernel of stem_kernels.cu (everything else there is tcgen05 / TMA): Σ partials → bf16 [64,176]
-    stem = open(os.path.join(_cuda_emu.KDIR, "stem_kernels.cu")).read()
-    body += "\nnamespace { constexpr int SK = 176;\n" + _cuda_emu.cut_function(
-        stem, r"__global__ void __launch_bounds__\(256\) psb_stem_wgrad_finalize_kernel\(") + "\n}\n" + _cuda_emu.cut_function(
-        stem, r"void psb_stem_wgrad_finalize_launch\(")
-    body, n = _cuda_emu.rewrite_launches(body)
-    assert n == 8 and "<<<" not in body, n
-    common = open(os.path.join(_cuda_emu.KDIR, "common.cuh")).read()
-    conv = "\n".join(_cuda_emu.cut_function(common, r"(template <int FP8KIND>[^\n]*\n)?__device__ __forceinline__ [^\n]*\b" + name + r"\(")
-                     for name in _cuda_emu.CONVERSIONS)
-    d = tempfile.mkdtemp(prefix="psb_emu_pool_")
-    full = _cuda_emu.SHIM_HEAD + conv + "\n}  // namespace psb\n" + _cuda_emu.CUDA_RT_SHIM + _cuda_emu.RUNNER + PRELUDE + body + DRIVER
-    open(os.path.join(d, "emu.cpp"), "w").write(full)
-    p = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", _cuda_emu.CUDA_INC, "-I", _cuda_emu.KDIR,
-                        "-o", os.path.join(d, "emu.so"), os.path.join(d, "emu.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       text=True)
-    if p.returncode != 0:
-        raise RuntimeError("emulator build failed:\n" + p.stdout[-3000:])
-    return ctypes.CDLL(os.path.join(d, "emu.so"))
+    return _cuda_emu.compile_shared(_cuda_emu.pool_source() + DRIVER, "psb_emu_pool_")
 
 
 def _p(t):
