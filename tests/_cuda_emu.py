@@ -479,7 +479,7 @@ def bindings_source() -> str:
         return text.replace(what, "")
 
     for inc in ("#include <ATen/cuda/CUDAContext.h>\n", "#include <c10/cuda/CUDAGuard.h>\n", "#include <c10/cuda/CUDAStream.h>\n",
-                '#include "symm_mem.h"\n', "void bind_gemm(py::module_& m);   // gemm_bindings.cpp\n", "  bind_gemm(m);\n"):
+                '#include "symm_mem.h"\n'):
         src = drop(src, inc)
     # no CUDA runtime underneath: launches cannot fail, there is one "stream", 148 "SMs"
     src = src.replace('#include "kernels.h"\n', '#include "kernels.h"\n#define cudaGetLastError() cudaSuccess\n'
@@ -492,6 +492,60 @@ def bindings_source() -> str:
     a = src.index("  py::class_<psb::SymmBlock")
     b = src.index(';', src.index('.def("ptr", &psb::SymmBlock::ptr)')) + 1
     return src[:a] + src[b:]                                 # the VMM runtime (driver API) is not part of the emulation
+
+
+GEMM_STANDINS = r"""
+// ---- the tensor-core kernels (tcgen05 / TMEM / TMA) are NOT emulated: reference math through ATen with the same contract ----
+at::Tensor bcast_gemm(const at::Tensor& x, uint64_t w_ptr, int64_t N, int64_t K, c10::optional<at::Tensor> bias, bool relu,
+                      uint64_t flag_ptr, uint64_t epoch, double timeout_s, int variant) {
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.size(1) == K, "x must be [M,K] bf16");
+  if (flag_ptr) TORCH_CHECK(*reinterpret_cast<const volatile uint64_t*>(flag_ptr) >= epoch, "gate: PARAMS_READY not reached");
+  auto w = at::from_blob(reinterpret_cast<void*>(w_ptr), {N, K}, x.options());
+  auto y = at::matmul(x.to(at::kFloat), w.to(at::kFloat).t());
+  if (bias.has_value() && bias->defined()) y = y + bias->to(at::kFloat);
+  if (relu) y = at::relu(y);
+  return y.to(at::kBFloat16);
+}
+
+std::vector<at::Tensor> stem_fwd(const at::Tensor& x, const at::Tensor& w2d, bool want_sums, uint64_t flag_ptr, uint64_t epoch,
+                                 double timeout_s) {
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.size(1) == 3, "x must be [N,3,H,W] bf16");
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "x must be channels_last contiguous");
+  TORCH_CHECK(w2d.dim() == 2 && w2d.size(0) == 64 && w2d.size(1) == 176 && w2d.is_contiguous(), "w2d must be [64,176]");
+  if (flag_ptr) TORCH_CHECK(*reinterpret_cast<const volatile uint64_t*>(flag_ptr) >= epoch, "gate: PARAMS_READY not reached");
+  const int64_t N = x.size(0), H = x.size(2), W = x.size(3), OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  TORCH_CHECK(W % 8 == 0 && W <= 256 && W >= 8, "fused stem: W must be a multiple of 8 and <= 256");
+  auto a = im2col_stem(x);                                           // the REAL (emulated) patch-matrix kernel
+  auto y32 = at::matmul(a.to(at::kFloat), w2d.to(at::kFloat).t());   // [M,64], fp32 accumulators
+  at::Tensor sums = want_sums ? at::cat({y32.sum(0), (y32 * y32).sum(0)}).contiguous() : at::Tensor();
+  return {y32.to(at::kBFloat16).view({N, OH, OW, 64}).permute({0, 3, 1, 2}), sums};
+}
+
+at::Tensor stem_wgrad(const at::Tensor& x, const at::Tensor& gy) {
+  check_nhwc(gy, "gy");
+  auto a = im2col_stem(x);                                           // [M,176]
+  auto g = gy.permute({0, 2, 3, 1}).reshape({-1, 64});               // NHWC rows
+  return at::matmul(a.to(at::kFloat).t(), g.to(at::kFloat)).unsqueeze(0).contiguous();   // one "CTA" partial [1,176,64]
+}
+"""
+
+
+def gemm_bindings_source() -> str:
+    """``csrc/gemm_bindings.cpp`` for the emulated extension: the bindings of every plain-CUDA op are the repository's own text
+    (BatchNorm forward / presummed / backward, max-pool, normalisers, im2col, wgrad finalize, ``bind_gemm``); the three
+    tensor-core entry points are replaced by ATen reference math (``GEMM_STANDINS``)."""
+    src = open(os.path.join(ROOT, "pytorch_ps_mpi_b200", "csrc", "gemm_bindings.cpp")).read()
+    real = ["void check_nhwc", "std::vector<at::Tensor> bn_forward", "std::vector<at::Tensor> bn_backward",
+            "std::vector<at::Tensor> maxpool_forward", "at::Tensor maxpool_backward", "at::Tensor normalize_pad8",
+            "std::vector<at::Tensor> bn_forward_presummed", "at::Tensor stem_wgrad_finalize", "at::Tensor im2col_stem",
+            "at::Tensor normalize_nhwc3"]
+    parts = [cut_function(src, re.escape(h) + r"\(") for h in real]
+    text = "\n\n".join(parts[:1] + [parts[8]] + parts[1:8] + parts[9:])          # im2col_stem before its users
+    text = text.replace("c10::cuda::getCurrentCUDAStream().stream()", "nullptr").replace(".is_cuda()", ".defined()").replace(
+        "->is_cuda()", "->defined()")
+    head = ('#include <torch/extension.h>\n#include "kernels.h"\n#define cudaGetLastError() cudaSuccess\n'
+            '#define cudaGetErrorString(e) "n/a"\nnamespace py = pybind11;\nint psb_bcast_gemm_smem_bytes() { return 0; }\nnamespace {\n')
+    return head + text + GEMM_STANDINS + "\n}  // namespace\n" + cut_function(src, r"void bind_gemm\(py::module_& m\)") + "\n"
 
 
 def build_extension():
@@ -511,7 +565,8 @@ def build_extension():
     import torch
     from torch.utils import cpp_extension as ce
     ksrc, bsrc = kernel_source(), bindings_source()
-    tag = hashlib.sha1((ksrc + bsrc + torch.__version__).encode()).hexdigest()[:16]
+    extra = {"emu_bn": bn_source(False), "emu_pool": pool_source(False), "gemm_emu": gemm_bindings_source()}
+    tag = hashlib.sha1((ksrc + bsrc + "".join(extra.values()) + torch.__version__).encode()).hexdigest()[:16]
     d = os.path.join(tempfile.gettempdir(), f"psb_emu_ext_{tag}")
     so = os.path.join(d, "_psb200_emu.so")
     if not os.path.exists(so):
@@ -526,6 +581,11 @@ def build_extension():
                 ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={int(abi)}",
                  "-DTORCH_EXTENSION_NAME=_psb200_emu", "-DTORCH_API_INCLUDE_EXTENSION_H", *inc, "-c",
                  os.path.join(d, "bindings_emu.cpp"), "-o", os.path.join(d, "bindings_emu.o")]]
+        for name, text in extra.items():
+            open(os.path.join(d, name + ".cpp"), "w").write(text)
+            flags = [f"-D_GLIBCXX_USE_CXX11_ABI={int(abi)}", "-DTORCH_API_INCLUDE_EXTENSION_H"] if name == "gemm_emu" else []
+            jobs.append(["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-w", *flags, *inc, "-c", os.path.join(d, name + ".cpp"),
+                         "-o", os.path.join(d, name + ".o")])
         procs = [subprocess.Popen(j, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for j in jobs]
         for pr in procs:
             out, _ = pr.communicate()
@@ -533,6 +593,7 @@ def build_extension():
                 raise RuntimeError("emulated extension build failed:\n" + out[-4000:])
         libdirs = ce.library_paths()
         link = ["g++", "-shared", "-o", so + ".tmp", os.path.join(d, "bindings_emu.o"), os.path.join(d, "emu_kernels.o"),
+                *[os.path.join(d, name + ".o") for name in extra],
                 *["-L" + x for x in libdirs], *["-Wl,-rpath," + x for x in libdirs], "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python",
                 "-pthread"]
         p = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

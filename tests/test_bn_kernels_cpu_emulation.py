@@ -3,9 +3,6 @@ apply with the 1-bit ReLU mask, backward reduce / finalize / apply reading the m
 the CPU emulator, against ``F.batch_norm`` + autograd in fp32.  ``kernel<<<grid, block, smem, s>>>(args)`` is rewritten to the
 emulator's CTA runner, so the real grid-size logic (``grid_for`` / ``REDUCE_MIN_ITERS``) is what runs."""
 import ctypes
-import os
-import subprocess
-import tempfile
 
 import pytest
 import torch

@@ -3,10 +3,7 @@ normalisers and the stem's im2col — executed on the CPU **through their real l
 shape): the whole translation unit is compiled with g++ against the fiber emulator (``tests/_cuda_emu.py``) with its
 ``<<< >>>`` launches rewritten, and compared with ``F.max_pool2d`` + autograd / plain torch expressions."""
 import ctypes
-import os
 import shutil
-import subprocess
-import tempfile
 
 import pytest
 import torch
