@@ -31,6 +31,13 @@ class ModelM(H.RealM):
         return self.x.stem_fwd(x, w2d, want_sums, flag_ptr, epoch, timeout_s)
 
 
+    def bcast_gemm(self, x, w_ptr, N, K, bias, relu, flag_ptr=0, epoch=0, timeout_s=30.0, variant=0):
+        if flag_ptr:
+            self.cluster.poll(lambda: H._words(flag_ptr, 1)[0] >= epoch, "gated PARAMS_READY (GEMM)")
+            self.log.append(("gate", epoch))
+        return self.x.bcast_gemm(x, w_ptr, N, K, bias, relu, flag_ptr, epoch, timeout_s, variant)
+
+
 @pytest.fixture
 def world(monkeypatch):
     extm = _cuda_emu.build_extension()
@@ -183,3 +190,78 @@ def test_resnet_matches_a_plain_torch_model_loosely(world):
         err = (got.float() - want.detach()).abs().max()
         # the update itself (≈ lr·grad) must be reproduced to bf16 accuracy; parameters are stored in bf16 (2^-8 relative)
         assert float(err) <= 0.1 * float(step.abs().max()) + 2.0 ** -7 * float(want.abs().max()) + 1e-3, (name, float(err))
+
+
+@pytest.mark.parametrize("pull", [False, True])
+def test_gated_first_linear_of_an_mlp(world, pull):
+    """``convert_first_linear`` + ``BcastLinear.attach``: the first forward GEMM acquires the broadcast epoch itself (no wait kernel
+    on workers), optionally reading the weight from the SERVER's arena (``pull``), and writes dW straight into the wire arena — 3
+    ranks, bf16 parameters with fp32 masters, against the grad-gather oracle (each step: every rank's actual gradients, summed in
+    fp32, reference SGD on fp32 shadows)."""
+    from pytorch_ps_mpi_b200.ops.linear import BcastLinear, convert_first_linear
+    n, steps = 3, 3
+    hyper = dict(lr=0.05, momentum=0.9)
+    cluster = H.Cluster(world.emu, n)
+    out, errs = [None] * n, []
+
+    def main(rank):
+        H._tls.world, H._tls.m = H.World(cluster, rank), ModelM(cluster, world)
+        w = H._tls.world
+        try:
+            with _lock:
+                torch.manual_seed(0)
+                model = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.Linear(64, 10)).bfloat16()
+            shadow = [torch.nn.Parameter(p.detach().float().clone()) for p in model.parameters()]
+            oracle = ps.SGD([(f"p{i}", q) for i, q in enumerate(shadow)], shadow, engine="host", use_mpi=False, **hyper)
+            for h in oracle._hooks:
+                h.remove()
+            groups = oracle._group_of()
+            opt = ps.SGD(model.named_parameters(), model.parameters(), mode="ps", engine="device", **hyper)
+            layer = convert_first_linear(model, opt, relu=True, pull=pull, gate=True)
+            assert isinstance(layer, BcastLinear) and model[0] is layer
+            eng = opt._engine
+            for s in range(steps):
+                g = torch.Generator().manual_seed(10 * rank + s)
+                x, y = torch.randn(8, 32, generator=g).bfloat16(), torch.randint(0, 10, (8,), generator=g)
+                opt.zero_grad(set_to_none=True)
+                torch.nn.functional.cross_entropy(model(x).float(), y).backward()
+                mine = [p.grad.detach().float().clone() for p in model.parameters()]
+                opt.step()
+                allg = w.all_gather_object(mine)
+                with torch.no_grad():
+                    for i, q in enumerate(shadow):
+                        oracle.optim_step(q, sum(allg[r][i] for r in range(n)), **oracle._hyper(groups[id(q)]))
+            eng.ensure_params()
+            eng.check()
+            w.barrier()
+            got = [(opt.state[p]["master_param"] if eng.master is not None else p).detach().float().clone()
+                   for p in model.parameters()]
+            res = dict(got=got, pub=[p.detach().clone() for p in model.parameters()], shadow=[q.detach().clone() for q in shadow],
+                       log=list(H._tls.m.log), direct=set(eng.direct_names), server=eng.is_server)
+            opt.close()
+            oracle.close()
+            out[rank] = res
+        except BaseException as exc:       # noqa: BLE001
+            errs.append(exc)
+            cluster.fail(exc)
+
+    ts = [threading.Thread(target=main, args=(r,), daemon=True) for r in range(n)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not any(t.is_alive() for t in ts), "a rank thread is stuck"
+    if errs:
+        real = [e for e in errs if "another rank" not in str(e) and not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or errs)[0]
+    for r, res in enumerate(out):
+        for a, b in zip(res["pub"], out[0]["pub"]):
+            assert torch.equal(a, b)
+        if res["server"]:
+            for g, q in zip(res["got"], res["shadow"]):
+                assert torch.allclose(g, q, rtol=2e-4, atol=2e-5), float((g - q).abs().max())
+        assert "0.weight" in res["direct"]                                  # dW of the gated layer skipped the encode pass
+        waits = [e for e in res["log"] if e[0] == "wait" and e[1] == H.M.SIG_PARAMS_READY]
+        gates = [e[1] for e in res["log"] if e[0] == "gate"]
+        if r > 0:
+            assert len(waits) == 1 and gates == list(range(1, steps)), (waits, gates)
