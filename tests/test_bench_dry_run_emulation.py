@@ -155,6 +155,28 @@ def test_bench_main_runs_end_to_end_on_the_emulator(bench_env, monkeypatch, caps
     assert out["warmup_total_steps"] >= 5 and set(out["step_ms"]) >= {"median", "p90", "min", "max"}
 
 
+@pytest.mark.parametrize("extra,expect", [
+    (["--mode", "async"], dict(mode="async", contributors=1)),
+    (["--code", "topk:0.25", "--optim", "adam"], dict(coding="topk:0.25", optimizer="adam")),
+    (["--mode", "allgather", "--code", "scale:int8", "--no-pipeline"], dict(coding="scale:int8"))])
+def test_bench_other_configurations_at_two_ranks(bench_env, monkeypatch, capsys, extra, expect):
+    """The other BASELINE configurations through the same ``main()``: AsySG-InCon (rank 0 only serves; throughput counts the
+    workers), a top-k coded wire with Adam, all-gather with an int8 wire and the unpipelined update."""
+    bench, extm = bench_env
+    out = _run_bench(bench, extm, 2, ["--steps", "2", "--warmup", "3", "--batch", "2", "--no-comparators"] + extra, monkeypatch, capsys)
+    cfg = out["config"]
+    assert out["value"] > 0 and out["e2e"]["value"] > 0 and out["gpu_launches"] > 0
+    if "mode" in expect:
+        assert expect["mode"] in cfg["parallelism"] and cfg["global_batch"] == 2 * expect["contributors"] and out["check"] is None
+    else:
+        assert out["check"]["params_bit_identical_across_ranks"] and out["check"]["params_finite"]
+    for k in ("coding", "optimizer"):
+        if k in expect:
+            assert cfg[k] == expect[k]
+    if "--no-pipeline" in extra:
+        assert cfg["update_pipeline_chunks"] == 1
+
+
 def test_bench_with_same_invocation_comparators(bench_env, monkeypatch, capsys):
     """The comparator block (NCCL-PS and the stock-tools reference-equivalent path, ``baseline/comparator.py``) after the headline:
     whatever happens in it — here NCCL cannot exist — the headline line is still printed, with a value or an error per comparator."""
