@@ -265,3 +265,84 @@ def test_gated_first_linear_of_an_mlp(world, pull):
         gates = [e[1] for e in res["log"] if e[0] == "gate"]
         if r > 0:
             assert len(waits) == 1 and gates == list(range(1, steps)), (waits, gates)
+
+
+def test_tiny_bert_topk_adam_with_never_used_heads(world):
+    """BASELINE config 4 in miniature: the package's BERT (tied decoder: one hook for two uses of the embedding matrix; the pooler
+    and NSP head get NO gradient when only the MLM loss is trained → inactive parameters on every step), block-wise top-k wire,
+    Adam with per-parameter step counts, bf16 parameters with fp32 masters, 2 ranks — against the grad-gather oracle."""
+    n, steps = 2, 3
+    hyper = dict(lr=1e-2, eps=1e-8, weight_decay=1e-2)
+    cluster = H.Cluster(world.emu, n)
+    out, errs = [None] * n, []
+
+    def main(rank):
+        H._tls.world, H._tls.m = H.World(cluster, rank), ModelM(cluster, world)
+        w = H._tls.world
+        try:
+            with _lock:
+                torch.manual_seed(0)
+                model = models.bert_base(vocab_size=97, hidden_size=32, num_hidden_layers=2, num_attention_heads=4,
+                                         intermediate_size=64, max_position_embeddings=16).bfloat16()
+            names = [k for k, _ in model.named_parameters()]
+            shadow = [torch.nn.Parameter(p.detach().float().clone()) for p in model.parameters()]
+            oracle = ps.Adam([(f"p{i}", q) for i, q in enumerate(shadow)], shadow, engine="host", use_mpi=False, **hyper)
+            for h in oracle._hooks:
+                h.remove()
+            groups = oracle._group_of()
+            opt = ps.Adam(model.named_parameters(), model.parameters(), mode="ps", engine="device", code=ps.TopK(ratio=0.25), **hyper)
+            eng = opt._engine
+            before = {k: p.detach().clone() for k, p in model.named_parameters()}
+            for s in range(steps):
+                g = torch.Generator().manual_seed(7 * rank + s)
+                ids = torch.randint(0, 97, (4, 12), generator=g)
+                lab = torch.where(torch.rand(4, 12, generator=g) < 0.3, ids, torch.full_like(ids, -100))
+                lab[0, 0] = ids[0, 0]
+                opt.zero_grad(set_to_none=True)
+                model(ids, mlm_labels=lab, nsp_labels=None).backward()
+                mine = [None if p.grad is None else p.grad.detach().clone() for p in model.parameters()]
+                opt.step()
+                allg = w.all_gather_object(mine)
+                with torch.no_grad():
+                    for i, q in enumerate(shadow):
+                        if allg[0][i] is None:
+                            continue
+                        total = torch.zeros_like(q)
+                        for r in range(n):
+                            code = ps.TopK(ratio=0.25)
+                            total += code.decode(code.encode(allg[r][i], name=f"p{i}")).reshape(q.shape).float()
+                        oracle.optim_step(q, total, **oracle._hyper(groups[id(q)]))
+            eng.check()
+            w.barrier()
+            got = [(opt.state[p]["master_param"] if eng.master is not None else p).detach().float().clone()
+                   for p in model.parameters()]
+            sd = opt.state_dict()
+            res = dict(names=names, got=got, shadow=[q.detach().clone() for q in shadow], server=eng.is_server,
+                       pub={k: p.detach().clone() for k, p in model.named_parameters()}, before=before,
+                       steps=[int(st.get("step", 0)) for st in sd["state"].values()] if eng.is_server else None)
+            opt.close()
+            oracle.close()
+            out[rank] = res
+        except BaseException as exc:       # noqa: BLE001
+            errs.append(exc)
+            cluster.fail(exc)
+
+    ts = [threading.Thread(target=main, args=(r,), daemon=True) for r in range(n)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not any(t.is_alive() for t in ts), "a rank thread is stuck"
+    if errs:
+        real = [e for e in errs if "another rank" not in str(e) and not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or errs)[0]
+    for res in out:
+        unused = [k for k in res["names"] if k.startswith("nsp.") or "pooler" in k]
+        assert len(unused) == 4
+        for k in res["names"]:
+            assert torch.equal(res["pub"][k], out[0]["pub"][k])                     # ranks identical
+            assert torch.equal(res["pub"][k], res["before"][k]) == (k in unused), k   # never-used heads untouched, the rest moved
+        if res["server"]:
+            for k, g, q in zip(res["names"], res["got"], res["shadow"]):
+                assert torch.allclose(g, q, rtol=2e-4, atol=2e-5), (k, float((g - q).abs().max()))
+            assert sorted(set(res["steps"])) == [0, steps]                           # per-parameter step counts
