@@ -200,15 +200,19 @@ class M:
     def encode(self, kind, wire, grads, first_tile, ntiles, param_idx, tiles_ptr, wire_ptr, scales_ptr, amax_ptr, residual_ptr,
                bpt, cap, ratio, sig_targets, sig_slot, sig_value, sig_counter, stream):
         self.cluster.jitter()
-        n = len(grads)
-        assert 0 < n <= 64
-        ia = lambda xs: (ctypes.c_int * n)(*xs)      # noqa: E731
+        assert len(grads) > 0
         tg = (ctypes.c_void_p * max(len(sig_targets), 1))(*sig_targets)
-        with self.cluster.lock:
-            rc = self.lib.emu_encode(kind, wire, n, (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads]), ia(first_tile),
-                                     ia(ntiles), ia(param_idx), _p(tiles_ptr), _p(wire_ptr), _p(scales_ptr), _p(amax_ptr),
-                                     _p(residual_ptr), bpt, cap, ctypes.c_double(ratio), DT[grads[0].dtype], tg, len(sig_targets),
-                                     sig_slot, ctypes.c_uint64(sig_value), _p(sig_counter))
+        for base in range(0, len(grads), 64):          # PSB_ENCODE_MAX tensors per launch; only the last launch raises the flag
+            sl = slice(base, base + 64)
+            n = len(grads[sl])
+            last = base + 64 >= len(grads)
+            ia = lambda xs: (ctypes.c_int * n)(*xs[sl])      # noqa: E731
+            with self.cluster.lock:
+                rc = self.lib.emu_encode(kind, wire, n, (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads[sl]]), ia(first_tile),
+                                         ia(ntiles), ia(param_idx), _p(tiles_ptr), _p(wire_ptr), _p(scales_ptr), _p(amax_ptr),
+                                         _p(residual_ptr), bpt, cap, ctypes.c_double(ratio), DT[grads[0].dtype], tg,
+                                         len(sig_targets) if last else 0, sig_slot, ctypes.c_uint64(sig_value), _p(sig_counter))
+            assert rc == 0
         assert rc == 0
         self.log.append(("encode", list(first_tile), sig_value if sig_targets else None))
 
@@ -972,3 +976,72 @@ def test_randomised_async_applies_every_gradient_exactly_once(emu, seed):
         for a, b in zip(mine, res[0][0]):
             assert torch.equal(a, b)
     assert all(torch.isfinite(p).all() for p in res[0][0])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_many_odd_shaped_parameters_groups_and_encode_batches(emu, monkeypatch, dtype):
+    """Layout / batching stress at 2 ranks: 150 parameters of awkward sizes (1 element … several tiles, a channels-last conv
+    weight that keeps its physical order in the arena) in ONE big chunk → encode launches are split at 64 tensors per launch
+    and only the last one raises the flag; three parameter groups with different hyper-parameters; a random third of the
+    parameters sits out each step (the same ones on every rank).  Oracle: ``torch.optim.SGD`` per group on the summed gradients."""
+    monkeypatch.setenv("PSB200_CHUNK_BYTES", str(64 << 20))               # everything in one chunk → > 64 tensors per encode call
+    import random
+    rnd = random.Random(5)
+    sizes = [rnd.choice([1, 3, 7, 8, 17, 64, 300, 2048, 2049, 5000]) for _ in range(149)]
+    steps, n = 3, 2
+    groups_of = [i % 3 for i in range(150)]
+    ghyper = [dict(lr=0.1, momentum=0.9, weight_decay=0.0), dict(lr=0.05, momentum=0.0, weight_decay=1e-2),
+              dict(lr=0.02, momentum=0.5, weight_decay=1e-3, nesterov=True)]
+    skip = [set(rnd.sample(range(150), 50)) for _ in range(steps)]
+
+    def make_params():
+        with _rng_lock:
+            torch.manual_seed(3)
+            ps_ = [torch.nn.Parameter(torch.randn(s).to(dtype)) for s in sizes]
+            conv = torch.nn.Parameter(torch.randn(8, 4, 3, 3).to(dtype).contiguous(memory_format=torch.channels_last))
+            return ps_ + [conv]
+
+    def grads_for(rank, s, params):
+        g = torch.Generator().manual_seed(1000 * s + rank)
+        return [torch.randn(p.shape, generator=g).to(dtype) for p in params]
+
+    def rank_main(rank, w):
+        params = make_params()
+        named = [(f"p{i}", p) for i, p in enumerate(params)]
+        pgs = [dict(params=[p for i, p in enumerate(params) if groups_of[i] == g], **ghyper[g]) for g in range(3)]
+        opt = ps.SGD(named, pgs, engine="host", mode="ps", lr=0.1)
+        _attach(opt)
+        eng = opt._engine
+        assert eng.nchunks == 1 and eng.layout.nparams == 150
+        for s in range(steps):
+            opt.zero_grad(set_to_none=True)
+            gs = grads_for(rank, s, params)
+            loss = sum((p.float() * g.float()).sum() for i, (p, g) in enumerate(zip(params, gs)) if i not in skip[s])
+            loss.backward()
+            opt.step()
+        eng.check()
+        w.barrier()
+        got = [(opt.state[p]["master_param"] if eng.master is not None else p).detach().float().clone() for p in params]
+        pub = [p.detach().clone() for p in params]
+        strides = params[-1].stride()
+        enc = [e for e in _tls.m.log if e[0] == "encode"]
+        opt.close()
+        return got, pub, strides, enc, eng.is_server
+
+    res = run_ranks(emu, n, rank_main)
+    # oracle in fp32 on the dtype-rounded gradients the ranks produced
+    ref = [torch.nn.Parameter(p.detach().float().clone()) for p in make_params()]
+    o = torch.optim.SGD([dict(params=[p for i, p in enumerate(ref) if groups_of[i] == g], **ghyper[g]) for g in range(3)], lr=0.1)
+    for s in range(steps):
+        per_rank = [grads_for(r, s, ref) for r in range(n)]
+        for i, p in enumerate(ref):
+            p.grad = None if i in skip[s] else sum(pr[i].float() for pr in per_rank)
+        o.step()
+    for got, pub, strides, enc, is_server in res:
+        assert strides == (36, 1, 12, 4)                                   # channels-last physical order kept inside the arena
+        for a, b in zip(pub, res[0][1]):
+            assert torch.equal(a, b)
+        if is_server:
+            for i, (g, q) in enumerate(zip(got, ref)):
+                assert torch.allclose(g, q.detach(), rtol=1e-5, atol=1e-6), (i, sizes[i] if i < 149 else "conv", float((g - q.detach()).abs().max()))
+        assert len(enc) == steps                                           # one encode CALL per step; the binding splits it
