@@ -157,7 +157,7 @@ def tune_host_allocator() -> bool:
     return ok
 
 
-def bind_to_gpu_numa_node(device=None, min_cpus: int = 4, nvml=None) -> dict:
+def bind_to_gpu_numa_node(device=None, min_cpus: int = 8, nvml=None) -> dict:
     """Pin every thread of this process to the CPUs NVML reports as local to ``device``'s PCIe root (the socket / NUMA node
     the GPU hangs off), so the launch path rings a local doorbell and pinned staging buffers allocated afterwards are
     first-touched on the local node — what ``mpirun --bind-to numa`` does for the reference's ranks (``Makefile:2`` leaves
@@ -165,7 +165,7 @@ def bind_to_gpu_numa_node(device=None, min_cpus: int = 4, nvml=None) -> dict:
     half of the ranks pull their input batches across the socket interconnect.
 
     Never raises; returns ``{"bound": bool, "cpus": n, "why": ...}``.  Skipped when the allowed set would shrink below
-    ``min_cpus`` or ``PSB200_NUMA_BIND=0``."""
+    ``min_cpus`` or a quarter of what the process may use now, or with ``PSB200_NUMA_BIND=0``."""
     out = {"bound": False, "cpus": 0, "why": ""}
     if os.environ.get("PSB200_NUMA_BIND", "1") == "0":
         out["why"] = "disabled"
@@ -193,7 +193,9 @@ def bind_to_gpu_numa_node(device=None, min_cpus: int = 4, nvml=None) -> dict:
         local = {64 * w + b for w, word in enumerate(words) for b in range(64) if int(word) >> b & 1}
         want = allowed & local
         out["cpus"] = len(want)
-        if len(want) < min_cpus:
+        # never trade locality for contention: the local share of the allowed CPUs must be a real socket's worth (a cpuset
+        # that leaves only a handful of local CPUs would stack every rank of that socket onto them)
+        if len(want) < max(min_cpus, len(allowed) // 4):
             out["why"] = f"only {len(want)} of the {len(allowed)} allowed CPUs are local to the GPU"
             return out
         if want == allowed:
