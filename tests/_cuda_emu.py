@@ -275,7 +275,12 @@ def rewrite_launches(text: str):
 
 CUDA_RT_SHIM = r'''
 static inline int emu_cudaGetDevice(int* d) { *d = 0; return 0; }
-static inline int emu_cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return 0; }
+// the "GPU" has emu_sm_count SMs (148 = B200).  Tests shrink it so that the launchers' grid caps bind on small tensors and the
+// kernels' grid-stride loops run more than one iteration per CTA — on hardware that is the normal case (ResNet-18: 14 336 pool rows
+// on 2 368 CTAs).  Weak: one copy shared by every emulated translation unit of a library.
+__attribute__((weak)) int emu_sm_count = 148;
+extern "C" __attribute__((weak)) void emu_set_sm_count(int n) { emu_sm_count = n; }
+static inline int emu_cudaDeviceGetAttribute(int* v, int, int) { *v = emu_sm_count; return 0; }
 static inline int emu_cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 '''
 
@@ -483,7 +488,7 @@ def bindings_source() -> str:
         src = drop(src, inc)
     # no CUDA runtime underneath: launches cannot fail, there is one "stream", 148 "SMs"
     src = src.replace('#include "kernels.h"\n', '#include "kernels.h"\n#define cudaGetLastError() cudaSuccess\n'
-                      '#define cudaGetDevice(p) (*(p) = 0)\n#define cudaDeviceGetAttribute(p, a, d) (*(p) = 148)\n', 1)
+                      '#define cudaGetDevice(p) (*(p) = 0)\nextern int emu_sm_count;\n#define cudaDeviceGetAttribute(p, a, d) (*(p) = emu_sm_count)\n', 1)
     src = drop(src, "c10::cuda::getCurrentCUDAStream().stream()").replace("cudaStream_t cur_stream() { return ; }",
                                                                           "cudaStream_t cur_stream() { return nullptr; }")
     assert "cur_stream() { return nullptr; }" in src

@@ -54,6 +54,21 @@ def _p(t):
 @pytest.mark.parametrize("shape,relu,has_res", [((2, 16, 6, 5), True, True), ((3, 64, 9, 9), True, False), ((2, 8, 4, 4), False, True),
                                                 ((1, 512, 5, 5), True, False), ((12, 16, 12, 12), False, False)])
 def test_bn_forward_backward_emulated(lib, shape, relu, has_res):
+    _bn_case(lib, shape, relu, has_res)
+
+
+def test_bn_with_capped_grids(lib):
+    """One "SM": every launcher's grid cap (8 CTAs per SM) binds, so the apply / reduce kernels run their grid-stride loops several
+    times per CTA — the normal case on hardware (ResNet-18 layer1: 25 088 pixel batches on 1 184 CTAs)."""
+    lib.emu_set_sm_count(1)
+    try:
+        _bn_case(lib, (4, 64, 12, 12), True, True)
+        _bn_case(lib, (3, 16, 9, 7), False, False)
+    finally:
+        lib.emu_set_sm_count(148)
+
+
+def _bn_case(lib, shape, relu, has_res):
     torch.manual_seed(0)
     N, C, H, W = shape
     pixels = N * H * W

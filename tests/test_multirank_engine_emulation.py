@@ -341,6 +341,8 @@ def emu(monkeypatch, request):
         # the extension module as built from csrc/bindings.cpp; its library also carries the emulator's own entry points
         _EXT = _cuda_emu.build_extension()
         lib = None if _EXT is None else _EXT.emu
+        if lib is not None:
+            lib.emu_set_sm_count(1)         # update grid = 3 CTAs: several tiles per CTA (grid-stride loops), as on big arenas
     else:
         _EXT, lib = None, _cuda_emu.build()
     if lib is None:

@@ -41,8 +41,18 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 12, 16), (1, 16, 6, 4), (2, 24, 8, 8), (1, 64, 7, 9), (2, 8, 5, 6), (1, 512, 2, 2)])
-def test_maxpool_launchers_match_torch(lib, shape):
+@pytest.fixture(params=[148, 1])
+def sms(lib, request):
+    """148 SMs, or ONE: then the launchers' grid caps (16 CTAs per SM) bind and every kernel walks its grid-stride loop several
+    times per CTA — what happens on the real ResNet-18 tensors."""
+    lib.emu_set_sm_count(request.param)
+    yield request.param
+    lib.emu_set_sm_count(148)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 12, 16), (1, 16, 6, 4), (2, 24, 8, 8), (1, 64, 7, 9), (2, 8, 5, 6), (1, 512, 2, 2),
+                                   (5, 64, 16, 8), (3, 8, 22, 40)])
+def test_maxpool_launchers_match_torch(lib, sms, shape):
     """Even H, W with 256 % (C/8) == 0 → the row / quad kernels; anything else → the general ones: same answer as ATen, ties
     included (the first maximum wins)."""
     N, C, H, W = shape
@@ -65,8 +75,8 @@ def test_maxpool_launchers_match_torch(lib, shape):
     assert torch.equal(dx.permute(0, 3, 1, 2).float(), xt.grad.bfloat16().float())
 
 
-def test_input_normalisers_match_torch(lib):
-    N, H, W = 2, 5, 7
+def test_input_normalisers_match_torch(lib, sms):
+    N, H, W = 3, 37, 41
     g = torch.Generator().manual_seed(0)
     x = torch.randint(0, 256, (N, 3, H, W), dtype=torch.uint8, generator=g)
     mean = torch.tensor([123.675, 116.28, 103.53])
@@ -81,7 +91,7 @@ def test_input_normalisers_match_torch(lib):
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 24), (1, 9, 10), (1, 32, 8)])
-def test_stem_im2col_matches_unfold(lib, shape):
+def test_stem_im2col_matches_unfold(lib, sms, shape):
     """The [N*OH*OW, 176] patch matrix of the 7x7 / stride-2 / pad-3 stem: per kernel row 7 x 3 = 21 values padded to 24, then 8
     zero columns — interior pixels take the aligned 4-byte-load path, border pixels the element-wise one."""
     N, H, W = shape
