@@ -124,9 +124,12 @@ def _run_bench(bench, extm, n, argv, monkeypatch, capsys):
         real = [e for e in errs if "another rank" not in str(e) and not isinstance(e, threading.BrokenBarrierError)]
         raise (real or errs)[0]
     assert rcs == [0] * n
-    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    cap = capsys.readouterr()
+    lines = [ln for ln in cap.out.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, lines                      # rank 0 prints ONE JSON line
-    return json.loads(lines[0])
+    out = json.loads(lines[0])
+    out["_stderr"] = cap.err
+    return out
 
 
 CONTRACT = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
@@ -175,6 +178,18 @@ def test_bench_other_configurations_at_two_ranks(bench_env, monkeypatch, capsys,
             assert cfg[k] == expect[k]
     if "--no-pipeline" in extra:
         assert cfg["update_pipeline_chunks"] == 1
+
+
+def test_bench_profile_flag_reports_device_spans(bench_env, monkeypatch, capsys):
+    """``--profile``: the engine's CUDA-event spans (``dev_step_tail_time``, ``dev_gather_update_bcast_time``,
+    ``dev_update_pipeline_time``: read one step late, never a sync) reach ``opt.timings`` and the per-rank stderr line."""
+    bench, extm = bench_env
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    out = _run_bench(bench, extm, 2, ["--steps", "2", "--warmup", "3", "--batch", "2", "--no-comparators", "--profile"], monkeypatch, capsys)
+    assert out["value"] > 0
+    spans = [ln for ln in out["_stderr"].splitlines() if ln.startswith("[rank ")]
+    assert len(spans) == 2 and all("dev_step_tail_time=" in ln for ln in spans), out["_stderr"][-500:]
+    assert any("dev_gather_update_bcast_time=" in ln and "dev_update_pipeline_time=" in ln for ln in spans)     # the server
 
 
 def test_bench_with_same_invocation_comparators(bench_env, monkeypatch, capsys):
