@@ -439,9 +439,22 @@ def pool_source(define_count_launch: bool = True) -> str:
     return SHIM_HEAD + _conversions() + "\n}  // namespace psb\n" + CUDA_RT_SHIM + RUNNER + _count_launch(define_count_launch) + body
 
 
+_TMP_DIRS = []
+
+
+def _scratch_dir(prefix: str) -> str:
+    """A per-process build directory, removed at interpreter exit (the loaded library stays mapped)."""
+    if not _TMP_DIRS:
+        import atexit
+        atexit.register(lambda: [shutil.rmtree(d, ignore_errors=True) for d in _TMP_DIRS])
+    d = tempfile.mkdtemp(prefix=prefix)
+    _TMP_DIRS.append(d)
+    return d
+
+
 def compile_shared(source: str, prefix: str):
     """g++ one emulated translation unit (+ its extern "C" driver) into a ctypes library."""
-    d = tempfile.mkdtemp(prefix=prefix)
+    d = _scratch_dir(prefix)
     open(os.path.join(d, "emu.cpp"), "w").write(source)
     p = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", CUDA_INC, "-I", KDIR,
                         "-o", os.path.join(d, "emu.so"), os.path.join(d, "emu.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
@@ -458,7 +471,7 @@ def build():
         return _LIB
     if shutil.which("g++") is None:
         return None
-    d = tempfile.mkdtemp(prefix="psb_emu_")
+    d = _scratch_dir("psb_emu_")
     open(os.path.join(d, "emu.cpp"), "w").write(kernel_source())
     cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I", CUDA_INC, "-I", KDIR, "-o", os.path.join(d, "emu.so"),
            os.path.join(d, "emu.cpp")]
