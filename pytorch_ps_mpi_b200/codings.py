@@ -111,6 +111,8 @@ class Coding:
 
     #: every rank's code for the parameter being decoded, set by the optimizer (``ps.py:165``)
     codes: Optional[List[Any]] = None
+    #: encode is a view / one elementwise pass: the host engine encodes small gradients inside the hook instead of on its pool
+    cheap: bool = False
 
     def encode(self, grad: torch.Tensor, **kwargs) -> Any:   # pragma: no cover - interface
         raise NotImplementedError
@@ -142,6 +144,8 @@ def _as_tensor(x) -> torch.Tensor:
 class Identity(Coding):
     """Send the gradient as it is (dtype preserved)."""
 
+    cheap = True
+
     def encode(self, grad, **kwargs):
         return {"grad": grad.detach()}
 
@@ -167,6 +171,8 @@ def _sat_cast(x: torch.Tensor, wire: int) -> torch.Tensor:
 
 class Cast(Coding):
     """Down-cast the gradient to a narrower float on the wire (bf16 / fp16 / fp8)."""
+
+    cheap = True
 
     def __init__(self, dtype="bf16"):
         self.wire = wire_code_of(dtype)
