@@ -1047,3 +1047,59 @@ def test_many_odd_shaped_parameters_groups_and_encode_batches(emu, monkeypatch, 
             for i, (g, q) in enumerate(zip(got, ref)):
                 assert torch.allclose(g, q.detach(), rtol=1e-5, atol=1e-6), (i, sizes[i] if i < 149 else "conv", float((g - q.detach()).abs().max()))
         assert len(enc) == steps                                           # one encode CALL per step; the binding splits it
+
+
+def test_lr_scheduler_retained_grads_and_two_optimizers_per_rank(emu):
+    """Everyday usage around the engine, 2 ranks: (a) a ``torch.optim.lr_scheduler`` drives the learning rate (sampled at the
+    first chunk of every step), (b) ``zero_grad(set_to_none=False)`` keeps ``.grad`` tensors alive between steps, (c) TWO
+    optimizers (two engines, two arenas, two flag pads) live in the same process and step alternately.  Each model must end on its
+    own single-process oracle."""
+    steps, n = 4, 2
+    hyper = dict(lr=0.08, momentum=0.9, weight_decay=1e-3)
+
+    def rank_main(rank, w):
+        models_, opts, scheds = [], [], []
+        for k in range(2):
+            m = _model()
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.mul_(1.0 + 0.5 * k)                               # two different models
+            o = ps.SGD(m.named_parameters(), m.parameters(), engine="host", mode="ps", **hyper)
+            _attach(o)
+            models_.append(m), opts.append(o), scheds.append(torch.optim.lr_scheduler.StepLR(o, step_size=2, gamma=0.5))
+        for s in range(steps):
+            for k in (0, 1):
+                opts[k].zero_grad(set_to_none=False)
+                _loss(models_[k], *_data(rank + 10 * k, s), skip_head=False).backward()
+                opts[k].step()
+                scheds[k].step()
+        for o in opts:
+            o._engine.check()
+        w.barrier()
+        out = [[p.detach().clone() for p in m.parameters()] for m in models_]
+        for o in opts:
+            o.close()
+        return out
+
+    res = run_ranks(emu, n, rank_main)
+    for k in range(2):
+        ref = _model()
+        with torch.no_grad():
+            for p in ref.parameters():
+                p.mul_(1.0 + 0.5 * k)
+        o = torch.optim.SGD(ref.parameters(), **hyper)
+        sch = torch.optim.lr_scheduler.StepLR(o, step_size=2, gamma=0.5)
+        for s in range(steps):
+            tot = None
+            for r in range(n):
+                ref.zero_grad(set_to_none=True)
+                _loss(ref, *_data(r + 10 * k, s), skip_head=False).backward()
+                gs = [p.grad.clone() for p in ref.parameters()]
+                tot = gs if tot is None else [a + b for a, b in zip(tot, gs)]
+            for p, g in zip(ref.parameters(), tot):
+                p.grad = g
+            o.step()
+            sch.step()
+        for rank_out in res:
+            for a, b in zip(rank_out[k], ref.parameters()):
+                assert torch.allclose(a, b.detach(), rtol=3e-5, atol=3e-6), (k, float((a - b.detach()).abs().max()))
