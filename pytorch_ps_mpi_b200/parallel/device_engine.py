@@ -92,6 +92,7 @@ class DeviceEngine:
             and self.mode in ("ps", "allgather")
         L = self.layout
         nt, n_pad = L.ntiles, L.numel_padded
+        self._check_same_layout_everywhere()
 
         # ---- symmetric block: [signal pad | scales | wire arena | parameter arena] ----
         self.off_signal = 0
@@ -284,6 +285,28 @@ class DeviceEngine:
         self._err_event = None
         self._err_every = max(1, int(os.environ.get("PSB200_ERROR_POLL", "16")))
         self.world.barrier()
+
+    def _check_same_layout_everywhere(self):
+        """Every rank must describe the SAME flat arena (the kernels address peers' arenas by tile number): compare a fingerprint
+        of mode / optimizer / dtype / wire format / parameter names and shapes across ranks and fail on all of them with the first
+        difference.  The reference silently assumes identical models on every rank; a mismatch there hangs or corrupts."""
+        if self.size == 1 or os.environ.get("PSB200_CHECK_LAYOUT", "1") == "0":
+            return
+        L = self.layout
+        mine = (self.mode, self.opt.optim, str(self.dtype), int(self.kind), int(self.wire), int(self.bpt), L.nparams, L.ntiles,
+                tuple((s.name, tuple(s.param.shape)) for s in L.slots))
+        every = self.world.all_gather_object(mine)
+        for r, other in enumerate(every):
+            if other != every[0]:
+                what = ["mode", "optimizer", "parameter dtype", "coding kind", "wire dtype", "bytes per tile", "number of parameters",
+                        "number of tiles", "parameter names / shapes"]
+                k = next(i for i in range(len(mine)) if other[i] != every[0][i])
+                detail = ""
+                if k == 8:
+                    diff = [(a, b) for a, b in zip(every[0][8], other[8]) if a != b][:1]
+                    detail = f": first difference {diff[0] if diff else (len(every[0][8]), len(other[8]))}"
+                raise ValueError(f"rank {r} and rank 0 disagree on the {what[k]} ({other[k] if k < 8 else '...'} vs "
+                                 f"{every[0][k] if k < 8 else '...'}){detail} — every rank must build the same model, coding and mode")
 
     def _make_chunks(self):
         """Static chunks of the update pipeline (identical on every rank: they depend on the layout only).

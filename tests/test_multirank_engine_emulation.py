@@ -1103,3 +1103,21 @@ def test_lr_scheduler_retained_grads_and_two_optimizers_per_rank(emu):
         for rank_out in res:
             for a, b in zip(rank_out[k], ref.parameters()):
                 assert torch.allclose(a, b.detach(), rtol=3e-5, atol=3e-6), (k, float((a - b.detach()).abs().max()))
+
+
+def test_mismatched_models_fail_loudly_on_every_rank(emu):
+    """The kernels address peers' arenas by tile number, so ranks that built different models (or codings / modes) must not get as
+    far as allocating symmetric memory: every rank raises, naming the first difference."""
+    def rank_main(rank, w):
+        model = _model()
+        if rank == 1:
+            model[4] = torch.nn.Linear(24, 11)                            # a different head on rank 1
+        opt = ps.SGD(model.named_parameters(), model.parameters(), engine="host", mode="ps", lr=0.1)
+        try:
+            _attach(opt)
+        except ValueError as exc:
+            return str(exc)
+        return None
+
+    res = run_ranks(emu, 2, rank_main)
+    assert all(r is not None and "rank 1 and rank 0 disagree" in r and "4.bias" in r and "(11,)" in r for r in res), res
