@@ -95,6 +95,26 @@ def p2p_any_source(rank, size, transport):
     comms.barrier()
 
 
+def three_rank_suite(rank, size, transport):
+    """Three ranks, one set of processes: (shm only) the synchronous PS oracle run, then ``average=True`` with several parameter
+    groups, then AsySG-InCon — in that order (the async protocol's goodbye messages come last)."""
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    if transport == "shm":
+        _mlp_train_body(ps, w, rank, size, "ps", "sgd", "identity")
+        w.barrier()
+    mlp_average_and_groups(rank, size, transport)
+    w.barrier()
+    mlp_async(rank, size, transport)
+
+
+def comm_suite(rank, size, transport, names):
+    """Several of the comm scenarios above in ONE set of processes (a spawn costs far more than the scenarios; and the façade
+    must survive being used for one pattern after another: tags, pending requests, ring state)."""
+    for name in names:
+        globals()[name](rank, size, transport)
+
+
 # --- BASELINE config 1: 2-layer MLP, MNIST-shaped synthetic, world_size 2 -------------------
 def _mlp_data(rank, step, batch=16):
     g = torch.Generator().manual_seed(1000 * step + rank)
@@ -125,6 +145,21 @@ def _oracle_sum_sgd(size, steps, optim, hyper, coding_factory):
 def mlp_train(rank, size, mode, optim, coding, transport, coalesce=False):
     os.environ["PSB200_TRANSPORT"] = transport
     ps, w = _world(rank, size)
+    _mlp_train_body(ps, w, rank, size, mode, optim, coding, coalesce)
+
+
+def mlp_train_many(rank, size, transport, cases):
+    """Several (mode, optim, coding, coalesce) scenarios in ONE set of processes: a spawn costs ~10 s of interpreter start-up and
+    ``import torch`` per rank, the scenarios themselves a fraction of a second — and optimizers following each other in one
+    process is itself a scenario (transport tags, pools and hooks of a closed optimizer must not leak into the next)."""
+    os.environ["PSB200_TRANSPORT"] = transport
+    ps, w = _world(rank, size)
+    for mode, optim, coding, coalesce in cases:
+        _mlp_train_body(ps, w, rank, size, mode, optim, coding, coalesce)
+        w.barrier()
+
+
+def _mlp_train_body(ps, w, rank, size, mode, optim, coding, coalesce=False):
     from pytorch_ps_mpi_b200.models import mnist_mlp
     factory = {"identity": ps.Identity, "cast": lambda: ps.Cast("bf16"), "scale": lambda: ps.Scale("int8"),
                "topk": lambda: ps.TopK(ratio=0.25), "svd": lambda: ps.SVD(rank=2)}[coding]

@@ -15,23 +15,11 @@ TRANSPORTS = ["shm", "gloo"]
 
 @pytest.mark.parametrize("transport", TRANSPORTS)
 @pytest.mark.parametrize("n", [2, 3])
-def test_gather(transport, n):
-    spawn(_mp.gather_objects, n, (transport,))
-
-
-@pytest.mark.parametrize("transport", TRANSPORTS)
-def test_bcast(transport):
-    spawn(_mp.bcast_objects, 2, (transport,))
-
-
-@pytest.mark.parametrize("transport", TRANSPORTS)
-def test_iallgather(transport):
-    spawn(_mp.iallgather_objects, 3, (transport,))
-
-
-@pytest.mark.parametrize("transport", TRANSPORTS)
-def test_any_source(transport):
-    spawn(_mp.p2p_any_source, 3, (transport,))
+def test_gather_bcast_iallgather_any_source(transport, n):
+    """The reference's three test files re-created (``test_comms.py:9-26``, ``test_iallgather.py:37-54``, ``test_mpi.py:34-96``)
+    + any-source point-to-point, at 2 and 3 ranks over both transports — one set of processes per (transport, n)."""
+    names = ["gather_objects", "bcast_objects"] + (["iallgather_objects", "p2p_any_source"] if n == 3 else [])
+    spawn(_mp.comm_suite, n, (transport, names), timeout=240)
 
 
 def test_single_process_world():

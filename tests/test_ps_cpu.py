@@ -9,32 +9,25 @@ from pytorch_ps_mpi_b200.launch import spawn
 from tests import _mp
 
 
-@pytest.mark.parametrize("mode,optim,coding,transport", [
-    ("ps", "sgd", "identity", "shm"),
-    ("ps", "adam", "cast", "shm"),
-    ("ps", "sgd", "topk", "gloo"),
-    ("allgather", "sgd", "identity", "shm"),
-    ("allgather", "adam", "scale", "gloo"),
-    ("allgather", "sgd", "topk", "shm"),
-    ("ps", "sgd", "svd", "shm"),          # a host-path-only (user-style) coding through the generic wire format
-])
-def test_mlp_sync(mode, optim, coding, transport):
-    spawn(_mp.mlp_train, 2, (mode, optim, coding, transport))
-
-
-@pytest.mark.parametrize("mode", ["ps", "allgather"])
-def test_mlp_sync_coalesced(mode):
-    """coalesce=True: one message per step instead of one collective per parameter — same numerics."""
-    spawn(_mp.mlp_train, 2, (mode, "sgd", "cast", "shm", True))
-
-
-def test_mlp_sync_three_ranks():
-    spawn(_mp.mlp_train, 3, ("ps", "sgd", "identity", "shm"))
+SYNC_CASES = {          # (mode, optim, coding, coalesce)
+    "shm": [("ps", "sgd", "identity", False), ("ps", "adam", "cast", False), ("allgather", "sgd", "identity", False),
+            ("allgather", "sgd", "topk", False),
+            ("ps", "sgd", "svd", False),          # a host-path-only (user-style) coding through the generic wire format
+            ("ps", "sgd", "cast", True), ("allgather", "sgd", "cast", True)],     # one framed message per step (coalesce=True)
+    "gloo": [("ps", "sgd", "topk", False), ("allgather", "adam", "scale", False)],
+}
 
 
 @pytest.mark.parametrize("transport", ["shm", "gloo"])
-def test_mlp_async(transport):
-    spawn(_mp.mlp_async, 3, (transport,))
+def test_mlp_sync(transport):
+    """Every scenario of a transport runs in one pair of processes (see ``_mp.mlp_train_many``)."""
+    spawn(_mp.mlp_train_many, 2, (transport, SYNC_CASES[transport]), timeout=300)
+
+
+@pytest.mark.parametrize("transport", ["shm", "gloo"])
+def test_three_ranks_sync_average_groups_async(transport):
+    """3 ranks: sync PS vs the oracle (shm), ``average=True`` + several param groups, AsySG-InCon with quota 1 (both transports)."""
+    spawn(_mp.three_rank_suite, 3, (transport,), timeout=300)
 
 
 def test_shm_transport_detects_dead_peer():
@@ -42,11 +35,6 @@ def test_shm_transport_detects_dead_peer():
     import multiprocessing
     # rank 1 exits with os._exit(0) on purpose; rank 0 must notice instead of hanging
     _spawn(_mp.shm_dead_peer, 2, timeout=90)
-
-
-@pytest.mark.parametrize("transport", ["shm", "gloo"])
-def test_average_and_param_groups(transport):
-    spawn(_mp.mlp_average_and_groups, 3, (transport,))
 
 
 def test_async_consistent_reads():
